@@ -1,0 +1,197 @@
+/*
+ * mashgpu.h -- C ABI of the B200-native MinHash engine (libmashgpu.so, sm_100a).
+ *
+ * This is the drop-in boundary for the three data-parallel hot paths of marbl/Mash.  The reference has
+ * no FFI; its seams are the ThreadPool worker functions and the pure-compute functions underneath them
+ * (paths below are relative to the reference's src/mash/):
+ *
+ *   mashgpu_sketch_batch      replaces  sketchFile / sketchSequence      Sketch.cpp:1147-1365 (Sketch.h:229-234)
+ *                                       addMinHashes                     Sketch.cpp:512-583   (Sketch.h:226)
+ *                                       getHash                          hash.cpp:10-38       (hash.h:21)
+ *                                       MinHashHeap::tryInsert/toHashList MinHashHeap.cpp:68-146, HashSet.cpp:78-118
+ *   mashgpu_dist_*            replaces  compare / compareSketches / pValue CommandDistance.cpp:306-448 (CommandDistance.h:91-93)
+ *   mashgpu_screen_*          replaces  hashSequence + the shared/median/identity/p-value reduce
+ *                                       CommandScreen.cpp:93-114, 484-599, 288-355, 409-455, 463-482, 601-615
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer; every function returns an int
+ * status (0 = MASHGPU_OK), never throws and never calls exit() (the reference prints to cerr and exit(1)s,
+ * Sketch.cpp:1294-1312 -- the host shim maps statuses back to those messages); a context is bound to one
+ * CUDA device and must not be used from two threads at once.  Hashes are always carried as uint64_t, 32-bit
+ * hashes (use64 == 0) zero-extended, exactly as HashList stores hash_u (HashList.h:13-37, hash.h:15-19).
+ * Unlike addMinHashes (Sketch.cpp:524-530) the sequence buffers are NOT modified.
+ *
+ * There is no CPU fallback: without a CUDA device mashgpu_create fails.
+ */
+#ifndef MASHGPU_H
+#define MASHGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MASHGPU_OK 0
+#define MASHGPU_ERR_INVALID 1      /* bad argument */
+#define MASHGPU_ERR_CUDA 2         /* CUDA runtime error (message in mashgpu_last_error) */
+#define MASHGPU_ERR_UNSUPPORTED 3  /* parameter combination outside the GPU path (see mashgpu_sketch_params) */
+#define MASHGPU_ERR_NOMEM 4
+
+typedef struct mashgpu_ctx mashgpu_ctx;
+
+/* Sketch::Parameters (Sketch.h:34-109), the fields the hot path reads. */
+typedef struct mashgpu_sketch_params {
+    int32_t kmer_size;        /* kmerSize, 1..32 (Command.cpp:168) */
+    uint32_t sketch_size;     /* minHashesPerWindow (s) */
+    uint32_t seed;            /* hash seed (default 42) */
+    int32_t use64;            /* alphabetSize^k > 2^32 (Sketch.cpp:1136); filled by mashgpu_set_alphabet */
+    int32_t noncanonical;
+    int32_t preserve_case;
+    uint8_t alphabet[256];    /* Parameters::alphabet; filled by mashgpu_set_alphabet */
+} mashgpu_sketch_params;
+/* GPU path coverage: alphabet == {A,C,G,T} (canonical or not, any k 1..32, either case mode) runs the 4-bit
+ * packed DNA kernels; any other alphabet requires noncanonical != 0 (the protein setting of the reference,
+ * sketchParameterSetup.cpp) and runs the byte-alphabet kernels.  Other combinations return
+ * MASHGPU_ERR_UNSUPPORTED (never a CPU fallback). */
+
+/* setAlphabetFromString (Sketch.cpp:1108-1137): fills alphabet[] and use64 from kmer_size/preserve_case.
+ * Returns the alphabet size. */
+uint32_t mashgpu_set_alphabet(mashgpu_sketch_params *p, const char *characters);
+
+int mashgpu_device_count(void);
+int mashgpu_create(int device, mashgpu_ctx **ctx);
+void mashgpu_destroy(mashgpu_ctx *ctx);
+/* Message of the last failure on this context (ctx == NULL: of the last failed mashgpu_create). */
+const char *mashgpu_last_error(const mashgpu_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Hot path 1: sketching.
+ *
+ * n_records pre-parsed records (what kseq_read delivers: sequence bytes, kseq.h:170-208) are grouped into
+ * n_units sketch units: unit_of_record[r] (non-decreasing; NULL = record r is unit r).  A unit is one
+ * sketchFile job (all records of the listed files, k-mers never span records) or one sketchSequence job.
+ * Records shorter than kmer_size are skipped and not counted in the length (Sketch.cpp:1222-1226,1251-1254).
+ *
+ * Outputs, per unit u, in input order (ThreadPool ordering contract, ThreadPool.hxx:87-118):
+ *   out_hashes[u*sketch_size .. +out_n[u])  the min(s, #distinct) smallest distinct hashes, ascending
+ *   out_counts (nullable)                    multiplicity of each hash (HashSet counts)
+ *   out_n[u]                                 number of hashes
+ *   out_length[u]                            sum of the kept records' lengths (Reference::length, non -r mode)
+ * ------------------------------------------------------------------------------------------------------- */
+int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                         uint64_t n_records, const char *const *seq, const uint64_t *len,
+                         const uint32_t *unit_of_record, uint64_t n_units,
+                         uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_length);
+
+/* Same computation on a sequence stream already resident in device memory.  d_stream holds the units back to
+ * back; unit u occupies bytes [unit_start[u], unit_start[u+1]) (host array of n_units+1 offsets); records inside
+ * a unit are separated by at least one byte outside the alphabet (e.g. 0).  d_stream must be readable up to
+ * unit_start[n_units] rounded up to 16 bytes.  d_out_* are device pointers (d_out_counts nullable).
+ * `stream` is a cudaStream_t (NULL = the context's stream); the call returns after enqueueing unless a unit
+ * needs the exact re-run (then it synchronises the stream). */
+int mashgpu_sketch_stream_dev(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                              const void *d_stream, const uint64_t *unit_start, uint64_t n_units,
+                              uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, void *stream);
+
+/* getHash over every window (hash.cpp:10-38 applied as in Sketch.cpp:540-576): out_hash[i]/out_valid[i] for each
+ * window start i in [0, len-k]; invalid windows (a byte outside the alphabet) have out_valid[i] == 0.
+ * Host buffers.  Diagnostic/test entry point of the scan+hash kernel. */
+int mashgpu_hash_windows(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                         const char *seq, uint64_t len, uint64_t *out_hash, uint8_t *out_valid);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Hot path 2: all-pairs sketch comparison.
+ * ------------------------------------------------------------------------------------------------------- */
+/* A Sketch's reference list (Sketch.h:131-139): n rows of `stride` uint64 slots; row i holds n_hashes[i]
+ * ascending distinct hashes (Reference::hashesSorted) and has sequence length length[i] (Reference::length).
+ * on_device != 0: hashes/n_hashes/length are device pointers. */
+typedef struct mashgpu_sketch_set {
+    uint64_t n;
+    uint64_t stride;
+    const uint64_t *hashes;
+    const uint32_t *n_hashes;
+    const uint64_t *length;
+    int32_t on_device;
+} mashgpu_sketch_set;
+
+/* Arguments of compareSketches (CommandDistance.h:92). */
+typedef struct mashgpu_dist_params {
+    uint64_t sketch_size;   /* min(s_query, s_ref)  (CommandDistance.cpp:313-315) */
+    int32_t kmer_size;
+    double kmer_space;      /* alphabetSize^k as double (Sketch.cpp:509) */
+    double max_distance;    /* -d, < 0 disables (CommandDistance.cpp:409) */
+    double max_pvalue;      /* -v, < 0 disables (CommandDistance.cpp:419) */
+} mashgpu_dist_params;
+
+typedef struct mashgpu_dist_job mashgpu_dist_job;
+
+/* Uploads both sets (qry == NULL or qry == ref: all-vs-all of one set), builds the order-preserving 32-bit
+ * dictionary of all hashes and keeps everything resident. */
+int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
+                      const mashgpu_dist_params *params, mashgpu_dist_job **job);
+
+/* Compares queries [q_begin, q_begin+q_count) with every reference: pair (q, r) is written at index
+ * (q - q_begin) * n_ref + r, the reference's query-major order (CommandDistance.cpp:213-232, 306-334).
+ * Per pair (PairOutput, CommandDistance.h:63-70): numer (shared hashes), denom, distance, pvalue, pass.
+ * Where the reference leaves numer/denom/distance/pValue unset (distance > max_distance, :409-412) this
+ * engine still writes the computed numer/denom/distance and pvalue = 0, with pass = 0.
+ * Any output pointer may be NULL.  Host buffers. */
+int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
+                     uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint8_t *pass);
+/* Same with device output buffers, enqueued on `stream` (cudaStream_t, NULL = context stream). */
+int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
+                         uint32_t *d_numer, uint32_t *d_denom, double *d_distance, double *d_pvalue, uint8_t *d_pass,
+                         void *stream);
+int mashgpu_dist_close(mashgpu_dist_job *job);
+
+/* One-shot convenience: open + run over all queries + close (the whole `compare` grid). */
+int mashgpu_dist(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
+                 const mashgpu_dist_params *params,
+                 uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint8_t *pass);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Hot path 3: screen (containment of reference sketches in a read stream).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mashgpu_screen_job mashgpu_screen_job;
+
+/* Builds the distinct-hash table of the reference sketches with zeroed counters (CommandScreen.cpp:93-114). */
+int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params *params, const mashgpu_sketch_set *refs,
+                        mashgpu_screen_job **job);
+/* One HashInput (CommandScreen.h:104-133): a '*'-joined chunk of reads (CommandScreen.cpp:224-262; any byte
+ * outside the alphabet separates reads).  Host buffer; chunks may be of any size. */
+int mashgpu_screen_feed(mashgpu_screen_job *job, const char *chunk, uint64_t len);
+/* Same for a chunk already in device memory (readable up to len rounded up to 16). */
+int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64_t len);
+/* Reduce (CommandScreen.cpp:288-355, 409-455): per reference sketch i the number of its hashes seen at least
+ * once (shared), the median multiplicity depths[shared/2], identity (estimateIdentity, :463-482) and p-value
+ * (pValueWithin, :601-615); *set_size = (uint64_t)estimateSetSize() of the mixture's bottom-s heap (:322).
+ * mixture_hashes (nullable, sketch_size slots) / mixture_n receive that bottom-s list.  Host buffers. */
+int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, uint64_t *median, double *identity,
+                          double *pvalue, uint64_t *set_size, uint64_t *mixture_hashes, uint32_t *mixture_n);
+int mashgpu_screen_close(mashgpu_screen_job *job);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Instrumentation (bench.py): kernel launch counter and device time of the dominant kernels.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mashgpu_stats {
+    uint64_t kernel_launches;      /* kernels launched by this context since the last reset */
+    double scan_kernel_ms;         /* accumulated device time of the sketch/screen scan kernel (CUDA events) */
+    uint64_t scan_kernel_launches;
+    double dist_kernel_ms;         /* accumulated device time of the merge kernel */
+    uint64_t dist_kernel_launches;
+    uint64_t exact_reruns;         /* units that needed the exact re-run path */
+} mashgpu_stats;
+/* timing != 0 brackets the dominant kernels with CUDA events (adds a sync at mashgpu_get_stats). */
+int mashgpu_set_timing(mashgpu_ctx *ctx, int timing);
+int mashgpu_get_stats(mashgpu_ctx *ctx, mashgpu_stats *out, int reset);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASHGPU_H */

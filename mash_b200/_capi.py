@@ -1,0 +1,294 @@
+"""ctypes mirror of include/mashgpu.h.
+
+Names follow the reference's seams: Engine.sketch ~ sketchFile/sketchSequence jobs (Sketch.cpp:1147-1365),
+Engine.dist ~ compare/compareSketches (CommandDistance.cpp:306-448), Engine.screen_* ~ hashSequence + reduce
+(CommandScreen.cpp:484-599, 288-455).  Every call goes through libmashgpu.so; nothing here computes hashes,
+merges or p-values on the host.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ALPHABET_NUCLEOTIDE = "ACGT"                 # reference Sketch.h:25
+ALPHABET_PROTEIN = "ACDEFGHIKLMNPQRSTVWY"    # reference Sketch.h:26
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+u8p = C.POINTER(C.c_uint8)
+f64p = C.POINTER(C.c_double)
+
+
+class MashGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mashgpu error {code}: {msg}")
+        self.code = code
+
+
+class SketchParams(C.Structure):
+    """mashgpu_sketch_params (Sketch::Parameters subset, reference Sketch.h:34-109)."""
+    _fields_ = [("kmer_size", C.c_int32), ("sketch_size", C.c_uint32), ("seed", C.c_uint32),
+                ("use64", C.c_int32), ("noncanonical", C.c_int32), ("preserve_case", C.c_int32),
+                ("alphabet", C.c_uint8 * 256)]
+
+    @property
+    def kmer_space(self):
+        return float(sum(1 for a in self.alphabet if a)) ** self.kmer_size   # Sketch.cpp:509
+
+
+class DistParams(C.Structure):
+    """mashgpu_dist_params (arguments of compareSketches, reference CommandDistance.h:92)."""
+    _fields_ = [("sketch_size", C.c_uint64), ("kmer_size", C.c_int32), ("kmer_space", C.c_double),
+                ("max_distance", C.c_double), ("max_pvalue", C.c_double)]
+
+
+class SketchSet(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("stride", C.c_uint64), ("hashes", C.c_void_p),
+                ("n_hashes", C.c_void_p), ("length", C.c_void_p), ("on_device", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("scan_kernel_ms", C.c_double), ("scan_kernel_launches", C.c_uint64),
+                ("dist_kernel_ms", C.c_double), ("dist_kernel_launches", C.c_uint64), ("exact_reruns", C.c_uint64)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libmashgpu.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmashgpu.so (built in-tree by __graft_entry__.build()). No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build the CUDA extension first "
+                          "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    L = C.CDLL(path)
+    L.mashgpu_set_alphabet.restype = C.c_uint32
+    L.mashgpu_set_alphabet.argtypes = [C.POINTER(SketchParams), C.c_char_p]
+    L.mashgpu_device_count.restype = C.c_int
+    L.mashgpu_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.mashgpu_destroy.argtypes = [C.c_void_p]
+    L.mashgpu_destroy.restype = None
+    L.mashgpu_last_error.restype = C.c_char_p
+    L.mashgpu_last_error.argtypes = [C.c_void_p]
+    L.mashgpu_sketch_batch.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_uint64, C.c_void_p, u64p, u32p, C.c_uint64,
+                                       u64p, u32p, u32p, u64p]
+    L.mashgpu_sketch_stream_dev.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, u64p, C.c_uint64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_hash_windows.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, C.c_uint64, u64p, u8p]
+    L.mashgpu_dist_open.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), C.POINTER(C.c_void_p)]
+    L.mashgpu_dist_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u32p, u32p, f64p, f64p, u8p]
+    L.mashgpu_dist_run_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_dist_close.argtypes = [C.c_void_p]
+    L.mashgpu_dist.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), u32p, u32p, f64p, f64p, u8p]
+    L.mashgpu_screen_open.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.POINTER(SketchSet), C.POINTER(C.c_void_p)]
+    L.mashgpu_screen_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.mashgpu_screen_feed_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.mashgpu_screen_finish.argtypes = [C.c_void_p, u64p, u64p, f64p, f64p, u64p, u64p, u32p]
+    L.mashgpu_screen_close.argtypes = [C.c_void_p]
+    L.mashgpu_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.mashgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def _as_u8(s):
+    if isinstance(s, (bytes, bytearray, memoryview)):
+        return np.frombuffer(s, dtype=np.uint8)
+    return np.ascontiguousarray(s, dtype=np.uint8)
+
+
+class _Set:
+    """Keeps the numpy arrays behind a mashgpu_sketch_set alive."""
+
+    def __init__(self, hashes, n_hashes, length=None, on_device=False, n=None, stride=None):
+        if on_device:
+            self.c = SketchSet(n, stride, hashes, n_hashes, length, 1)
+            return
+        self.h = np.ascontiguousarray(hashes, np.uint64)
+        if self.h.ndim != 2:
+            raise ValueError("hashes must be (n, stride)")
+        self.n = np.ascontiguousarray(n_hashes, np.uint32)
+        self.l = np.ascontiguousarray(length if length is not None else np.ones(self.h.shape[0]), np.uint64)
+        self.c = SketchSet(self.h.shape[0], self.h.shape[1], self.h.ctypes.data, self.n.ctypes.data, self.l.ctypes.data, 0)
+
+
+class Engine:
+    """One mashgpu context (one CUDA device)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.mashgpu_create(device, C.byref(h))
+        if rc != 0:
+            raise MashGpuError(rc, (self.lib.mashgpu_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mashgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MashGpuError(rc, (self.lib.mashgpu_last_error(self.h) or b"").decode())
+
+    # ---- parameters (sketchParameterSetup / setAlphabetFromString) --------------------------------------
+    def params(self, k=21, s=1000, seed=42, alphabet=ALPHABET_NUCLEOTIDE, noncanonical=False, preserve_case=False):
+        p = SketchParams()
+        p.kmer_size = k
+        p.sketch_size = s
+        p.seed = seed
+        p.noncanonical = int(noncanonical)
+        p.preserve_case = int(preserve_case)
+        self.lib.mashgpu_set_alphabet(C.byref(p), alphabet.encode())
+        return p
+
+    # ---- hot path 1 ----------------------------------------------------------------------------------------
+    def sketch(self, records, p, unit_of_record=None, n_units=None, counts=False):
+        """records: list of byte strings / uint8 arrays.  Returns (hashes (n_units, s) u64, n u32, length u64[, counts])."""
+        bufs = [_as_u8(r) for r in records]
+        ptrs = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data if b.size else None for b in bufs])
+        lens = np.array([b.size for b in bufs], dtype=np.uint64)
+        if unit_of_record is None:
+            n_units = len(bufs)
+            uor = None
+        else:
+            uor = np.ascontiguousarray(unit_of_record, np.uint32)
+            if n_units is None:
+                n_units = int(uor.max()) + 1 if uor.size else 0
+        s = p.sketch_size
+        out = np.zeros((n_units, s), np.uint64)
+        out_n = np.zeros(n_units, np.uint32)
+        out_len = np.zeros(n_units, np.uint64)
+        out_c = np.zeros((n_units, s), np.uint32) if counts else None
+        self._check(self.lib.mashgpu_sketch_batch(self.h, C.byref(p), len(bufs), C.cast(ptrs, C.c_void_p), _p(lens, u64p),
+                                                  _p(uor, u32p), n_units, _p(out, u64p), _p(out_c, u32p), _p(out_n, u32p), _p(out_len, u64p)))
+        return (out, out_n, out_len, out_c) if counts else (out, out_n, out_len)
+
+    def sketch_stream_dev(self, p, d_stream_ptr, unit_start, d_out_hashes, d_out_n, d_out_counts=None, stream=None):
+        us = np.ascontiguousarray(unit_start, np.uint64)
+        self._check(self.lib.mashgpu_sketch_stream_dev(self.h, C.byref(p), d_stream_ptr, _p(us, u64p), us.size - 1,
+                                                       d_out_hashes, d_out_counts, d_out_n, stream))
+
+    def hash_windows(self, seq, p):
+        b = _as_u8(seq)
+        n = max(0, b.size - p.kmer_size + 1)
+        h = np.zeros(max(1, n), np.uint64)
+        v = np.zeros(max(1, n), np.uint8)
+        self._check(self.lib.mashgpu_hash_windows(self.h, C.byref(p), b.ctypes.data, b.size, _p(h, u64p), _p(v, u8p)))
+        return h[:n], v[:n].astype(bool)
+
+    # ---- hot path 2 ----------------------------------------------------------------------------------------
+    def dist(self, ref, ref_n, ref_len, qry=None, qry_n=None, qry_len=None, *, sketch_size, k, kmer_space,
+             max_distance=1.0, max_pvalue=1.0):
+        """All pairs, query-major.  Returns a dict of (n_qry, n_ref) arrays: numer, denom, distance, pvalue, pass."""
+        job = self.dist_open(ref, ref_n, ref_len, qry, qry_n, qry_len, sketch_size=sketch_size, k=k, kmer_space=kmer_space,
+                             max_distance=max_distance, max_pvalue=max_pvalue)
+        try:
+            return job.run(0, job.n_qry)
+        finally:
+            job.close()
+
+    def dist_open(self, ref, ref_n, ref_len, qry=None, qry_n=None, qry_len=None, *, sketch_size, k, kmer_space,
+                  max_distance=1.0, max_pvalue=1.0):
+        return DistJob(self, ref, ref_n, ref_len, qry, qry_n, qry_len, sketch_size, k, kmer_space, max_distance, max_pvalue)
+
+    # ---- hot path 3 ----------------------------------------------------------------------------------------
+    def screen_open(self, ref, ref_n, p):
+        return ScreenJob(self, ref, ref_n, p)
+
+    # ---- instrumentation -----------------------------------------------------------------------------------
+    def set_timing(self, on=True):
+        self._check(self.lib.mashgpu_set_timing(self.h, int(on)))
+
+    def stats(self, reset=False):
+        st = Stats()
+        self._check(self.lib.mashgpu_get_stats(self.h, C.byref(st), int(reset)))
+        return {f: getattr(st, f) for f, _ in Stats._fields_}
+
+
+class DistJob:
+    def __init__(self, eng, ref, ref_n, ref_len, qry, qry_n, qry_len, sketch_size, k, kmer_space, max_distance, max_pvalue):
+        self.eng = eng
+        if isinstance(ref, _Set):
+            self._ref = ref
+            self._qry = qry
+        else:
+            self._ref = _Set(ref, ref_n, ref_len)
+            self._qry = None if qry is None else _Set(qry, qry_n, qry_len)
+        self.n_ref = int(self._ref.c.n)
+        self.n_qry = self.n_ref if self._qry is None else int(self._qry.c.n)
+        self.params = DistParams(sketch_size, k, kmer_space, max_distance, max_pvalue)
+        h = C.c_void_p()
+        eng._check(eng.lib.mashgpu_dist_open(eng.h, C.byref(self._ref.c), C.byref(self._qry.c) if self._qry is not None else None,
+                                             C.byref(self.params), C.byref(h)))
+        self.h = h
+
+    def run(self, q_begin, q_count):
+        n = q_count * self.n_ref
+        numer = np.zeros(n, np.uint32); denom = np.zeros(n, np.uint32)
+        dist = np.zeros(n, np.float64); pv = np.zeros(n, np.float64); ok = np.zeros(n, np.uint8)
+        self.eng._check(self.eng.lib.mashgpu_dist_run(self.h, q_begin, q_count, _p(numer, u32p), _p(denom, u32p), _p(dist, f64p), _p(pv, f64p), _p(ok, u8p)))
+        shp = (q_count, self.n_ref)
+        return {"numer": numer.reshape(shp), "denom": denom.reshape(shp), "distance": dist.reshape(shp),
+                "pvalue": pv.reshape(shp), "pass": ok.reshape(shp).astype(bool)}
+
+    def run_dev(self, q_begin, q_count, d_numer=None, d_denom=None, d_distance=None, d_pvalue=None, d_pass=None, stream=None):
+        self.eng._check(self.eng.lib.mashgpu_dist_run_dev(self.h, q_begin, q_count, d_numer, d_denom, d_distance, d_pvalue, d_pass, stream))
+
+    def close(self):
+        if self.h:
+            self.eng.lib.mashgpu_dist_close(self.h)
+            self.h = None
+
+
+class ScreenJob:
+    def __init__(self, eng, ref, ref_n, p):
+        self.eng = eng
+        self._ref = ref if isinstance(ref, _Set) else _Set(ref, ref_n)
+        self.n_ref = int(self._ref.c.n)
+        self.p = p
+        h = C.c_void_p()
+        eng._check(eng.lib.mashgpu_screen_open(eng.h, C.byref(p), C.byref(self._ref.c), C.byref(h)))
+        self.h = h
+
+    def feed(self, chunk):
+        b = _as_u8(chunk)
+        self.eng._check(self.eng.lib.mashgpu_screen_feed(self.h, b.ctypes.data, b.size))
+
+    def feed_dev(self, d_ptr, length):
+        self.eng._check(self.eng.lib.mashgpu_screen_feed_dev(self.h, d_ptr, length))
+
+    def finish(self):
+        n, s = self.n_ref, self.p.sketch_size
+        shared = np.zeros(n, np.uint64); median = np.zeros(n, np.uint64)
+        ident = np.zeros(n, np.float64); pv = np.zeros(n, np.float64)
+        set_size = C.c_uint64(0); mix = np.zeros(s, np.uint64); mix_n = C.c_uint32(0)
+        self.eng._check(self.eng.lib.mashgpu_screen_finish(self.h, _p(shared, u64p), _p(median, u64p), _p(ident, f64p), _p(pv, f64p),
+                                                           C.byref(set_size), _p(mix, u64p), C.byref(mix_n)))
+        return dict(shared=shared, median=median, identity=ident, pvalue=pv, set_size=set_size.value, mixture=mix[:mix_n.value].copy())
+
+    def close(self):
+        if self.h:
+            self.eng.lib.mashgpu_screen_close(self.h)
+            self.h = None

@@ -1,0 +1,120 @@
+// common.cuh -- context, error handling and small device-buffer helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <utility>
+
+#include "../../include/mashgpu.h"
+
+namespace mashgpu {
+
+struct EventPair { cudaEvent_t a, b; };
+
+}  // namespace mashgpu
+
+struct mashgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D staging
+    std::string err;
+    // instrumentation
+    bool timing = false;
+    uint64_t kernel_launches = 0;
+    uint64_t scan_launches = 0, dist_launches = 0, exact_reruns = 0;
+    double scan_ms = 0, dist_ms = 0;
+    std::vector<mashgpu::EventPair> scan_events, dist_events;
+};
+
+namespace mashgpu {
+
+inline int fail(mashgpu_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define MG_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return mashgpu::fail((ctx), MASHGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call,           \
+                                 cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define MG_TRY(expr)                      \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ != MASHGPU_OK) return rc__; \
+    } while (0)
+
+// RAII device buffer (freed on scope exit)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() { release(); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMallocHost((void **)&p, count * sizeof(T));
+    }
+};
+
+inline uint32_t ceil_log2(uint64_t x)
+{
+    uint32_t l = 0;
+    while ((1ull << l) < x) l++;
+    return l;
+}
+
+// Begin/end a timed region for one of the dominant kernels (no-ops unless ctx->timing).
+inline void time_begin(mashgpu_ctx *ctx, std::vector<EventPair> &list, cudaStream_t s)
+{
+    if (!ctx->timing) return;
+    EventPair ev;
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, s);
+    list.push_back(ev);
+}
+inline void time_end(mashgpu_ctx *ctx, std::vector<EventPair> &list, cudaStream_t s)
+{
+    if (!ctx->timing) return;
+    cudaEventRecord(list.back().b, s);
+}
+
+}  // namespace mashgpu

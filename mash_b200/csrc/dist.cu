@@ -1,0 +1,404 @@
+// dist.cu -- hot path 2: all-pairs sketch comparison (C-ABI: mashgpu_dist_*).
+//
+// Replaces compare / compareSketches / pValue (reference CommandDistance.cpp:306-448).
+//
+// Data layout: at open time every hash of every sketch is replaced by its rank in the sorted set of
+// all distinct hashes (an order- and equality-preserving 32-bit dictionary, built with one radix sort), and each
+// sketch becomes a row of P = sketch_size+1 uint32 ranks padded with the sentinel 0xFFFFFFFF.  The merge kernel
+// keeps a tile of 32 reference rows in shared memory, element-interleaved so that lane r only ever touches bank r,
+// and streams query rows through per-warp shared buffers; each lane runs the reference's sequential merge for its
+// (query, reference) pair for exactly sketch_size steps (every step adds one element to the union):
+//      a <= b -> advance ref;  b <= a -> advance query;   common = i + j - steps.
+// Steps that consume sentinels on both sides are the "list ran out" case of CommandDistance.cpp:367-385 and are
+// subtracted afterwards.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "binom.cuh"
+
+namespace mashgpu {
+
+constexpr uint32_t RANK_PAD = 0xFFFFFFFFu;
+constexpr int DIST_WARPS = 12;
+constexpr int DIST_ILP = 2;
+constexpr int DIST_THREADS = DIST_WARPS * 32;
+constexpr int DIST_TILE_R = 32;
+
+struct DistArgs {
+    const uint32_t *ranks;      // rows of P ranks: references first, then queries (or shared when self)
+    uint32_t P;                 // row pitch = sketch_size + 1
+    uint32_t S;                 // sketch_size (merge steps)
+    const uint32_t *ref_n;      // min(n_hashes, P) per reference row
+    const uint32_t *qry_n;
+    const uint64_t *ref_len;
+    const uint64_t *qry_len;
+    uint64_t ref_row0, qry_row0;   // first row of each set in `ranks`
+    uint32_t n_ref;
+    uint32_t q_begin, q_count;
+    uint32_t q_per_cta;         // queries handled by one CTA (grid.y slices the query range)
+    int kmer_size;
+    double kmer_space, max_distance, max_pvalue;
+    const double *dist_lut;     // distance for (common, denom == S), S+1 entries
+    uint32_t *numer; uint32_t *denom; double *distance; double *pvalue; uint8_t *pass;   // outputs, (q - q_begin) * n_ref + r
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// distance of compareSketches (CommandDistance.cpp:387-407)
+__device__ __forceinline__ double mash_distance(uint32_t common, uint32_t denom, int k)
+{
+    if (common == denom) return 0.0;
+    if (common == 0) return 1.0;
+    const double j = (double)common / (double)denom;
+    double d = -log(2 * j / (1. + j)) / k;
+    return d > 1 ? 1.0 : d;
+}
+
+__global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t *s_ref = smem;                                  // [P][32]
+    uint32_t *s_qry = smem + (size_t)a.P * DIST_TILE_R;      // [DIST_WARPS][DIST_ILP][P]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r0 = blockIdx.x * DIST_TILE_R;
+    const uint32_t r = r0 + lane;
+    const bool r_ok = r < a.n_ref;
+
+    // stage the reference tile, interleaved: element i of reference (r0+l) at s_ref[i*32 + l]
+    {
+        const uint32_t *row = a.ranks + (a.ref_row0 + (r_ok ? r : r0)) * (uint64_t)a.P;
+        for (uint32_t i = warp; i < a.P; i += DIST_WARPS) s_ref[i * DIST_TILE_R + lane] = r_ok ? row[i] : RANK_PAD;
+    }
+    __syncthreads();
+    const uint32_t nA = r_ok ? a.ref_n[r] : 0;
+    const uint64_t lenA = r_ok ? a.ref_len[r] : 1;
+    const uint32_t sref_base = (uint32_t)__cvta_generic_to_shared(s_ref) + lane * 4;
+
+    const uint32_t q_lo = a.q_begin + blockIdx.y * a.q_per_cta;
+    const uint32_t q_hi = min(q_lo + a.q_per_cta, a.q_begin + a.q_count);
+    uint32_t *my_q = s_qry + (size_t)warp * DIST_ILP * a.P;
+
+    for (uint32_t qb = q_lo + warp * DIST_ILP; qb < q_hi; qb += DIST_WARPS * DIST_ILP) {
+        // load DIST_ILP query rows (coalesced) into this warp's buffers
+#pragma unroll
+        for (int c = 0; c < DIST_ILP; c++) {
+            const uint32_t q = qb + c;
+            uint32_t *dst = my_q + (size_t)c * a.P;
+            if (q < q_hi) {
+                const uint32_t *row = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
+                for (uint32_t i = lane; i < a.P; i += 32) dst[i] = row[i];
+            } else {
+                for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
+            }
+        }
+        __syncwarp();
+        uint32_t pa[DIST_ILP], pb[DIST_ILP], va[DIST_ILP], vb[DIST_ILP], pb0[DIST_ILP];
+#pragma unroll
+        for (int c = 0; c < DIST_ILP; c++) {
+            pa[c] = sref_base;
+            pb0[c] = pb[c] = (uint32_t)__cvta_generic_to_shared(my_q + (size_t)c * a.P);
+            va[c] = lds32(pa[c]);
+            vb[c] = lds32(pb[c]);
+        }
+#pragma unroll 4
+        for (uint32_t t = 0; t < a.S; t++) {
+#pragma unroll
+            for (int c = 0; c < DIST_ILP; c++) {
+                const bool adv_a = va[c] <= vb[c];
+                const bool adv_b = vb[c] <= va[c];
+                if (adv_a) { pa[c] += DIST_TILE_R * 4; va[c] = lds32(pa[c]); }
+                if (adv_b) { pb[c] += 4; vb[c] = lds32(pb[c]); }
+            }
+        }
+        // epilogue
+#pragma unroll
+        for (int c = 0; c < DIST_ILP; c++) {
+            const uint32_t q = qb + c;
+            if (q >= q_hi || !r_ok) continue;
+            const uint32_t i_end = (pa[c] - sref_base) / (DIST_TILE_R * 4);
+            const uint32_t j_end = (pb[c] - pb0[c]) / 4;
+            const uint32_t nB = a.qry_n[q];
+            const uint32_t bogus = i_end > nA ? i_end - nA : 0;   // steps that consumed padding on both sides
+            const uint32_t denom = a.S - bogus;
+            const uint32_t common = (i_end - bogus) + (j_end - bogus) - denom;
+            double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
+            const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
+            bool pass = true;
+            double p = 0.0;
+            if (a.max_distance >= 0 && dist > a.max_distance) pass = false;     // CommandDistance.cpp:409-412
+            else {
+                p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
+                if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;        // :419-422
+            }
+            (void)nB;
+            if (a.numer) a.numer[o] = common;
+            if (a.denom) a.denom[o] = denom;
+            if (a.distance) a.distance[o] = dist;
+            if (a.pvalue) a.pvalue[o] = p;
+            if (a.pass) a.pass[o] = pass ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dictionary encoding
+// ---------------------------------------------------------------------------------------------------------
+// keys[row*P + i] = hash i of the row (or all-ones padding); idx = slot id
+__global__ void dict_gather_kernel(const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, uint64_t n_rows,
+                                   uint32_t P, uint64_t row0, uint64_t *keys, uint32_t *idx, uint32_t *n_eff)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_rows * P) return;
+    const uint64_t row = t / P;
+    const uint32_t i = (uint32_t)(t % P);
+    const uint32_t n = min(n_hashes[row], P);
+    const uint64_t slot = (row0 + row) * P + i;
+    keys[slot] = (i < n && i < stride) ? hashes[row * stride + i] : 0xFFFFFFFFFFFFFFFFULL;
+    idx[slot] = (uint32_t)slot;
+    if (i == 0) n_eff[row0 + row] = min(n, (uint32_t)min((uint64_t)P, stride));
+}
+
+__global__ void dict_flag_kernel(const uint64_t *sorted_keys, uint64_t n, uint32_t *flags)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    flags[t] = (t == 0 || sorted_keys[t] != sorted_keys[t - 1]) ? 1u : 0u;
+}
+
+__global__ void dict_scatter_kernel(const uint32_t *sorted_idx, const uint32_t *scan, uint64_t n, uint32_t P,
+                                    const uint32_t *n_eff, uint32_t *ranks)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t slot = sorted_idx[t];
+    const uint32_t row = slot / P, i = slot % P;
+    ranks[slot] = (i < n_eff[row]) ? (scan[t] - 1u) : RANK_PAD;
+}
+
+}  // namespace mashgpu
+
+using namespace mashgpu;
+
+struct mashgpu_dist_job {
+    mashgpu_ctx *ctx = nullptr;
+    mashgpu_dist_params params{};
+    uint64_t n_ref = 0, n_qry = 0;
+    bool self = false;
+    uint32_t P = 0;
+    DevBuf<uint32_t> ranks, n_eff;
+    DevBuf<uint64_t> lens;          // ref lengths then query lengths
+    DevBuf<double> lut;
+};
+
+namespace {
+
+// device copies of a sketch set's arrays (uploaded when the set lives in host memory)
+struct SetOnDevice {
+    const uint64_t *hashes = nullptr; const uint32_t *n_hashes = nullptr; const uint64_t *length = nullptr;
+    DevBuf<uint64_t> h, l; DevBuf<uint32_t> n;
+};
+
+int stage_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, SetOnDevice &d, cudaStream_t st)
+{
+    if (s->on_device) { d.hashes = s->hashes; d.n_hashes = s->n_hashes; d.length = s->length; return MASHGPU_OK; }
+    if (d.h.alloc(s->n * s->stride) != cudaSuccess || d.n.alloc(s->n) != cudaSuccess || d.l.alloc(s->n) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sketch set of %llu x %llu)", (unsigned long long)s->n, (unsigned long long)s->stride);
+    MG_CUDA(ctx, cudaMemcpyAsync(d.h.p, s->hashes, s->n * s->stride * 8, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d.n.p, s->n_hashes, s->n * 4, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d.l.p, s->length, s->n * 8, cudaMemcpyHostToDevice, st));
+    d.hashes = d.h.p; d.n_hashes = d.n.p; d.length = d.l.p;
+    return MASHGPU_OK;
+}
+
+int check_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, const char *what)
+{
+    if (!s) return fail(ctx, MASHGPU_ERR_INVALID, "%s set is NULL", what);
+    if (s->n && (!s->hashes || !s->n_hashes || !s->length)) return fail(ctx, MASHGPU_ERR_INVALID, "%s set has NULL arrays", what);
+    return MASHGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
+                                 const mashgpu_dist_params *params, mashgpu_dist_job **job_out)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    if (!params || !job_out) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    MG_TRY(check_set(ctx, ref, "reference"));
+    const bool self = (qry == nullptr || qry == ref);
+    if (!self) MG_TRY(check_set(ctx, qry, "query"));
+    if (params->sketch_size < 1 || params->sketch_size > 0x7FFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size out of range");
+    if (params->kmer_size < 1) return fail(ctx, MASHGPU_ERR_INVALID, "kmer_size out of range");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    mashgpu_dist_job *job = new mashgpu_dist_job();
+    job->ctx = ctx; job->params = *params; job->self = self;
+    job->n_ref = ref->n; job->n_qry = self ? ref->n : qry->n;
+    const uint32_t P = (uint32_t)params->sketch_size + 1;
+    job->P = P;
+    const uint64_t rows = job->n_ref + (self ? 0 : job->n_qry);
+    const uint64_t total = rows * P;
+    auto bail = [&](int rc) { delete job; return rc; };
+    if (total >= 0x7FFFFFFFull) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)rows, P));
+    // shared memory needed by the merge kernel
+    const size_t smem = ((size_t)P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * P) * 4;
+    if (smem > 227 * 1024) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "sketch_size %llu needs %zu B of shared memory per CTA (max 232448)", (unsigned long long)params->sketch_size, smem));
+
+    SetOnDevice dr, dq;
+    int rc = stage_set(ctx, ref, dr, st);
+    if (rc) return bail(rc);
+    if (!self && (rc = stage_set(ctx, qry, dq, st))) return bail(rc);
+
+    if (job->ranks.alloc(total) != cudaSuccess || job->n_eff.alloc(rows) != cudaSuccess || job->lens.alloc(rows) != cudaSuccess ||
+        job->lut.alloc(params->sketch_size + 1) != cudaSuccess)
+        return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (rank rows)"));
+    if (rows == 0) { *job_out = job; return MASHGPU_OK; }
+    {
+        DevBuf<uint64_t> keys, keys2; DevBuf<uint32_t> idx, idx2, flags, scan; DevBuf<uint8_t> tmp;
+        if (keys.alloc(total) != cudaSuccess || keys2.alloc(total) != cudaSuccess || idx.alloc(total) != cudaSuccess ||
+            idx2.alloc(total) != cudaSuccess || flags.alloc(total) != cudaSuccess || scan.alloc(total) != cudaSuccess)
+            return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)total));
+        const unsigned tb = 256;
+        dict_gather_kernel<<<(unsigned)((job->n_ref * P + tb - 1) / tb), tb, 0, st>>>(dr.hashes, ref->stride, dr.n_hashes, job->n_ref, P, 0, keys.p, idx.p, job->n_eff.p);
+        if (!self && job->n_qry)
+            dict_gather_kernel<<<(unsigned)((job->n_qry * P + tb - 1) / tb), tb, 0, st>>>(dq.hashes, qry->stride, dq.n_hashes, job->n_qry, P, job->n_ref, keys.p, idx.p, job->n_eff.p);
+        size_t tmp_sort = 0, tmp_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys.p, keys2.p, idx.p, idx2.p, (int)total, 0, 64, st);
+        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, flags.p, scan.p, (int)total, st);
+        if (tmp.alloc(std::max(tmp_sort, tmp_scan)) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)"));
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_sort, keys.p, keys2.p, idx.p, idx2.p, (int)total, 0, 64, st);
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e)));
+        dict_flag_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(keys2.p, total, flags.p);
+        e = cub::DeviceScan::InclusiveSum(tmp.p, tmp_scan, flags.p, scan.p, (int)total, st);
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e)));
+        dict_scatter_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(idx2.p, scan.p, total, P, job->n_eff.p, job->ranks.p);
+        ctx->kernel_launches += 14;
+        MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p, dr.length, job->n_ref * 8, cudaMemcpyDeviceToDevice, st));
+        if (!self && job->n_qry)
+            MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p + job->n_ref, dq.length, job->n_qry * 8, cudaMemcpyDeviceToDevice, st));
+        // distance LUT for denom == sketch_size, computed with the host libm exactly as the reference does
+        std::vector<double> lut(params->sketch_size + 1);
+        const uint64_t S = params->sketch_size;
+        for (uint64_t c = 0; c <= S; c++) {
+            double d;
+            double j = (double)c / (double)S;
+            if (c == S) d = 0; else if (c == 0) d = 1.; else { d = -log(2 * j / (1. + j)) / params->kmer_size; if (d > 1) d = 1; }
+            lut[c] = d;
+        }
+        MG_CUDA(ctx, cudaMemcpyAsync(job->lut.p, lut.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+        cudaError_t es = cudaStreamSynchronize(st);
+        if (es != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(es)));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
+        attr_set = true;
+    }
+    *job_out = job;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
+                                    uint32_t *d_numer, uint32_t *d_denom, double *d_distance, double *d_pvalue, uint8_t *d_pass,
+                                    void *stream)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (q_begin + q_count > job->n_qry) return fail(ctx, MASHGPU_ERR_INVALID, "query range [%llu, %llu) exceeds %llu", (unsigned long long)q_begin, (unsigned long long)(q_begin + q_count), (unsigned long long)job->n_qry);
+    if (q_count == 0 || job->n_ref == 0) return MASHGPU_OK;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    DistArgs a;
+    a.ranks = job->ranks.p; a.P = job->P; a.S = (uint32_t)job->params.sketch_size;
+    a.ref_n = job->n_eff.p; a.ref_len = job->lens.p; a.ref_row0 = 0;
+    const uint64_t qrow0 = job->self ? 0 : job->n_ref;
+    a.qry_n = job->n_eff.p + qrow0; a.qry_len = job->lens.p + qrow0; a.qry_row0 = qrow0;
+    a.n_ref = (uint32_t)job->n_ref; a.q_begin = (uint32_t)q_begin; a.q_count = (uint32_t)q_count;
+    a.kmer_size = job->params.kmer_size; a.kmer_space = job->params.kmer_space;
+    a.max_distance = job->params.max_distance; a.max_pvalue = job->params.max_pvalue;
+    a.dist_lut = job->lut.p;
+    a.numer = d_numer; a.denom = d_denom; a.distance = d_distance; a.pvalue = d_pvalue; a.pass = d_pass;
+    const uint32_t r_tiles = (uint32_t)((job->n_ref + DIST_TILE_R - 1) / DIST_TILE_R);
+    // slice the query range so that about 2 waves of CTAs cover the machine, at least one full round of warps each
+    const uint32_t round = DIST_WARPS * DIST_ILP;
+    uint32_t want_slices = std::max(1u, (uint32_t)(2 * ctx->sm_count + r_tiles - 1) / r_tiles);
+    uint32_t q_per_cta = (uint32_t)((q_count + want_slices - 1) / want_slices);
+    q_per_cta = std::max(round, ((q_per_cta + round - 1) / round) * round);
+    const uint32_t slices = (uint32_t)((q_count + q_per_cta - 1) / q_per_cta);
+    a.q_per_cta = q_per_cta;
+    const size_t smem = ((size_t)a.P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * a.P) * 4;
+    dim3 grid(r_tiles, slices);
+    time_begin(ctx, ctx->dist_events, st);
+    dist_kernel<<<grid, DIST_THREADS, smem, st>>>(a);
+    time_end(ctx, ctx->dist_events, st);
+    ctx->kernel_launches++;
+    ctx->dist_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
+                                uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint8_t *pass)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (q_begin + q_count > job->n_qry) return fail(ctx, MASHGPU_ERR_INVALID, "query range exceeds query count");
+    if (q_count == 0 || job->n_ref == 0) return MASHGPU_OK;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // bound the device output tile: chunks of queries
+    const uint64_t n_ref = job->n_ref;
+    const uint64_t max_pairs = 1ull << 27;     // 128 Mi pairs (~3.2 GB of outputs) per launch
+    uint64_t q_chunk = std::max<uint64_t>(1, max_pairs / n_ref);
+    q_chunk = std::min(q_chunk, q_count);
+    const uint64_t pairs = q_chunk * n_ref;
+    DevBuf<uint32_t> dn, dd; DevBuf<double> dD, dP; DevBuf<uint8_t> dpass;
+    if ((numer && dn.alloc(pairs) != cudaSuccess) || (denom && dd.alloc(pairs) != cudaSuccess) || (distance && dD.alloc(pairs) != cudaSuccess) ||
+        (pvalue && dP.alloc(pairs) != cudaSuccess) || (pass && dpass.alloc(pairs) != cudaSuccess))
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (pair outputs)");
+    cudaStream_t st = ctx->stream;
+    for (uint64_t q = 0; q < q_count; q += q_chunk) {
+        const uint64_t qc = std::min(q_chunk, q_count - q);
+        MG_TRY(mashgpu_dist_run_dev(job, q_begin + q, qc, numer ? dn.p : nullptr, denom ? dd.p : nullptr, distance ? dD.p : nullptr,
+                                    pvalue ? dP.p : nullptr, pass ? dpass.p : nullptr, st));
+        const uint64_t np = qc * n_ref, o = q * n_ref;
+        if (numer) MG_CUDA(ctx, cudaMemcpyAsync(numer + o, dn.p, np * 4, cudaMemcpyDeviceToHost, st));
+        if (denom) MG_CUDA(ctx, cudaMemcpyAsync(denom + o, dd.p, np * 4, cudaMemcpyDeviceToHost, st));
+        if (distance) MG_CUDA(ctx, cudaMemcpyAsync(distance + o, dD.p, np * 8, cudaMemcpyDeviceToHost, st));
+        if (pvalue) MG_CUDA(ctx, cudaMemcpyAsync(pvalue + o, dP.p, np * 8, cudaMemcpyDeviceToHost, st));
+        if (pass) MG_CUDA(ctx, cudaMemcpyAsync(pass + o, dpass.p, np, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_close(mashgpu_dist_job *job)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    delete job;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
+                            const mashgpu_dist_params *params,
+                            uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint8_t *pass)
+{
+    mashgpu_dist_job *job = nullptr;
+    MG_TRY(mashgpu_dist_open(ctx, ref, qry, params, &job));
+    int rc = mashgpu_dist_run(job, 0, job->n_qry, numer, denom, distance, pvalue, pass);
+    mashgpu_dist_close(job);
+    return rc;
+}

@@ -1,0 +1,274 @@
+// scan.cuh -- the k-mer scan + hash + filter kernel (K1 of DESIGN.md), shared by sketch and screen.
+//
+// Replaces the per-base loop of addMinHashes (reference Sketch.cpp:512-583) and hashSequence
+// (CommandScreen.cpp:484-599):  upper-case -> alphabet check -> canonical k-mer -> getHash -> tryInsert.
+//
+// Layout.  The input is one flat byte stream in HBM (units back to back, records separated by a byte
+// outside the alphabet).  A CTA processes TILE window-start positions at a time: the tile's ASCII bytes
+// are read once with 128-bit loads, converted to 4-bit codes (A,C,G,T -> 0,1,2,3, anything else -> 8)
+// and staged in shared memory as nibble words (8 bases per 32-bit word).  A thread takes a block of 8
+// consecutive window starts: it loads the BW words that cover them, builds the reverse-complement block
+// in registers (nibble reversal + xor 3), and for each of the 8 windows extracts the forward and the
+// reverse-complement k-mer with funnel shifts, picks the canonical one by an integer compare of the
+// little-endian nibble words (equivalent to the reference's memcmp because complementing reverses the
+// base order), expands it to ASCII with one PRMT per 4 bases and runs MurmurHash3_x64_128.
+// Only hashes at or below the tile's coarse threshold leave the fast path.
+#pragma once
+#include <cstdint>
+#include "murmur3.cuh"
+
+namespace mashgpu {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = 8192;              // window starts per tile
+constexpr int SCAN_HALO_WORDS = 8;           // extra nibble words (64 bases) staged past the tile
+constexpr int SCAN_WORDS = SCAN_TILE / 8 + SCAN_HALO_WORDS;
+constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
+
+enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2 };
+
+struct ScanArgs {
+    const uint8_t *stream;        // flat byte stream
+    uint64_t stream_len;          // bytes >= stream_len are treated as separators
+    uint64_t tile_begin, tile_end;
+    const uint64_t *tile_tmax;    // per-tile coarse threshold (indexed by absolute tile id); NULL -> coarse_t
+    uint64_t coarse_t;
+    uint32_t seed;
+    int use64;
+    int preserve_case;
+    int mode;
+    // candidate tables (sketch units / the screen mixture): open addressing, keys EMPTY_KEY when free
+    const uint64_t *unit_start;   // n_units + 1 stream offsets
+    uint32_t n_units;
+    const uint64_t *unit_t;       // per-unit threshold: keep hash <= unit_t[u]
+    const uint64_t *tab_off;      // per-unit slot offset into tab_keys / tab_cnt
+    const uint32_t *tab_log2;     // per-unit log2(capacity)
+    uint64_t *tab_keys;
+    uint32_t *tab_cnt;
+    uint32_t *unit_flags;         // bit0: table overflow
+    uint32_t *unit_maxhash;       // occurrences of the hash value 2^64-1 (cannot be a table key)
+    int64_t only_unit;            // >= 0: ignore every other unit (exact re-run)
+    // screen: reference hash table (distinct keys, EMPTY_KEY when free) with u32 hit counters
+    const uint64_t *ref_keys;
+    uint32_t *ref_cnt;
+    uint32_t ref_log2;
+    uint64_t ref_hmax;            // largest reference hash (probe prefilter)
+    // dump
+    uint64_t *out_hash;
+    uint8_t *out_valid;
+};
+
+__device__ __forceinline__ uint32_t slot_hash(uint64_t key, uint32_t log2cap)
+{
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap));
+}
+
+// Insert-or-count into an open-addressing table. Returns false when the table is full.
+__device__ __forceinline__ bool table_add(uint64_t *keys, uint32_t *cnt, uint32_t log2cap, uint64_t key)
+{
+    const uint32_t mask = (1u << log2cap) - 1;
+    uint32_t slot = slot_hash(key, log2cap);
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        unsigned long long prev = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) {
+            atomicAdd(&cnt[slot], 1u);
+            return true;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return false;
+}
+
+// Slow path: a hash passed the tile's coarse threshold.
+static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint64_t hash, uint64_t pos)
+{
+    if (a.mode == SCAN_DUMP) {
+        a.out_hash[pos] = hash;
+        a.out_valid[pos] = 1;
+        return;
+    }
+    if (a.mode == SCAN_SCREEN && hash <= a.ref_hmax) {
+        // hashCounts[key]++ iff key is a reference hash (CommandScreen.cpp:571-575)
+        const uint32_t mask = (1u << a.ref_log2) - 1;
+        uint32_t slot = slot_hash(hash, a.ref_log2);
+        for (;;) {
+            uint64_t k = a.ref_keys[slot];
+            if (k == hash) { atomicAdd(&a.ref_cnt[slot], 1u); break; }
+            if (k == EMPTY_KEY) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+    // unit of this position: last u with unit_start[u] <= pos
+    uint32_t lo = 0, hi = a.n_units;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.unit_start[mid] <= pos) lo = mid; else hi = mid;
+    }
+    const uint32_t u = lo;
+    if (a.only_unit >= 0 && (int64_t)u != a.only_unit) return;
+    if (hash > a.unit_t[u]) return;
+    if (hash == EMPTY_KEY) { atomicAdd(&a.unit_maxhash[u], 1u); return; }
+    if (!table_add(a.tab_keys + a.tab_off[u], a.tab_cnt + a.tab_off[u], a.tab_log2[u], hash))
+        atomicOr(&a.unit_flags[u], 1u);
+}
+
+// 4 ASCII bytes -> 4 nibbles (in the low 16 bits).  Codes: A=0 C=1 G=2 T=3 (order preserving, complement = xor 3),
+// anything else 8.  `fold` = 0xDFDFDFDF to upper-case first (a..z -> A..Z is the only effect that matters), or ~0.
+__device__ __forceinline__ uint32_t ascii4_to_nibbles(uint32_t w, uint32_t fold)
+{
+    const uint32_t u = w & fold;
+    const uint32_t t = (u >> 2) & ~(u >> 1) & 0x01010101u;                    // bit2 & ~bit1: 'T'
+    const uint32_t expect = (0x41414141u | (u & 0x06060606u)) ^ (t * 0x11u);  // the ACGT byte with these bits 1,2
+    const uint32_t bad = u ^ expect;
+    const uint32_t nz = (((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u;  // bit7 set where byte != 0
+    const uint32_t c = (u >> 1) & 0x03030303u;                                // A0 C1 T2 G3
+    const uint32_t code = c ^ ((c >> 1) & 0x01010101u);                       // A0 C1 G2 T3
+    uint32_t x = code | (nz >> 4);
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t nibble_reverse(uint32_t x)
+{
+    x = __byte_perm(x, 0, 0x0123);
+    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+
+// word i of (block >> 4*OFF nibbles), block = BW little-endian words
+template <int OFF, int BW>
+__device__ __forceinline__ uint32_t block_word(const uint32_t (&b)[BW], int i)
+{
+    constexpr int WS = OFF / 8, SH = 4 * (OFF % 8);
+    const int lo_i = i + WS, hi_i = i + WS + 1;
+    const uint32_t lo = lo_i < BW ? b[lo_i < BW ? lo_i : 0] : 0u;
+    if (SH == 0) return lo;
+    const uint32_t hi = hi_i < BW ? b[hi_i < BW ? hi_i : 0] : 0u;
+    return __funnelshift_r(lo, hi, SH);
+}
+
+template <int K>
+struct KmerShape {
+    static constexpr int NW = (K + 7) / 8;           // nibble words per k-mer
+    static constexpr int BW = (K + 7 + 7) / 8;       // nibble words per block of 8 window starts
+    static constexpr int NA = 2 * NW;                // ASCII words per k-mer
+    static constexpr uint32_t LAST_MASK = (K % 8) ? ((1u << (4 * (K % 8))) - 1u) : 0xFFFFFFFFu;
+};
+
+// nibble words (codes 0..3) -> ASCII words, bytes >= K zeroed
+template <int K>
+__device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::NW], uint32_t (&a)[KmerShape<K>::NA])
+{
+    constexpr uint32_t POOL = 0x54474341u;  // bytes 'A','C','G','T'
+#pragma unroll
+    for (int i = 0; i < KmerShape<K>::NW; i++) {
+        uint32_t lo = __byte_perm(POOL, 0, c[i]);
+        uint32_t hi = __byte_perm(POOL, 0, c[i] >> 16);
+        const int rem_lo = K - 8 * i;      // bases left for word 2i
+        const int rem_hi = K - 8 * i - 4;  // bases left for word 2i+1
+        if (rem_lo < 4) lo &= (1u << (8 * rem_lo)) - 1u;
+        if (rem_hi <= 0) hi = 0;
+        else if (rem_hi < 4) hi &= (1u << (8 * rem_hi)) - 1u;
+        a[2 * i] = lo;
+        a[2 * i + 1] = hi;
+    }
+}
+
+template <int K, bool CANON, int J>
+__device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW],
+                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t pos0, uint64_t tmax)
+{
+    using S = KmerShape<K>;
+    uint32_t f[S::NW];
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < S::NW; i++) {
+        f[i] = block_word<J, S::BW>(b, i);
+        if (i == S::NW - 1) f[i] &= S::LAST_MASK;
+        any |= f[i];
+    }
+    const bool valid = (any & 0x88888888u) == 0;
+    uint32_t c[S::NW];
+    if (CANON) {
+        constexpr int RO = 8 * S::BW - K - J;   // nibble offset of the reverse-complement window
+        uint32_t r[S::NW];
+#pragma unroll
+        for (int i = 0; i < S::NW; i++) {
+            r[i] = block_word<RO, S::BW>(rb, i);
+            if (i == S::NW - 1) r[i] &= S::LAST_MASK;
+        }
+        // fwd <= rc as little-endian integers  <=>  memcmp(fwd, rc, k) <= 0   (Sketch.cpp:569-571)
+        bool use_fwd = true;   // equal -> forward
+#pragma unroll
+        for (int i = 0; i < S::NW; i++) {   // from least to most significant: the last differing word decides
+            if (f[i] != r[i]) use_fwd = f[i] < r[i];
+        }
+#pragma unroll
+        for (int i = 0; i < S::NW; i++) c[i] = use_fwd ? f[i] : r[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < S::NW; i++) c[i] = f[i];
+    }
+    uint32_t asc[S::NA];
+    expand_ascii<K>(c, asc);
+    uint64_t h = murmur3_h1<K, S::NA>(asc, a.seed);
+    if (!a.use64) h &= 0xFFFFFFFFULL;
+    if (valid && h <= tmax) scan_emit(a, h, pos0 + J);
+}
+
+template <int K, bool CANON>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ScanArgs a)
+{
+    using S = KmerShape<K>;
+    __shared__ uint32_t sm[SCAN_WORDS];
+    const uint32_t fold = a.preserve_case ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+
+    for (uint64_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
+        const uint64_t base = tile * (uint64_t)SCAN_TILE;
+        // stage: 16 ASCII bytes -> 2 nibble words
+        for (int v = threadIdx.x; v < SCAN_WORDS / 2; v += SCAN_THREADS) {
+            const uint64_t off = base + 16ull * v;
+            uint32_t w0 = 0x88888888u, w1 = 0x88888888u;
+            if (off < a.stream_len) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.stream + off));
+                w0 = ascii4_to_nibbles(q.x, fold) | (ascii4_to_nibbles(q.y, fold) << 16);
+                w1 = ascii4_to_nibbles(q.z, fold) | (ascii4_to_nibbles(q.w, fold) << 16);
+                if (off + 16 > a.stream_len) {   // ragged end: bytes >= stream_len are separators
+                    const int keep = (int)(a.stream_len - off);   // 1..15
+                    if (keep < 8) { w0 |= 0x88888888u << (4 * keep); w1 = 0x88888888u; }
+                    else if (keep > 8) w1 |= 0x88888888u << (4 * (keep - 8));
+                    else w1 = 0x88888888u;
+                }
+            }
+            sm[2 * v] = w0;
+            sm[2 * v + 1] = w1;
+        }
+        __syncthreads();
+        const uint64_t tmax = a.tile_tmax ? a.tile_tmax[tile] : a.coarse_t;
+        for (int g = threadIdx.x; g < SCAN_TILE / 8; g += SCAN_THREADS) {
+            uint32_t b[S::BW], rb[S::BW];
+#pragma unroll
+            for (int i = 0; i < S::BW; i++) b[i] = sm[g + i];
+            if (CANON) {
+#pragma unroll
+                for (int i = 0; i < S::BW; i++) rb[i] = nibble_reverse(b[S::BW - 1 - i]) ^ 0x33333333u;
+            }
+            const uint64_t pos0 = base + 8ull * g;
+            scan_window<K, CANON, 0>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 1>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 2>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 3>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 4>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 5>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 6>(a, b, rb, pos0, tmax);
+            scan_window<K, CANON, 7>(a, b, rb, pos0, tmax);
+        }
+        __syncthreads();
+    }
+}
+
+// Host-side launcher table (defined in scan_inst_*.cu)
+typedef void (*scan_launch_fn)(const ScanArgs &a, int grid, cudaStream_t stream);
+scan_launch_fn get_scan_launcher(int k, bool canonical);
+
+}  // namespace mashgpu

@@ -1,0 +1,290 @@
+// screen.cu -- hot path 3: streaming containment screen (C-ABI: mashgpu_screen_*).
+//
+// Replaces hashSequence (reference CommandScreen.cpp:484-599) and the reduce that follows it
+// (CommandScreen.cpp:288-355, 409-455, 463-482, 601-615).  The reference keeps a robin_hood map
+// hash -> atomic<uint32_t> (:93-114); here it is an open-addressing table of the distinct reference hashes in
+// HBM with a parallel uint32 counter array.  Each fed chunk runs the same scan kernel as sketching in
+// SCAN_SCREEN mode: k-mer hashes <= the largest reference hash probe the table and bump the counter on a hit,
+// and the chunk's bottom-s candidates are merged into the running bottom-s of the whole mixture (the
+// reference merges per-thread MinHashHeaps the same way, :288-302; bottom-s of a union is order independent).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "scan.cuh"
+#include "sketch_core.cuh"
+#include "binom.cuh"
+
+namespace mashgpu {
+
+constexpr int SCR_THREADS = 256;
+
+__global__ void screen_insert_kernel(const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, uint64_t n_rows,
+                                     uint64_t *keys, uint32_t log2cap, unsigned long long *hmax, uint32_t *err)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_rows * stride) return;
+    const uint64_t row = t / stride, i = t % stride;
+    if (i >= n_hashes[row]) return;
+    const uint64_t key = hashes[t];
+    if (key == EMPTY_KEY) { atomicOr(err, 1u); return; }   // 2^64-1 cannot be a table key (probability 2^-64 per hash)
+    atomicMax(hmax, (unsigned long long)key);
+    const uint32_t mask = (1u << log2cap) - 1;
+    uint32_t slot = slot_hash(key, log2cap);
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) return;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// merge two ascending distinct lists (a: running mixture, b: chunk) -> ascending distinct, truncated to s.
+// Single CTA, bitonic sort of the concatenation in shared memory (2s <= 2^14 entries).
+__global__ void __launch_bounds__(SCR_THREADS) merge_bottom_s_kernel(uint64_t *mix, uint32_t *mix_n, const uint64_t *chunk, const uint32_t *chunk_n, uint32_t s)
+{
+    extern __shared__ uint64_t sk[];
+    const uint32_t na = *mix_n, nb = *chunk_n;
+    const uint32_t n = na + nb;
+    uint32_t N = 2;
+    while (N < n) N <<= 1;
+    for (uint32_t i = threadIdx.x; i < N; i += SCR_THREADS) sk[i] = i < na ? mix[i] : (i < n ? chunk[i - na] : EMPTY_KEY);
+    __syncthreads();
+    for (uint32_t size = 2; size <= N; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < N / 2; t += SCR_THREADS) {
+                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t a = sk[lo], b = sk[hi];
+                if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    // unique + truncate: rank of each first occurrence = number of distinct predecessors (serial scan by one warp is fine: n <= 2s)
+    if (threadIdx.x == 0) {
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < n && m < s; i++)
+            if (i == 0 || sk[i] != sk[i - 1]) mix[m++] = sk[i];
+        *mix_n = m;
+    }
+}
+
+// One CTA per reference sketch: shared count, sorted depths -> median, identity, p-value.
+__global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
+    const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, const uint64_t *keys, const uint32_t *cnt, uint32_t log2cap,
+    uint64_t set_size, int kmer_size, double kmer_space,
+    uint64_t *shared_out, uint64_t *median_out, double *identity_out, double *pvalue_out)
+{
+    extern __shared__ uint32_t depths[];
+    __shared__ uint32_t n_s;
+    const uint64_t r = blockIdx.x;
+    const uint32_t n = n_hashes[r];
+    if (threadIdx.x == 0) n_s = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << log2cap) - 1;
+    for (uint32_t i = threadIdx.x; i < n; i += SCR_THREADS) {
+        const uint64_t key = hashes[r * stride + i];
+        uint32_t slot = slot_hash(key, log2cap), c = 0;
+        for (;;) {
+            uint64_t k = keys[slot];
+            if (k == key) { c = cnt[slot]; break; }
+            if (k == EMPTY_KEY) break;
+            slot = (slot + 1) & mask;
+        }
+        if (c >= 1) depths[atomicAdd(&n_s, 1u)] = c;        // minCov == 1 (CommandScreen.cpp:152, 333-337)
+    }
+    __syncthreads();
+    const uint32_t shared = n_s;
+    uint32_t N = 2;
+    while (N < shared) N <<= 1;
+    for (uint32_t i = shared + threadIdx.x; i < N; i += SCR_THREADS) depths[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t size = 2; size <= N; size <<= 1)
+        for (uint32_t st = size >> 1; st > 0; st >>= 1) {
+            for (uint32_t t = threadIdx.x; t < N / 2; t += SCR_THREADS) {
+                uint32_t lo = 2 * t - (t & (st - 1)), hi = lo + st;
+                bool up = (lo & size) == 0;
+                uint32_t a = depths[lo], b = depths[hi];
+                if ((a > b) == up) { depths[lo] = b; depths[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        shared_out[r] = shared;
+        median_out[r] = shared > 0 ? depths[shared / 2] : 0;                      // :436
+        double identity;                                                         // estimateIdentity, :463-482
+        if (shared == n) identity = 1.;
+        else if (shared == 0) identity = 0.;
+        else identity = pow((double)shared / (double)n, 1. / kmer_size);
+        identity_out[r] = identity;
+        // pValueWithin, :601-615
+        pvalue_out[r] = shared == 0 ? 1.0 : binomial_upper_tail(shared, (double)set_size / kmer_space, n);
+    }
+}
+
+}  // namespace mashgpu
+
+using namespace mashgpu;
+
+struct mashgpu_screen_job {
+    mashgpu_ctx *ctx = nullptr;
+    mashgpu_sketch_params params{};
+    uint64_t n_ref = 0, stride = 0;
+    const uint64_t *ref_hashes = nullptr; const uint32_t *ref_n = nullptr;   // device
+    DevBuf<uint64_t> own_hashes; DevBuf<uint32_t> own_n;
+    DevBuf<uint64_t> keys; DevBuf<uint32_t> cnt;
+    uint32_t log2cap = 4;
+    uint64_t hmax = 0;
+    DevBuf<uint64_t> mix, chunk_hashes; DevBuf<uint32_t> mix_n, chunk_n;
+    uint32_t h_mix_n = 0; uint64_t h_mix_top = 0;
+    DevBuf<uint8_t> stage;   // device staging for host chunks
+};
+
+extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params *params, const mashgpu_sketch_set *refs,
+                                   mashgpu_screen_job **job_out)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    if (!refs || !job_out) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (refs->n && (!refs->hashes || !refs->n_hashes)) return fail(ctx, MASHGPU_ERR_INVALID, "reference set has NULL arrays");
+    if (params->sketch_size > (1u << 13)) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "screen supports sketch_size <= 8192");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    mashgpu_screen_job *job = new mashgpu_screen_job();
+    job->ctx = ctx; job->params = *params; job->n_ref = refs->n; job->stride = refs->stride;
+    auto bail = [&](int rc) { delete job; return rc; };
+    const uint64_t total = refs->n * refs->stride;
+    if (refs->on_device) { job->ref_hashes = refs->hashes; job->ref_n = refs->n_hashes; }
+    else {
+        if (job->own_hashes.alloc(total) != cudaSuccess || job->own_n.alloc(refs->n) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (reference sketches)"));
+        if (total) cudaMemcpyAsync(job->own_hashes.p, refs->hashes, total * 8, cudaMemcpyHostToDevice, st);
+        if (refs->n) cudaMemcpyAsync(job->own_n.p, refs->n_hashes, refs->n * 4, cudaMemcpyHostToDevice, st);
+        job->ref_hashes = job->own_hashes.p; job->ref_n = job->own_n.p;
+    }
+    job->log2cap = std::max(4u, ceil_log2(2 * total + 2));
+    if (job->log2cap > 31) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference table too large"));
+    const uint64_t cap = 1ull << job->log2cap;
+    const uint32_t s = params->sketch_size;
+    DevBuf<unsigned long long> d_hmax; DevBuf<uint32_t> d_err;
+    if (job->keys.alloc(cap) != cudaSuccess || job->cnt.alloc(cap) != cudaSuccess || job->mix.alloc(s) != cudaSuccess || job->chunk_hashes.alloc(s) != cudaSuccess ||
+        job->mix_n.alloc(1) != cudaSuccess || job->chunk_n.alloc(1) != cudaSuccess || d_hmax.alloc(1) != cudaSuccess || d_err.alloc(1) != cudaSuccess)
+        return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen table of %llu slots)", (unsigned long long)cap));
+    cudaMemsetAsync(job->keys.p, 0xFF, cap * 8, st);
+    cudaMemsetAsync(job->cnt.p, 0, cap * 4, st);
+    cudaMemsetAsync(job->mix_n.p, 0, 4, st);
+    cudaMemsetAsync(d_hmax.p, 0, 8, st);
+    cudaMemsetAsync(d_err.p, 0, 4, st);
+    if (total) {
+        screen_insert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(job->ref_hashes, refs->stride, job->ref_n, refs->n, job->keys.p, job->log2cap, d_hmax.p, d_err.p);
+        ctx->kernel_launches++;
+    }
+    unsigned long long hmax = 0; uint32_t err = 0;
+    cudaMemcpyAsync(&hmax, d_hmax.p, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
+    if (err) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketch contains the hash value 2^64-1"));
+    job->hmax = hmax;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(merge_bottom_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        attr_set = true;
+    }
+    *job_out = job;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64_t len)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (len == 0) return MASHGPU_OK;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t s = job->params.sketch_size;
+    uint64_t unit_start[2] = {0, len};
+    SketchStream S;
+    S.d_stream = d_chunk; S.unit_start = unit_start; S.n_units = 1;
+    if (job->h_mix_n == s) { S.t_cap = true; S.t_cap_value = job->h_mix_top; }   // nothing above the running s-th smallest can matter
+    ScreenProbe probe{job->keys.p, job->cnt.p, job->log2cap, job->hmax};
+    MG_TRY(sketch_stream_core(ctx, &job->params, S, job->chunk_hashes.p, nullptr, job->chunk_n.p, st, &probe));
+    uint32_t N = 2;
+    while (N < 2 * s) N <<= 1;
+    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, s);
+    ctx->kernel_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (job->h_mix_n) {
+        MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_top, job->mix.p + (job->h_mix_n - 1), 8, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_feed(mashgpu_screen_job *job, const char *chunk, uint64_t len)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (len == 0) return MASHGPU_OK;
+    if (!chunk) return fail(ctx, MASHGPU_ERR_INVALID, "chunk is NULL");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t padded = ((len + 15) / 16) * 16;
+    if (job->stage.n < padded && job->stage.alloc(padded + (padded >> 2)) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+    MG_CUDA(ctx, cudaMemcpyAsync(job->stage.p, chunk, len, cudaMemcpyHostToDevice, ctx->stream));
+    return mashgpu_screen_feed_dev(job, job->stage.p, len);
+}
+
+extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, uint64_t *median, double *identity,
+                                     double *pvalue, uint64_t *set_size_out, uint64_t *mixture_hashes, uint32_t *mixture_n)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int k = job->params.kmer_size;
+    int asize = 0;
+    for (int i = 0; i < 256; i++) asize += job->params.alphabet[i] != 0;
+    const double kmer_space = std::pow((double)asize, (double)k);
+    // estimateSetSize (reference MinHashHeap.h:45), cast to uint64_t as in CommandScreen.cpp:322
+    uint64_t set_size = 0;
+    if (job->h_mix_n)
+        set_size = (uint64_t)(std::pow(2.0, job->params.use64 ? 64.0 : 32.0) * (double)job->h_mix_n / (double)job->h_mix_top);
+    if (set_size_out) *set_size_out = set_size;
+    if (mixture_n) *mixture_n = job->h_mix_n;
+    if (mixture_hashes && job->h_mix_n)
+        MG_CUDA(ctx, cudaMemcpyAsync(mixture_hashes, job->mix.p, job->h_mix_n * 8ull, cudaMemcpyDeviceToHost, st));
+    const uint64_t n = job->n_ref;
+    if (n) {
+        DevBuf<uint64_t> d_shared, d_median; DevBuf<double> d_ident, d_p;
+        if (d_shared.alloc(n) != cudaSuccess || d_median.alloc(n) != cudaSuccess || d_ident.alloc(n) != cudaSuccess || d_p.alloc(n) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen outputs)");
+        uint32_t N = 2;
+        while (N < job->stride) N <<= 1;
+        if ((size_t)N * 4 > 200 * 1024) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketches larger than 51200 hashes");
+        if ((size_t)N * 4 > 48 * 1024)
+            MG_CUDA(ctx, cudaFuncSetAttribute(screen_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)N * 4)));
+        screen_reduce_kernel<<<(unsigned)n, SCR_THREADS, (size_t)N * 4, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->cnt.p, job->log2cap,
+                                                                            set_size, k, kmer_space, d_shared.p, d_median.p, d_ident.p, d_p.p);
+        ctx->kernel_launches++;
+        MG_CUDA(ctx, cudaGetLastError());
+        if (shared) MG_CUDA(ctx, cudaMemcpyAsync(shared, d_shared.p, n * 8, cudaMemcpyDeviceToHost, st));
+        if (median) MG_CUDA(ctx, cudaMemcpyAsync(median, d_median.p, n * 8, cudaMemcpyDeviceToHost, st));
+        if (identity) MG_CUDA(ctx, cudaMemcpyAsync(identity, d_ident.p, n * 8, cudaMemcpyDeviceToHost, st));
+        if (pvalue) MG_CUDA(ctx, cudaMemcpyAsync(pvalue, d_p.p, n * 8, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_close(mashgpu_screen_job *job)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    delete job;
+    return MASHGPU_OK;
+}

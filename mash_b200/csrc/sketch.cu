@@ -1,0 +1,595 @@
+// sketch.cu -- hot path 1: batched bottom-s sketching on the GPU (C-ABI: mashgpu_sketch_*, mashgpu_hash_windows).
+//
+// Pipeline per batch:
+//   flat byte stream in HBM  ->  scan_kernel (scan.cuh): hash every valid canonical k-mer, keep hash <= T_unit
+//   in the unit's open-addressing table (distinct keys + multiplicities)  ->  select_kernel: compact the table,
+//   sort, emit the s smallest.  This replaces MinHashHeap::tryInsert / HashSet::toHashList
+//   (reference MinHashHeap.cpp:68-146, HashSet.cpp:78-118): bottom-s of a set does not depend on insertion order.
+//   T_unit is chosen so that ~SURVIVOR_FACTOR*s distinct hashes are expected; a unit that ends with fewer than s
+//   distinct survivors (while k-mers were dropped) or overflows its table is re-run exactly with a larger T.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "scan.cuh"
+#include "sketch_core.cuh"
+
+namespace mashgpu {
+
+scan_launch_fn get_scan_launcher_part0(int, bool);
+scan_launch_fn get_scan_launcher_part1(int, bool);
+scan_launch_fn get_scan_launcher_part2(int, bool);
+scan_launch_fn get_scan_launcher_part3(int, bool);
+
+scan_launch_fn get_scan_launcher(int k, bool canonical)
+{
+    if (auto f = get_scan_launcher_part0(k, canonical)) return f;
+    if (auto f = get_scan_launcher_part1(k, canonical)) return f;
+    if (auto f = get_scan_launcher_part2(k, canonical)) return f;
+    return get_scan_launcher_part3(k, canonical);
+}
+
+constexpr double SURVIVOR_FACTOR = 3.0;   // expected distinct survivors = 3 s
+constexpr double TABLE_SLACK = 2.7;       // table slots per expected survivor
+constexpr uint32_t SEL_MAX_LOG2 = 14;     // select_kernel sorts up to 2^14 keys in shared memory (128 KB)
+constexpr int SEL_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------------------
+// per-tile coarse threshold: max T over the units a tile touches
+// ---------------------------------------------------------------------------------------------------------
+__global__ void tile_tmax_kernel(const uint64_t *unit_start, uint32_t n_units, const uint64_t *unit_t,
+                                 uint64_t stream_len, int k, uint64_t tile_begin, uint64_t tile_end, uint64_t *tile_tmax)
+{
+    uint64_t tile = tile_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (tile >= tile_end) return;
+    uint64_t first = tile * (uint64_t)SCAN_TILE;
+    uint64_t last = first + SCAN_TILE - 1;
+    if (last >= stream_len) last = stream_len ? stream_len - 1 : 0;
+    uint32_t lo = 0, hi = n_units;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (unit_start[mid] <= first) lo = mid; else hi = mid; }
+    uint64_t t = 0;
+    for (uint32_t u = lo; u < n_units && unit_start[u] <= last; u++) t = max(t, unit_t[u]);
+    tile_tmax[tile] = t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// select: table -> ascending bottom-s (+ counts)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t table_count(const uint64_t *keys, const uint32_t *cnt, uint32_t log2cap, uint64_t key)
+{
+    const uint32_t mask = (1u << log2cap) - 1;
+    uint32_t slot = slot_hash(key, log2cap);
+    for (;;) {
+        uint64_t k = keys[slot];
+        if (k == key) return cnt[slot];
+        if (k == EMPTY_KEY) return 0;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// One CTA per unit; tables up to 2^SEL_MAX_LOG2 slots.  flags bit1 = fewer than s distinct survivors although
+// k-mers were filtered (unit_t != max); units whose table is too large for shared memory get bit2.
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(
+    uint32_t unit_begin, uint32_t n_units, const uint64_t *unit_t, const uint64_t *tab_off, const uint32_t *tab_log2,
+    const uint64_t *tab_keys, const uint32_t *tab_cnt, const uint32_t *unit_maxhash, uint32_t *unit_flags,
+    uint32_t s, uint64_t capped_t, uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n)
+{
+    extern __shared__ uint64_t sk[];
+    __shared__ uint32_t n_s;
+    const uint32_t u = unit_begin + blockIdx.x;
+    if (u >= unit_begin + n_units) return;
+    const uint32_t log2cap = tab_log2[u];
+    if (unit_flags[u] & 1u) return;                    // overflowed: will be re-run
+    if (log2cap > SEL_MAX_LOG2) { if (threadIdx.x == 0) atomicOr(&unit_flags[u], 4u); return; }
+    const uint32_t cap = 1u << log2cap;
+    const uint64_t *keys = tab_keys + tab_off[u];
+    const uint32_t *cnt = tab_cnt + tab_off[u];
+    if (threadIdx.x == 0) n_s = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cap; i += SEL_THREADS) {
+        uint64_t k = keys[i];
+        if (k != EMPTY_KEY) sk[atomicAdd(&n_s, 1u)] = k;
+    }
+    __syncthreads();
+    const uint32_t n = n_s;
+    uint32_t N = 2;
+    while (N < n) N <<= 1;
+    for (uint32_t i = n + threadIdx.x; i < N; i += SEL_THREADS) sk[i] = EMPTY_KEY;
+    __syncthreads();
+    for (uint32_t size = 2; size <= N; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < N / 2; t += SEL_THREADS) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t a = sk[lo], b = sk[hi];
+                if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t n_max = unit_maxhash[u] ? 1u : 0u;          // the value 2^64-1 itself, largest possible
+    const uint32_t total = n + n_max;
+    const uint32_t m = total < s ? total : s;
+    if (threadIdx.x == 0) {
+        out_n[u] = m;
+        // too few survivors although k-mers were dropped -- unless the threshold is the caller's cap (screen: the
+        // running s-th smallest of the mixture; nothing above it can enter the bottom-s)
+        if (total < s && unit_t[u] != EMPTY_KEY && unit_t[u] != capped_t) atomicOr(&unit_flags[u], 2u);
+    }
+    for (uint32_t i = threadIdx.x; i < m; i += SEL_THREADS) {
+        uint64_t key = i < n ? sk[i] : EMPTY_KEY;
+        out_hashes[(uint64_t)u * s + i] = key;
+        if (out_counts) out_counts[(uint64_t)u * s + i] = i < n ? table_count(keys, cnt, log2cap, key) : unit_maxhash[u];
+    }
+}
+
+// Large tables: compact non-empty keys to scratch (then cub radix sort on the host side of this file).
+__global__ void compact_table_kernel(const uint64_t *keys, uint64_t cap, uint64_t *out, unsigned long long *out_n)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    uint64_t k = keys[i];
+    if (k != EMPTY_KEY) out[atomicAdd(out_n, 1ull)] = k;
+}
+
+__global__ void emit_sorted_kernel(const uint64_t *sorted, uint32_t m, const uint64_t *keys, const uint32_t *cnt, uint32_t log2cap,
+                                   uint32_t maxhash_cnt, uint32_t n_sorted, uint64_t *out_hashes, uint32_t *out_counts)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint64_t key = i < n_sorted ? sorted[i] : EMPTY_KEY;
+    out_hashes[i] = key;
+    if (out_counts) out_counts[i] = i < n_sorted ? table_count(keys, cnt, log2cap, key) : maxhash_cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p)
+{
+    if (!p) return fail(ctx, MASHGPU_ERR_INVALID, "params is NULL");
+    if (p->kmer_size < 1 || p->kmer_size > 32) return fail(ctx, MASHGPU_ERR_INVALID, "kmer_size %d outside 1..32", p->kmer_size);
+    if (p->sketch_size < 1) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size must be >= 1");
+    int n = 0;
+    for (int i = 0; i < 256; i++) n += p->alphabet[i] != 0;
+    bool dna = n == 4 && p->alphabet['A'] && p->alphabet['C'] && p->alphabet['G'] && p->alphabet['T'];
+    if (!dna)
+        return fail(ctx, MASHGPU_ERR_UNSUPPORTED,
+                    "alphabet other than {A,C,G,T} is not on the GPU path yet (byte-alphabet kernels pending)");
+    return MASHGPU_OK;
+}
+
+static double kmer_space_of(const mashgpu_sketch_params *p)
+{
+    int n = 0;
+    for (int i = 0; i < 256; i++) n += p->alphabet[i] != 0;
+    return std::pow((double)n, (double)p->kmer_size);
+}
+
+// Threshold / table geometry of one unit. factor = expected-survivor multiple of s (<= 0: keep everything).
+void plan_unit(const mashgpu_sketch_params *p, uint64_t span, double factor, uint64_t *t_out, uint32_t *log2_out)
+{
+    const double hash_space = p->use64 ? 18446744073709551616.0 : 4294967296.0;
+    double kspace = kmer_space_of(p);
+    double distinct_max = std::min((double)span, kspace);          // upper bound on distinct hashes
+    double expect = factor * (double)p->sketch_size;
+    if (factor <= 0 || expect >= (double)span * 0.5 || expect >= kspace * 0.25) {
+        *t_out = EMPTY_KEY;                                            // keep all
+        *log2_out = std::max(4u, ceil_log2((uint64_t)(2.0 * distinct_max) + 2));
+        return;
+    }
+    double frac = expect / (double)span;
+    double t = frac * hash_space;
+    *t_out = t >= 18446744073709549568.0 ? (EMPTY_KEY - 1) : (uint64_t)t;
+    *log2_out = std::max(4u, ceil_log2((uint64_t)(TABLE_SLACK * expect) + 2));
+}
+
+static int launch_scan(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const ScanArgs &a, cudaStream_t st)
+{
+    scan_launch_fn fn = get_scan_launcher(p->kmer_size, !p->noncanonical);
+    if (!fn) return fail(ctx, MASHGPU_ERR_INVALID, "no scan kernel for k=%d", p->kmer_size);
+    uint64_t ntiles = a.tile_end - a.tile_begin;
+    if (ntiles == 0) return MASHGPU_OK;
+    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
+    time_begin(ctx, ctx->scan_events, st);
+    fn(a, grid, st);
+    time_end(ctx, ctx->scan_events, st);
+    ctx->kernel_launches++;
+    ctx->scan_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+    return MASHGPU_OK;
+}
+
+// Exact re-run of one unit with growing thresholds, ending at keep-all (always succeeds).
+static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S, uint32_t u,
+                      uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
+                      const ScanArgs &base)
+{
+    const uint64_t span = S.unit_start[u + 1] - S.unit_start[u];
+    const uint32_t s = p->sketch_size;
+    double factor = SURVIVOR_FACTOR;
+    ctx->exact_reruns++;
+    for (int attempt = 0; attempt < 64; attempt++) {
+        factor *= 8.0;
+        uint64_t t; uint32_t lg;
+        plan_unit(p, span, factor, &t, &lg);
+        const bool keep_all = (t == EMPTY_KEY);
+        const uint64_t cap = 1ull << lg;
+        DevBuf<uint64_t> keys; DevBuf<uint32_t> cnt; DevBuf<uint64_t> meta;   // meta: [t, off]
+        DevBuf<uint32_t> small;                                                   // [log2, flags, maxhash]
+        if (keys.alloc(cap) != cudaSuccess || cnt.alloc(cap) != cudaSuccess || meta.alloc(2) != cudaSuccess || small.alloc(3) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory in exact re-run (table of %llu slots)", (unsigned long long)cap);
+        MG_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * 8, st));
+        MG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, cap * 4, st));
+        uint64_t h_meta[2] = {t, 0};
+        uint32_t h_small[3] = {lg, 0, 0};
+        MG_CUDA(ctx, cudaMemcpyAsync(meta.p, h_meta, sizeof h_meta, cudaMemcpyHostToDevice, st));
+        MG_CUDA(ctx, cudaMemcpyAsync(small.p, h_small, sizeof h_small, cudaMemcpyHostToDevice, st));
+        // The scan looks units up by index u: give it views shifted so that index u lands on our single entries.
+        ScanArgs a = base;
+        a.tile_begin = S.unit_start[u] / SCAN_TILE;
+        a.tile_end = (S.unit_start[u + 1] + SCAN_TILE - 1) / SCAN_TILE;
+        a.tile_tmax = nullptr;
+        a.coarse_t = t;
+        a.only_unit = u;
+        a.unit_t = meta.p - u;
+        a.tab_off = meta.p + 1 - u;
+        a.tab_log2 = small.p - u;
+        a.unit_flags = small.p + 1 - u;
+        a.unit_maxhash = small.p + 2 - u;
+        a.tab_keys = keys.p;
+        a.tab_cnt = cnt.p;
+        MG_TRY(launch_scan(ctx, p, a, st));
+        MG_CUDA(ctx, cudaMemcpyAsync(h_small, small.p, sizeof h_small, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_small[1] & 1u) continue;                                            // overflow: grow
+        // compact + sort
+        DevBuf<uint64_t> comp, sorted; DevBuf<unsigned long long> d_n;
+        if (comp.alloc(cap) != cudaSuccess || sorted.alloc(cap) != cudaSuccess || d_n.alloc(1) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory in exact re-run");
+        MG_CUDA(ctx, cudaMemsetAsync(d_n.p, 0, 8, st));
+        compact_table_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(keys.p, cap, comp.p, d_n.p);
+        ctx->kernel_launches++;
+        unsigned long long n = 0;
+        MG_CUDA(ctx, cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+        const uint64_t total = n + (h_small[2] ? 1 : 0);
+        if (total < s && !keep_all) continue;                                     // still too few: grow
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, comp.p, sorted.p, (int)n, 0, 64, st);
+        DevBuf<uint8_t> tmp;
+        if (tmp.alloc(tmp_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+        if (n) {
+            MG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, comp.p, sorted.p, (int)n, 0, 64, st));
+            ctx->kernel_launches += 8;
+        }
+        const uint32_t m = (uint32_t)std::min<uint64_t>(total, s);
+        if (m)
+            emit_sorted_kernel<<<(m + 255) / 256, 256, 0, st>>>(sorted.p, m, keys.p, cnt.p, lg, h_small[2], (uint32_t)n,
+                                                               d_out_hashes + (uint64_t)u * s,
+                                                               d_out_counts ? d_out_counts + (uint64_t)u * s : nullptr);
+        ctx->kernel_launches++;
+        MG_CUDA(ctx, cudaMemcpyAsync(d_out_n + u, &m, 4, cudaMemcpyHostToDevice, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+        return MASHGPU_OK;
+    }
+    return fail(ctx, MASHGPU_ERR_CUDA, "exact re-run of unit %u did not converge", u);
+}
+
+// Core: sketch every unit of a device-resident stream.
+int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S,
+                       uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
+                       const ScreenProbe *probe)
+{
+    const uint32_t n_units = (uint32_t)S.n_units;
+    if (n_units == 0) return MASHGPU_OK;
+    const uint32_t s = p->sketch_size;
+    const uint64_t stream_len = S.unit_start[n_units];
+    const uint64_t ntiles = (stream_len + SCAN_TILE - 1) / SCAN_TILE;
+
+    // plan
+    std::vector<uint64_t> h_t(n_units), h_off(n_units);
+    std::vector<uint32_t> h_log2(n_units);
+    uint64_t slots = 0;
+    for (uint32_t u = 0; u < n_units; u++) {
+        uint64_t span = S.unit_start[u + 1] - S.unit_start[u];
+        plan_unit(p, span, S.force_keep_all ? 0.0 : SURVIVOR_FACTOR, &h_t[u], &h_log2[u]);
+        if (S.t_cap && h_t[u] > S.t_cap_value) h_t[u] = S.t_cap_value;
+        h_off[u] = slots;
+        slots += 1ull << h_log2[u];
+    }
+    DevBuf<uint64_t> d_start, d_t, d_off, d_keys, d_tmax;
+    DevBuf<uint32_t> d_log2, d_cnt, d_flags, d_maxhash;
+    if (d_start.alloc(n_units + 1) != cudaSuccess || d_t.alloc(n_units) != cudaSuccess || d_off.alloc(n_units) != cudaSuccess ||
+        d_log2.alloc(n_units) != cudaSuccess || d_flags.alloc(n_units) != cudaSuccess || d_maxhash.alloc(n_units) != cudaSuccess ||
+        d_keys.alloc(slots) != cudaSuccess || d_cnt.alloc(slots) != cudaSuccess || d_tmax.alloc(ntiles) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (%llu candidate slots for %u units)", (unsigned long long)slots, n_units);
+    MG_CUDA(ctx, cudaMemcpyAsync(d_start.p, S.unit_start, (n_units + 1) * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_t.p, h_t.data(), n_units * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_off.data(), n_units * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_log2.p, h_log2.data(), n_units * 4ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, n_units * 4ull, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_maxhash.p, 0, n_units * 4ull, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_keys.p, 0xFF, slots * 8ull, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, slots * 4ull, st));
+
+    ScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.stream = (const uint8_t *)S.d_stream;
+    a.stream_len = stream_len;
+    a.tile_begin = 0;
+    a.tile_end = ntiles;
+    a.seed = p->seed;
+    a.use64 = p->use64;
+    a.preserve_case = p->preserve_case;
+    a.mode = probe ? SCAN_SCREEN : SCAN_SKETCH;
+    a.unit_start = d_start.p;
+    a.n_units = n_units;
+    a.unit_t = d_t.p;
+    a.tab_off = d_off.p;
+    a.tab_log2 = d_log2.p;
+    a.tab_keys = d_keys.p;
+    a.tab_cnt = d_cnt.p;
+    a.unit_flags = d_flags.p;
+    a.unit_maxhash = d_maxhash.p;
+    a.only_unit = -1;
+    if (probe) {
+        a.ref_keys = probe->keys; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
+    }
+    if (ntiles) {
+        tile_tmax_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(d_start.p, n_units, d_t.p, stream_len, p->kmer_size, 0, ntiles, d_tmax.p);
+        ctx->kernel_launches++;
+    }
+    a.tile_tmax = d_tmax.p;
+    if (probe) {
+        // coarse filter must also let reference-hash candidates through
+        a.tile_tmax = nullptr;
+        uint64_t tm = 0;
+        for (uint32_t u = 0; u < n_units; u++) tm = std::max(tm, h_t[u]);
+        a.coarse_t = std::max(tm, probe->hmax);
+    }
+    MG_TRY(launch_scan(ctx, p, a, st));
+
+    static bool attr_set = false;
+    const size_t sel_smem = (size_t)8 << SEL_MAX_LOG2;
+    if (!attr_set) {
+        MG_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        attr_set = true;
+    }
+    uint32_t max_log2 = 4;
+    for (uint32_t u = 0; u < n_units; u++) max_log2 = std::max(max_log2, std::min(h_log2[u], SEL_MAX_LOG2));
+    select_kernel<<<n_units, SEL_THREADS, (size_t)8 << max_log2, st>>>(0, n_units, d_t.p, d_off.p, d_log2.p, d_keys.p, d_cnt.p,
+                                                                     d_maxhash.p, d_flags.p, s, S.t_cap ? S.t_cap_value : EMPTY_KEY,
+                                                                     d_out_hashes, d_out_counts, d_out_n);
+    ctx->kernel_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+
+    std::vector<uint32_t> h_flags(n_units);
+    MG_CUDA(ctx, cudaMemcpyAsync(h_flags.data(), d_flags.p, n_units * 4ull, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    for (uint32_t u = 0; u < n_units; u++) {
+        if (h_flags[u] == 0) continue;
+        a.mode = SCAN_SKETCH;    // reference-table hits were already counted in the first pass
+        MG_TRY(rerun_unit(ctx, p, S, u, d_out_hashes, d_out_counts, d_out_n, st, a));
+    }
+    return MASHGPU_OK;
+}
+
+}  // namespace mashgpu
+
+using namespace mashgpu;
+
+extern "C" uint32_t mashgpu_set_alphabet(mashgpu_sketch_params *p, const char *characters)
+{
+    // setAlphabetFromString, reference Sketch.cpp:1108-1137
+    memset(p->alphabet, 0, 256);
+    for (const char *c = characters; *c; c++) {
+        unsigned char u = (unsigned char)*c;
+        if (!p->preserve_case && u > 96 && u < 123) u -= 32;
+        p->alphabet[u] = 1;
+    }
+    uint32_t n = 0;
+    for (int i = 0; i < 256; i++) n += p->alphabet[i];
+    p->use64 = std::pow((double)n, (double)p->kmer_size) > std::pow(2.0, 32.0);
+    return n;
+}
+
+extern "C" int mashgpu_sketch_stream_dev(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                         const void *d_stream, const uint64_t *unit_start, uint64_t n_units,
+                                         uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, void *stream)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    if (n_units > 0xFFFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "too many units");
+    if (n_units && (!d_stream || !unit_start || !d_out_hashes || !d_out_n)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SketchStream S;
+    S.d_stream = d_stream; S.unit_start = unit_start; S.n_units = n_units;
+    return sketch_stream_core(ctx, params, S, d_out_hashes, d_out_counts, d_out_n, stream ? (cudaStream_t)stream : ctx->stream, nullptr);
+}
+
+namespace {
+
+struct Wave { uint64_t unit_begin, unit_end, rec_begin, rec_end, bytes; };
+
+constexpr uint64_t WAVE_BYTES = 1ull << 31;        // stream bytes per wave
+constexpr uint64_t DIRECT_COPY_MIN = 1ull << 18;   // records at least this long are copied straight from the caller's buffer
+
+}  // namespace
+
+extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                    uint64_t n_records, const char *const *seq, const uint64_t *len,
+                                    const uint32_t *unit_of_record, uint64_t n_units,
+                                    uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_length)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    if (n_units == 0) return MASHGPU_OK;
+    if (!out_hashes || !out_n) return fail(ctx, MASHGPU_ERR_INVALID, "out_hashes/out_n is NULL");
+    if (n_records && (!seq || !len)) return fail(ctx, MASHGPU_ERR_INVALID, "seq/len is NULL");
+    if (n_units > 0xFFFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "too many units");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t s = params->sketch_size;
+    const uint64_t k = (uint64_t)params->kmer_size;
+
+    // unit spans in the flat stream: kept records back to back, one separator byte after each
+    std::vector<uint64_t> unit_bytes(n_units, 0), unit_rec_begin(n_units + 1, 0);
+    {
+        uint64_t r = 0;
+        for (uint64_t u = 0; u < n_units; u++) {
+            unit_rec_begin[u] = r;
+            while (r < n_records && (unit_of_record ? unit_of_record[r] : r) == u) {
+                if (len[r] >= k) unit_bytes[u] += len[r] + 1;
+                r++;
+            }
+            if (r < n_records && unit_of_record && unit_of_record[r] < u)
+                return fail(ctx, MASHGPU_ERR_INVALID, "unit_of_record must be non-decreasing");
+        }
+        unit_rec_begin[n_units] = r;
+        if (r != n_records) return fail(ctx, MASHGPU_ERR_INVALID, "unit_of_record refers to units >= n_units or is not sorted");
+    }
+    if (out_length)
+        for (uint64_t u = 0; u < n_units; u++) {
+            uint64_t L = 0;
+            for (uint64_t r = unit_rec_begin[u]; r < unit_rec_begin[u + 1]; r++)
+                if (len[r] >= k) L += len[r];
+            out_length[u] = L;
+        }
+
+    // waves
+    std::vector<Wave> waves;
+    {
+        Wave w{0, 0, 0, 0, 0};
+        for (uint64_t u = 0; u < n_units; u++) {
+            if (w.unit_end > w.unit_begin && w.bytes + unit_bytes[u] > WAVE_BYTES) {
+                w.rec_end = unit_rec_begin[u];
+                waves.push_back(w);
+                w = Wave{u, u, unit_rec_begin[u], 0, 0};
+            }
+            w.unit_end = u + 1;
+            w.bytes += unit_bytes[u];
+        }
+        w.rec_end = n_records;
+        waves.push_back(w);
+    }
+    uint64_t max_bytes = 16, max_units = 1;
+    for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
+    const uint64_t buf_bytes = ((max_bytes + 15) / 16) * 16 + 16;
+
+    const int nbuf = waves.size() > 1 ? 2 : 1;
+    DevBuf<uint8_t> d_stream[2];
+    PinnedBuf<uint8_t> staging[2];
+    DevBuf<uint64_t> d_hashes; DevBuf<uint32_t> d_counts, d_n;
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; b++) {
+        if (d_stream[b].alloc(buf_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (stream buffer %llu B)", (unsigned long long)buf_bytes);
+        MG_CUDA(ctx, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    }
+    if (d_hashes.alloc(max_units * s) != cudaSuccess || d_n.alloc(max_units) != cudaSuccess ||
+        (out_counts && d_counts.alloc(max_units * s) != cudaSuccess))
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+
+    std::vector<std::vector<uint64_t>> wave_unit_start(waves.size());
+    auto issue_copy = [&](size_t wi) -> int {
+        const Wave &w = waves[wi];
+        const int b = (int)(wi % nbuf);
+        uint8_t *dst = d_stream[b].p;
+        // staging size: all small records of the wave
+        uint64_t small_bytes = 0;
+        for (uint64_t r = w.rec_begin; r < w.rec_end; r++)
+            if (len[r] >= k && len[r] < DIRECT_COPY_MIN) small_bytes += len[r] + 1;
+        if (staging[b].n < small_bytes && staging[b].alloc(small_bytes) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)small_bytes);
+        std::vector<uint64_t> &us = wave_unit_start[wi];
+        us.assign(w.unit_end - w.unit_begin + 1, 0);
+        uint64_t off = 0, st_off = 0;
+        uint64_t run_dst = 0, run_src = 0, run_len = 0;   // pending staged run
+        auto flush_run = [&]() -> cudaError_t {
+            if (!run_len) return cudaSuccess;
+            cudaError_t e = cudaMemcpyAsync(dst + run_dst, staging[b].p + run_src, run_len, cudaMemcpyHostToDevice, ctx->copy_stream);
+            run_len = 0;
+            return e;
+        };
+        for (uint64_t u = w.unit_begin; u < w.unit_end; u++) {
+            us[u - w.unit_begin] = off;
+            for (uint64_t r = unit_rec_begin[u]; r < unit_rec_begin[u + 1]; r++) {
+                if (len[r] < k) continue;
+                if (len[r] >= DIRECT_COPY_MIN) {
+                    MG_CUDA(ctx, flush_run());
+                    MG_CUDA(ctx, cudaMemcpyAsync(dst + off, seq[r], len[r], cudaMemcpyHostToDevice, ctx->copy_stream));
+                    MG_CUDA(ctx, cudaMemsetAsync(dst + off + len[r], 0, 1, ctx->copy_stream));
+                } else {
+                    if (!run_len) { run_dst = off; run_src = st_off; }
+                    memcpy(staging[b].p + st_off, seq[r], len[r]);
+                    staging[b].p[st_off + len[r]] = 0;
+                    st_off += len[r] + 1;
+                    run_len += len[r] + 1;
+                }
+                off += len[r] + 1;
+            }
+        }
+        MG_CUDA(ctx, flush_run());
+        us[w.unit_end - w.unit_begin] = off;
+        MG_CUDA(ctx, cudaEventRecord(copied[b], ctx->copy_stream));
+        return MASHGPU_OK;
+    };
+
+    MG_TRY(issue_copy(0));
+    int rc = MASHGPU_OK;
+    for (size_t wi = 0; wi < waves.size() && rc == MASHGPU_OK; wi++) {
+        const Wave &w = waves[wi];
+        const int b = (int)(wi % nbuf);
+        if (wi + 1 < waves.size()) rc = issue_copy(wi + 1);    // overlaps with this wave's kernels
+        if (rc != MASHGPU_OK) break;
+        MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, copied[b], 0));
+        const uint64_t nu = w.unit_end - w.unit_begin;
+        SketchStream S;
+        S.d_stream = d_stream[b].p; S.unit_start = wave_unit_start[wi].data(); S.n_units = nu;
+        rc = sketch_stream_core(ctx, params, S, d_hashes.p, out_counts ? d_counts.p : nullptr, d_n.p, ctx->stream, nullptr);
+        if (rc != MASHGPU_OK) break;
+        MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.unit_begin * s, d_hashes.p, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.unit_begin, d_n.p, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_counts)
+            MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.unit_begin * s, d_counts.p, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int b = 0; b < nbuf; b++) if (copied[b]) cudaEventDestroy(copied[b]);
+    return rc;
+}
+
+extern "C" int mashgpu_hash_windows(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                    const char *seq, uint64_t len, uint64_t *out_hash, uint8_t *out_valid)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    const uint64_t k = (uint64_t)params->kmer_size;
+    if (len < k) return MASHGPU_OK;
+    if (!seq || !out_hash || !out_valid) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nwin = len - k + 1;
+    DevBuf<uint8_t> d_seq, d_valid; DevBuf<uint64_t> d_hash;
+    const uint64_t padded = ((len + 15) / 16) * 16;
+    if (d_seq.alloc(padded) != cudaSuccess || d_valid.alloc(len) != cudaSuccess || d_hash.alloc(len) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory");
+    cudaStream_t st = ctx->stream;
+    MG_CUDA(ctx, cudaMemcpyAsync(d_seq.p, seq, len, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_valid.p, 0, len, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_hash.p, 0, len * 8, st));
+    ScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.stream = d_seq.p; a.stream_len = len;
+    a.tile_begin = 0; a.tile_end = (len + SCAN_TILE - 1) / SCAN_TILE;
+    a.coarse_t = EMPTY_KEY;
+    a.seed = params->seed; a.use64 = params->use64; a.preserve_case = params->preserve_case;
+    a.mode = SCAN_DUMP; a.only_unit = -1;
+    a.out_hash = d_hash.p; a.out_valid = d_valid.p;
+    MG_TRY(launch_scan(ctx, params, a, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(out_hash, d_hash.p, nwin * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(out_valid, d_valid.p, nwin, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    return MASHGPU_OK;
+}

@@ -1,0 +1,30 @@
+// sketch_core.cuh -- internal interface between sketch.cu and screen.cu
+#pragma once
+#include "common.cuh"
+
+namespace mashgpu {
+
+// A device-resident byte stream split into sketch units.
+struct SketchStream {
+    const void *d_stream = nullptr;
+    const uint64_t *unit_start = nullptr;   // host, n_units + 1
+    uint64_t n_units = 0;
+    bool force_keep_all = false;
+    bool t_cap = false;                     // clamp every unit threshold to t_cap_value (screen: running s-th smallest)
+    uint64_t t_cap_value = 0;
+};
+
+// Reference hash table of a screen job (distinct keys + hit counters)
+struct ScreenProbe {
+    const uint64_t *keys;
+    uint32_t *cnt;
+    uint32_t log2cap;
+    uint64_t hmax;
+};
+
+int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p);
+int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S,
+                       uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
+                       const ScreenProbe *probe);
+
+}  // namespace mashgpu

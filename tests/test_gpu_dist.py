@@ -1,0 +1,136 @@
+"""GPU parity tests for hot path 2 (compareSketches / pValue), through the C ABI.
+Bit-exact: numer (shared hashes), denom, pass.  Doubles: 1e-12 (relative for p-values, which span 300 decades)."""
+import numpy as np
+import pytest
+
+from fixtures import synth_sketches, fmt_g
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def check_against_oracle(res, want, max_distance=1.0):
+    assert np.array_equal(res["pass"], want["pass"].astype(bool))
+    filled = want["filled"].astype(bool)
+    assert np.array_equal(res["numer"][filled], want["numer"][filled])
+    assert np.array_equal(res["denom"][filled], want["denom"][filled])
+    d_g, d_o = res["distance"][filled], want["distance"][filled]
+    assert np.all(np.abs(d_g - d_o) <= TOL)
+    p_g, p_o = res["pvalue"][filled], want["pvalue"][filled]
+    big = p_o > 1e-290
+    assert np.all(np.abs(p_g[big] - p_o[big]) <= TOL * p_o[big])
+    assert np.all(p_g[~big] <= 1e-289)
+
+
+def test_golden_dist_lines(gpu, oracle, golden):
+    # BASELINE config 1: `mash dist genomes.msh reads.msh` -> test/ref/genomes.dist, plus the tutorial values
+    p = gpu.params(k=21, s=1000)
+    recs, uor = [], []
+    for u, (_, rs) in enumerate(golden.genomes):
+        for r in rs:
+            recs.append(r[2]); uor.append(u)
+    reads = golden.reads_round_robin()
+    recs += reads; uor += [3] * len(reads)
+    h, n, length = gpu.sketch(recs, p, unit_of_record=uor, n_units=4)
+    length[3] = int(np.uint64(2.0 ** 64 * float(n[3]) / float(h[3, n[3] - 1])))      # -r: estimateSetSize
+    res = gpu.dist(h[:3], n[:3], length[:3], h[3:], n[3:], length[3:], sketch_size=1000, k=21, kmer_space=p.kmer_space)
+    for i, line in enumerate(golden.dist_lines):
+        got = [fmt_g(res["distance"][0, i]), fmt_g(res["pvalue"][0, i]), f"{res['numer'][0, i]}/{res['denom'][0, i]}"]
+        assert got == line[2:5]
+    res = gpu.dist(h[:3], n[:3], length[:3], sketch_size=1000, k=21, kmer_space=p.kmer_space)   # genomes all-vs-all
+    assert (fmt_g(res["distance"][1, 0]), fmt_g(res["pvalue"][1, 0]), res["numer"][1, 0], res["denom"][1, 0]) == ("0.0222766", "0", 456, 1000)
+    assert (fmt_g(res["distance"][2, 0]), res["numer"][2, 0], res["denom"][2, 0]) == ("0", 1000, 1000)
+
+
+@pytest.mark.parametrize("s,k", [(1000, 21), (400, 16), (50, 11), (1, 21), (1030, 32)])
+def test_grid_matches_oracle(gpu, oracle, s, k):
+    H, N, L = synth_sketches(70, s, seed=3 + s, n_families=3, ragged=True)
+    Hq, Nq, Lq = synth_sketches(45, s, seed=99 + s, n_families=3, ragged=True)
+    Hq[:10] = H[:10]; Nq[:10] = N[:10]          # some identical pairs
+    ks = 4.0 ** k
+    res = gpu.dist(H, N, L, Hq, Nq, Lq, sketch_size=s, k=k, kmer_space=ks)
+    want = oracle.compare_all(H, N, L, Hq, Nq, Lq, s, k, ks)
+    check_against_oracle(res, want)
+
+
+def test_self_grid_and_row_ranges(gpu, oracle):
+    H, N, L = synth_sketches(130, 1000, seed=5, n_families=5, ragged=True)
+    ks = 4.0 ** 21
+    want = oracle.compare_all(H, N, L, H, N, L, 1000, 21, ks)
+    job = gpu.dist_open(H, N, L, sketch_size=1000, k=21, kmer_space=ks)
+    try:
+        full = job.run(0, 130)
+        check_against_oracle(full, want)
+        part = job.run(37, 50)                  # the reference's chunked `compare` jobs enumerate sub-ranges the same way
+        for key in ("numer", "denom", "distance", "pvalue", "pass"):
+            assert np.array_equal(part[key], full[key][37:87])
+    finally:
+        job.close()
+    # symmetry + diagonal (size-independent properties)
+    assert np.array_equal(full["numer"], full["numer"].T)
+    full_rows = N == 1000
+    assert np.all(np.diag(full["distance"])[N > 0] == 0)
+    assert np.all(np.diag(full["numer"]) == np.minimum(N, 1000))
+
+
+def test_thresholds(gpu, oracle):
+    # -d / -v filters: pass flags identical; filtered-by-distance pairs are left "unset" by the reference
+    H, N, L = synth_sketches(60, 500, seed=8, n_families=2)
+    ks = 4.0 ** 21
+    for md, mp in ((0.05, 1.0), (1.0, 1e-10), (0.2, 1e-3), (-1.0, -1.0)):
+        res = gpu.dist(H, N, L, sketch_size=500, k=21, kmer_space=ks, max_distance=md, max_pvalue=mp)
+        want = oracle.compare_all(H, N, L, H, N, L, 500, 21, ks, max_distance=md, max_pvalue=mp)
+        check_against_oracle(res, want)
+
+
+def test_sketch_size_smaller_than_lists(gpu, oracle):
+    # query/ref sketched with different s: sketchSize = min (CommandDistance.cpp:313-315); lists longer than it
+    H, N, L = synth_sketches(40, 1000, seed=21, n_families=2)
+    ks = 4.0 ** 21
+    res = gpu.dist(H, N, L, sketch_size=300, k=21, kmer_space=ks)
+    want = oracle.compare_all(H, N, L, H, N, L, 300, 21, ks)
+    check_against_oracle(res, want)
+
+
+def test_empty_and_tiny_sets(gpu, oracle):
+    ks = 4.0 ** 21
+    H = np.full((3, 8), np.uint64(2**64 - 1)); N = np.array([0, 3, 8], np.uint32); L = np.array([1000, 2000, 3000], np.uint64)
+    H[1, :3] = [5, 9, 100]
+    H[2] = [1, 5, 7, 9, 11, 100, 200, 300]
+    res = gpu.dist(H, N, L, sketch_size=8, k=21, kmer_space=ks)
+    want = oracle.compare_all(H, N, L, H, N, L, 8, 21, ks)
+    check_against_oracle(res, want)
+    assert res["denom"][0, 0] == 0 and res["distance"][0, 0] == 0 and res["pvalue"][0, 0] == 1.0
+
+
+def test_pvalue_device_vs_mpmath(gpu, golden):
+    # the device binomial tail against the 50-digit fixtures, driven through dist with crafted sketches:
+    # ref = {0..n-1}, qry shares exactly x of them -> numer = x, denom = n, r from the lengths
+    cases = [c for c in golden.pvalue_cases if c["n"] <= 1030 and 1 <= c["x"] <= c["n"]]
+    worst = 0.0
+    for c in cases[::3]:
+        n, x, r = c["n"], c["x"], float(c["r"])
+        # lengths with pX = pY = p0: r = p0 / (2 - p0)  ->  p0 = 2r/(1+r);  L = K p0/(1-p0)
+        k = 21; K = 4.0 ** k
+        p0 = 2 * r / (1 + r)
+        Lf = K * p0 / (1 - p0)
+        if not (1 <= Lf < 2**62):
+            continue
+        Li = int(round(Lf))
+        pX = 1. / (1. + K / Li)
+        r_eff = pX * pX / (pX + pX - pX * pX)
+        import mpmath as mp
+        mp.mp.dps = 50
+        truth = float(mp.betainc(x, n - x + 1, 0, mp.mpf(r_eff), regularized=True))
+        ref = np.arange(0, 2 * n, 2, dtype=np.uint64)[None, :]            # even numbers
+        q = ref.copy(); q[0, x:] += 1                                      # first x shared, the rest odd (distinct)
+        q.sort(axis=1)
+        res = gpu.dist(ref, [n], [Li], q, [n], [Li], sketch_size=n, k=k, kmer_space=K)
+        if res["numer"][0, 0] != x or res["denom"][0, 0] != n:
+            continue                                                       # merge stopped early: different x, skip
+        got = res["pvalue"][0, 0]
+        if truth > 1e-290:
+            worst = max(worst, abs(got - truth) / truth)
+            assert abs(got - truth) <= TOL * truth, (c, got, truth)
+    assert worst < 1e-12

@@ -1,0 +1,80 @@
+"""GPU parity tests for hot path 3 (screen), through the C ABI, against the oracle and test/ref/screen."""
+import numpy as np
+import pytest
+
+from fixtures import synth_genome, mutate, fmt_g
+
+pytestmark = pytest.mark.gpu
+
+
+def run_screen(gpu, ref, ref_n, p, chunks):
+    job = gpu.screen_open(ref, ref_n, p)
+    try:
+        for c in chunks:
+            job.feed(c)
+        return job.finish()
+    finally:
+        job.close()
+
+
+def check(res, want):
+    assert res["set_size"] == want["set_size"]
+    assert np.array_equal(res["mixture"], want["mixture"])
+    assert np.array_equal(res["shared"], want["shared"])
+    assert np.array_equal(res["median"], want["median"])
+    assert np.all(np.abs(res["identity"] - want["identity"]) <= 1e-12)
+    po, pg = want["pvalue"], res["pvalue"]
+    big = po > 1e-290
+    assert np.all(np.abs(pg[big] - po[big]) <= 1e-12 * po[big])
+    assert np.all(pg[~big] <= 1e-289)
+
+
+def test_golden_screen(gpu, golden):
+    # BASELINE config 1: `mash screen genomes.msh reads1.fastq reads2.fastq` -> test/ref/screen
+    p = gpu.params(k=21, s=1000)
+    ref = np.stack([golden.golden_sketch(i)[0] for i in range(3)])
+    reads = [r for r in golden.reads_round_robin() if len(r) >= 21]
+    chunk = b"".join(b"*" + r for r in reads)           # CommandScreen.cpp:224-262
+    res = run_screen(gpu, ref, np.full(3, 1000, np.uint32), p, [chunk])
+    for i, line in enumerate(golden.screen_lines):
+        got = [fmt_g(res["identity"][i]), f"{res['shared'][i]}/1000", str(res["median"][i]), fmt_g(res["pvalue"][i])]
+        assert got == line[:4]
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (16, 200), (11, 64)])
+def test_synthetic_screen_matches_oracle(gpu, oracle, k, s):
+    p = gpu.params(k=k, s=s)
+    po = oracle.params(k=k)
+    genomes = [synth_genome(40 + i, 150_000) for i in range(4)]
+    genomes.append(mutate(genomes[0], 0.02, 7))
+    ref = np.full((len(genomes) + 1, s), np.uint64(2**64 - 1)); ref_n = np.zeros(len(genomes) + 1, np.uint32)
+    for i, g in enumerate(genomes):
+        h, _, _ = oracle.sketch_unit([bytes(g)], po, s=s)
+        ref[i, :h.size] = h; ref_n[i] = h.size
+    # last reference: a short sketch (fewer than s hashes)
+    h, _, _ = oracle.sketch_unit([bytes(synth_genome(999, 300))], po, s=s)
+    ref[-1, :h.size] = h; ref_n[-1] = h.size
+    rng = np.random.Generator(np.random.PCG64(4242))
+    reads = []
+    for _ in range(6000):
+        g = genomes[int(rng.integers(0, 2))]
+        a = int(rng.integers(0, g.size - 150))
+        r = g[a:a + 150].copy()
+        if rng.random() < 0.1:
+            r[int(rng.integers(0, 150))] = ord("N")
+        if rng.random() < 0.05:
+            r = r[:int(rng.integers(1, 40))]                # shorter than k sometimes
+        reads.append(bytes(r))
+    kept = [r for r in reads if len(r) >= k]
+    chunks = [b"".join(b"*" + r for r in kept[i:i + 1500]) for i in range(0, len(kept), 1500)]
+    want = oracle.screen(ref, ref_n, chunks, po, s=s)
+    check(run_screen(gpu, ref, ref_n, p, chunks), want)
+    # chunking invariance (the reference flushes every 1 MiB; any split gives the same answer)
+    check(run_screen(gpu, ref, ref_n, p, [b"".join(chunks)]), want)
+
+
+def test_empty_stream(gpu, oracle):
+    p = gpu.params(k=21, s=100)
+    ref = np.arange(1, 101, dtype=np.uint64)[None, :] * np.uint64(1 << 40)
+    res = run_screen(gpu, ref, np.array([100], np.uint32), p, [b"*NNNNNNNNNNNNNNNNNNNNNNNNNNNNNN"])
+    assert res["set_size"] == 0 and res["shared"][0] == 0 and res["pvalue"][0] == 1.0 and res["identity"][0] == 0.0

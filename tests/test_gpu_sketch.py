@@ -1,0 +1,148 @@
+"""GPU parity tests for hot path 1 (sketching), through the C ABI, against the oracle and the
+reference's golden files.  Bit-exact: hashes, sketch sets, lengths."""
+import numpy as np
+import pytest
+
+from fixtures import synth_genome, mutate
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_sketch_equal(gpu_out, u, oracle_h):
+    h, n, _ = gpu_out[:3]
+    assert n[u] == oracle_h.size
+    assert np.array_equal(h[u, :n[u]], oracle_h)
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+@pytest.mark.parametrize("noncanonical", [False, True])
+def test_every_window_hash_matches_oracle(gpu, oracle, k, noncanonical):
+    # getHash over every window, all k, both strands modes, with N runs / lower case / junk bytes
+    seq = synth_genome(1000 + k, 20_000, n_runs=4, lower_frac=0.1)
+    seq[5000:5003] = np.frombuffer(b"*-\x00", np.uint8)
+    seq[17000] = 200
+    p = gpu.params(k=k, s=100, noncanonical=noncanonical)
+    po = oracle.params(k=k, noncanonical=noncanonical)
+    assert p.use64 == po.use64
+    h, v = gpu.hash_windows(seq, p)
+    want = oracle.all_hashes(bytes(seq), po)
+    assert int(v.sum()) == want.size
+    assert np.array_equal(h[v], want)
+
+
+def test_preserve_case_skips_lower_case(gpu, oracle):
+    seq = synth_genome(77, 30_000, lower_frac=0.02)
+    p = gpu.params(k=21, s=100, preserve_case=True)
+    po = oracle.params(k=21, preserve_case=True)
+    h, v = gpu.hash_windows(seq, p)
+    want = oracle.all_hashes(bytes(seq), po)
+    assert int(v.sum()) == want.size and np.array_equal(h[v], want)
+
+
+def test_golden_genomes_bit_exact(gpu, golden):
+    # BASELINE config 1: `mash sketch genome1.fna genome2.fna genome3.fna` -> test/ref/genomes.json
+    p = gpu.params(k=21, s=1000, seed=42)
+    recs, uor = [], []
+    for u, (_, rs) in enumerate(golden.genomes):
+        for r in rs:
+            recs.append(r[2]); uor.append(u)
+    h, n, length = gpu.sketch(recs, p, unit_of_record=uor, n_units=3)
+    for i in range(3):
+        gh, glen, _, _ = golden.golden_sketch(i)
+        assert length[i] == glen
+        assert n[i] == 1000 and np.array_equal(h[i], gh)
+
+
+def test_golden_reads_sketch_bit_exact(gpu, golden):
+    # `mash sketch -r reads1.fastq reads2.fastq`: one unit over all reads; length = estimateSetSize (host formula)
+    p = gpu.params(k=21, s=1000, seed=42)
+    reads = golden.reads_round_robin()
+    h, n, _ = gpu.sketch(reads, p, unit_of_record=[0] * len(reads), n_units=1)
+    gh, glen = golden.golden_reads_sketch()
+    assert n[0] == 1000 and np.array_equal(h[0], gh)
+    est = int(np.uint64(2.0 ** 64 * float(n[0]) / float(h[0, n[0] - 1])))     # MinHashHeap.h:45
+    assert est == glen
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (16, 400), (11, 10), (32, 1000), (21, 10), (17, 2000), (8, 50), (3, 1000), (1, 5)])
+def test_synthetic_units_match_oracle(gpu, oracle, k, s):
+    # ragged batch: big / tiny / empty / shorter-than-k records, multi-record units, soft-masking, N runs
+    p = gpu.params(k=k, s=s)
+    po = oracle.params(k=k)
+    g0 = synth_genome(1, 300_000, n_runs=5, lower_frac=0.05)
+    units = [
+        [bytes(g0)],
+        [bytes(mutate(g0, 0.01, 2))],
+        [bytes(synth_genome(3, 50_000)), b"ACGT", bytes(synth_genome(4, 1234)), b""],   # multi record
+        [b"A" * 5000],                                                                    # one k-mer repeated
+        [b"ACGTACGTAC" * 300],                                                            # few distinct k-mers
+        [b"N" * 1000],                                                                    # nothing valid
+        [b"ACG"],                                                                         # shorter than k (for k > 3)
+        [bytes(synth_genome(5, 700))],                                                    # fewer k-mers than s
+        [],                                                                               # unit without records
+    ]
+    recs, uor = [], []
+    for u, rs in enumerate(units):
+        for r in rs:
+            recs.append(r); uor.append(u)
+    out = gpu.sketch(recs, p, unit_of_record=uor, n_units=len(units), counts=True)
+    for u, rs in enumerate(units):
+        oh, oc, olen = oracle.sketch_unit(rs, po, s=s, counts=True)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)
+
+
+def test_counts_match_true_multiplicity(gpu, oracle):
+    # Multiplicities (HashSet counts). The reference's top-of-heap quirk can only under-count the LAST entry
+    # (SURVEY.md 8 a5); every other entry must equal the oracle's count exactly.
+    p = gpu.params(k=8, s=50)
+    po = oracle.params(k=8)
+    g = bytes(synth_genome(9, 100_000))
+    h, n, _, c = gpu.sketch([g], p, counts=True)
+    oh, oc, _ = oracle.sketch_unit([g], po, s=50, counts=True)
+    assert np.array_equal(h[0, :n[0]], oh)
+    assert np.array_equal(c[0, :n[0] - 1], oc[:-1])
+    assert c[0, n[0] - 1] >= oc[-1]
+
+
+def test_one_unit_per_record_order_preserved(gpu, oracle):
+    # `-i` mode: one sketch per record, outputs in input order (ThreadPool ordering contract)
+    p = gpu.params(k=21, s=200)
+    po = oracle.params(k=21)
+    recs = [bytes(synth_genome(100 + i, 20_000 + 997 * i)) for i in range(40)]
+    out = gpu.sketch(recs, p)
+    for u, r in enumerate(recs):
+        oh, _, olen = oracle.sketch_unit([r], po, s=200)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)
+
+
+def test_highly_repetitive_unit_takes_exact_rerun(gpu, oracle):
+    # a long unit with few distinct k-mers: the threshold pass finds < s survivors and the exact re-run must kick in
+    p = gpu.params(k=21, s=1000)
+    po = oracle.params(k=21)
+    unit = bytes(np.tile(synth_genome(5, 3000), 200))           # 600 kbp, ~3000 distinct k-mers
+    before = gpu.stats()["exact_reruns"]
+    out = gpu.sketch([unit], p)
+    oh, _, _ = oracle.sketch_unit([unit], po, s=1000)
+    assert_sketch_equal(out, 0, oh)
+    assert gpu.stats()["exact_reruns"] > before
+
+
+def test_union_property_full_size(gpu):
+    # size-independent property at BASELINE's unit size (5 Mbp): bottom-s(A ++ B) == bottom-s(bottom-s(A) U bottom-s(B))
+    p = gpu.params(k=21, s=1000)
+    a = synth_genome(20260923, 5_000_000)
+    b = synth_genome(20260924, 5_000_000)
+    h, n, _ = gpu.sketch([bytes(a), bytes(b), bytes(a), bytes(b)], p, unit_of_record=[0, 1, 2, 2], n_units=3)
+    assert n[0] == n[1] == n[2] == 1000
+    merged = np.unique(np.concatenate([h[0], h[1]]))[:1000]
+    assert np.array_equal(h[2], merged)
+    assert np.all(np.diff(h[2].astype(object)) > 0)      # ascending, distinct
+
+
+def test_unsupported_alphabet_is_loud(gpu):
+    import mash_b200
+    p = gpu.params(k=9, s=100, alphabet=mash_b200.ALPHABET_PROTEIN, noncanonical=True)
+    with pytest.raises(mash_b200.MashGpuError):
+        gpu.sketch([b"MKVLAAGIVALLLAAGCSSAPQ"], p)
