@@ -80,8 +80,10 @@ __device__ __forceinline__ bool table_add(uint64_t *keys, uint32_t *cnt, uint32_
 }
 
 // Slow path: a hash passed the tile's coarse threshold.
-static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint64_t hash, uint64_t pos)
+static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_lo, uint32_t hash_hi, uint64_t tile_base, uint32_t local_pos)
 {
+    const uint64_t hash = ((uint64_t)hash_hi << 32) | hash_lo;
+    const uint64_t pos = tile_base + local_pos;
     if (a.mode == SCAN_DUMP) {
         a.out_hash[pos] = hash;
         a.out_valid[pos] = 1;
@@ -129,6 +131,14 @@ __device__ __forceinline__ uint32_t ascii4_to_nibbles(uint32_t w, uint32_t fold)
     return x;
 }
 
+// PRMT in its native 4-bit-selector form (bit 3 of a selector nibble = sign replicate; never set for valid codes)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t nibble_reverse(uint32_t x)
 {
     x = __byte_perm(x, 0, 0x0123);
@@ -157,13 +167,12 @@ struct KmerShape {
 
 // nibble words (codes 0..3) -> ASCII words, bytes >= K zeroed
 template <int K>
-__device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::NW], uint32_t (&a)[KmerShape<K>::NA])
+__device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::NW], uint32_t (&a)[KmerShape<K>::NA], uint32_t POOL)
 {
-    constexpr uint32_t POOL = 0x54474341u;  // bytes 'A','C','G','T'
 #pragma unroll
     for (int i = 0; i < KmerShape<K>::NW; i++) {
-        uint32_t lo = __byte_perm(POOL, 0, c[i]);
-        uint32_t hi = __byte_perm(POOL, 0, c[i] >> 16);
+        uint32_t lo = prmt(POOL, 0, c[i]);
+        uint32_t hi = prmt(POOL, 0, c[i] >> 16);
         const int rem_lo = K - 8 * i;      // bases left for word 2i
         const int rem_hi = K - 8 * i - 4;  // bases left for word 2i+1
         if (rem_lo < 4) lo &= (1u << (8 * rem_lo)) - 1u;
@@ -176,7 +185,7 @@ __device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::N
 
 template <int K, bool CANON, int J>
 __device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW],
-                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t pos0, uint64_t tmax)
+                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t tile_base, uint32_t local0, uint64_t tmax, uint32_t pool)
 {
     using S = KmerShape<K>;
     uint32_t f[S::NW];
@@ -197,23 +206,33 @@ __device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&
             r[i] = block_word<RO, S::BW>(rb, i);
             if (i == S::NW - 1) r[i] &= S::LAST_MASK;
         }
-        // fwd <= rc as little-endian integers  <=>  memcmp(fwd, rc, k) <= 0   (Sketch.cpp:569-571)
-        bool use_fwd = true;   // equal -> forward
-#pragma unroll
-        for (int i = 0; i < S::NW; i++) {   // from least to most significant: the last differing word decides
-            if (f[i] != r[i]) use_fwd = f[i] < r[i];
+        // rc < fwd as little-endian multi-word integers  <=>  memcmp(fwd, rc, k) > 0  (Sketch.cpp:569-571):
+        // borrow out of rc - fwd.  m = all-ones when the reverse complement is the canonical k-mer.
+        uint32_t m;
+        if (S::NW == 1) {
+            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, 0, 0;\n\t}" : "=r"(m) : "r"(r[0]), "r"(f[0]));
+        } else if (S::NW == 2) {
+            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.cc.u32 t, %3, %4;\n\tsubc.u32 %0, 0, 0;\n\t}"
+                : "=r"(m) : "r"(r[0]), "r"(f[0]), "r"(r[S::NW > 1 ? 1 : 0]), "r"(f[S::NW > 1 ? 1 : 0]));
+        } else if (S::NW == 3) {
+            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.cc.u32 t, %3, %4;\n\tsubc.cc.u32 t, %5, %6;\n\tsubc.u32 %0, 0, 0;\n\t}"
+                : "=r"(m) : "r"(r[0]), "r"(f[0]), "r"(r[S::NW > 1 ? 1 : 0]), "r"(f[S::NW > 1 ? 1 : 0]), "r"(r[S::NW > 2 ? 2 : 0]), "r"(f[S::NW > 2 ? 2 : 0]));
+        } else {
+            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.cc.u32 t, %3, %4;\n\tsubc.cc.u32 t, %5, %6;\n\tsubc.cc.u32 t, %7, %8;\n\tsubc.u32 %0, 0, 0;\n\t}"
+                : "=r"(m) : "r"(r[0]), "r"(f[0]), "r"(r[S::NW > 1 ? 1 : 0]), "r"(f[S::NW > 1 ? 1 : 0]), "r"(r[S::NW > 2 ? 2 : 0]), "r"(f[S::NW > 2 ? 2 : 0]),
+                  "r"(r[S::NW > 3 ? 3 : 0]), "r"(f[S::NW > 3 ? 3 : 0]));
         }
 #pragma unroll
-        for (int i = 0; i < S::NW; i++) c[i] = use_fwd ? f[i] : r[i];
+        for (int i = 0; i < S::NW; i++) c[i] = (f[i] & ~m) | (r[i] & m);
     } else {
 #pragma unroll
         for (int i = 0; i < S::NW; i++) c[i] = f[i];
     }
     uint32_t asc[S::NA];
-    expand_ascii<K>(c, asc);
-    uint64_t h = murmur3_h1<K, S::NA>(asc, a.seed);
-    if (!a.use64) h &= 0xFFFFFFFFULL;
-    if (valid && h <= tmax) scan_emit(a, h, pos0 + J);
+    expand_ascii<K>(c, asc, pool);
+    u64x2 h = murmur3_h1<K, S::NA>(asc, a.seed);
+    if (K <= 16) h.hi = 0;        // 32-bit hashes: |{A,C,G,T}|^k <= 2^32 (reference Sketch.cpp:1136, hash.cpp:31-35)
+    if (valid && (((uint64_t)h.hi << 32) | h.lo) <= tmax) scan_emit(a, h.lo, h.hi, tile_base, local0 + J);
 }
 
 template <int K, bool CANON>
@@ -222,6 +241,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ScanArgs a)
     using S = KmerShape<K>;
     __shared__ uint32_t sm[SCAN_WORDS];
     const uint32_t fold = a.preserve_case ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+    uint32_t pool;   // bytes 'A','C','G','T' for PRMT; opaque to the compiler so that it stays in one register
+    asm volatile("mov.u32 %0, 0x54474341;" : "=r"(pool));
 
     for (uint64_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
         const uint64_t base = tile * (uint64_t)SCAN_TILE;
@@ -253,15 +274,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ScanArgs a)
 #pragma unroll
                 for (int i = 0; i < S::BW; i++) rb[i] = nibble_reverse(b[S::BW - 1 - i]) ^ 0x33333333u;
             }
-            const uint64_t pos0 = base + 8ull * g;
-            scan_window<K, CANON, 0>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 1>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 2>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 3>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 4>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 5>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 6>(a, b, rb, pos0, tmax);
-            scan_window<K, CANON, 7>(a, b, rb, pos0, tmax);
+            const uint32_t local0 = 8u * g;
+            scan_window<K, CANON, 0>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 1>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 2>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 3>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 4>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 5>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 6>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 7>(a, b, rb, base, local0, tmax, pool);
         }
         __syncthreads();
     }

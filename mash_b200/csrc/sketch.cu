@@ -156,6 +156,8 @@ int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p)
     int n = 0;
     for (int i = 0; i < 256; i++) n += p->alphabet[i] != 0;
     bool dna = n == 4 && p->alphabet['A'] && p->alphabet['C'] && p->alphabet['G'] && p->alphabet['T'];
+    if (dna && (p->use64 != 0) != (p->kmer_size > 16))
+        return fail(ctx, MASHGPU_ERR_INVALID, "use64=%d contradicts the reference rule alphabetSize^k > 2^32 for k=%d (Sketch.cpp:1136)", p->use64, p->kmer_size);
     if (!dna)
         return fail(ctx, MASHGPU_ERR_UNSUPPORTED,
                     "alphabet other than {A,C,G,T} is not on the GPU path yet (byte-alphabet kernels pending)");
