@@ -388,7 +388,7 @@ def main():
         torch.cuda.synchronize()
         open_ms = (time.perf_counter() - t_open) * 1e3
         n_ref, n_qry = job.n_ref, job.n_qry
-        q_tile = max(1, min(n_qry, (1 << 27) // max(1, n_ref)))
+        q_tile = max(1, min(n_qry, (1 << 29) // max(1, n_ref)))   # 2^29 pairs = 13.4 GB of dense outputs per launch
         o_numer = torch.empty(q_tile * n_ref, dtype=torch.int32, device=dev)
         o_denom = torch.empty(q_tile * n_ref, dtype=torch.int32, device=dev)
         o_dist = torch.empty(q_tile * n_ref, dtype=torch.float64, device=dev)

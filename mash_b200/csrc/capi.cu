@@ -53,6 +53,10 @@ extern "C" void mashgpu_destroy(mashgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (auto *list : {&ctx->scan_events, &ctx->dist_events})
         for (auto &ev : *list) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (int b = 0; b < 2; b++) {
+        if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
+        if (ctx->wave_copied[b]) cudaEventDestroy(ctx->wave_copied[b]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;

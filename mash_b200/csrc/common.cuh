@@ -16,6 +16,33 @@ struct EventPair { cudaEvent_t a, b; };
 
 }  // namespace mashgpu
 
+namespace mashgpu {
+// grow-only device scratch owned by the context (no cudaMalloc/cudaFree on the hot path after warm-up)
+struct Scratch {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~Scratch() { if (p) cudaFree(p); }
+    template <typename T>
+    T *get(size_t count)
+    {
+        size_t need = count * sizeof(T);
+        if (need == 0) need = 16;
+        if (need > bytes) {
+            if (p) cudaFree(p);
+            p = nullptr; bytes = 0;
+            size_t want = need + need / 8;
+            if (cudaMalloc(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+                want = need;
+            }
+            bytes = want;
+        }
+        return reinterpret_cast<T *>(p);
+    }
+};
+}  // namespace mashgpu
+
 struct mashgpu_ctx {
     int device = 0;
     int sm_count = 148;
@@ -28,6 +55,13 @@ struct mashgpu_ctx {
     uint64_t scan_launches = 0, dist_launches = 0, exact_reruns = 0;
     double scan_ms = 0, dist_ms = 0;
     std::vector<mashgpu::EventPair> scan_events, dist_events;
+    // sketch_stream_core scratch
+    mashgpu::Scratch sc_start, sc_t, sc_off, sc_log2, sc_flags, sc_maxhash, sc_keys, sc_cnt, sc_tmax;
+    // mashgpu_sketch_batch: wave stream buffers and outputs
+    mashgpu::Scratch sc_wave[2], sc_out_hashes, sc_out_n, sc_out_counts;
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes[2] = {0, 0};
+    cudaEvent_t wave_copied[2] = {nullptr, nullptr};
 };
 
 namespace mashgpu {

@@ -10,6 +10,42 @@ namespace mashgpu {
 //   x * const  -> IMAD.WIDE.U32 + 2 IMAD          rotl -> 2 SHF (funnel)        add -> IADD3 + IADD3.X
 struct u64x2 { uint32_t lo, hi; };
 
+// ---- pipe balancing -----------------------------------------------------------------------------------------
+// The hot loop is bound by the ALU pipe (SHF/LOP3/IADD3/PRMT; ncu r01: alu 76 %, fma 26-31 % of peak).  Shifts,
+// rotates and 64-bit adds can also be done by the integer multiply-add unit (IMAD / IMAD.WIDE / IMAD.HI on the FMA
+// pipe) if the multiplier is a power of two -- but ptxas strength-reduces a literal power of two back into
+// SHF/LEA/IADD3.  Reading the multipliers from constant memory keeps them opaque (the IMAD takes the constant-bank
+// operand directly, no register needed).  Each MG_*_FMA switch moves one class of operations to the FMA pipe.
+// Measured on B200 (tools/scan_microbench.cu, k=21 canonical, 2 Gbp): all off 187.5 Gbp/s; rot 170.7; shr 173.2;
+// add 168.2; sel 183.4; all on 128.3 -- IMAD.WIDE/IMAD.HI cost more issue slots than the SHF/IADD3 they replace,
+// so every switch defaults to 0.  Kept as documented dead ends.
+#ifndef MG_ROT_FMA
+#define MG_ROT_FMA 0
+#endif
+#ifndef MG_SHR_FMA
+#define MG_SHR_FMA 0
+#endif
+#ifndef MG_ADD_FMA
+#define MG_ADD_FMA 0
+#endif
+#ifndef MG_SEL_FMA
+#define MG_SEL_FMA 0
+#endif
+// g_pow2[i] = 2^i (i = 0..31)
+static __constant__ uint32_t g_pow2[32] = {
+    1u << 0, 1u << 1, 1u << 2, 1u << 3, 1u << 4, 1u << 5, 1u << 6, 1u << 7, 1u << 8, 1u << 9, 1u << 10, 1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15,
+    1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21, 1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31};
+
+// x >> S on the FMA pipe: high word of x * 2^(32-S)
+template <int S>
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x)
+{
+    static_assert(S >= 1 && S <= 31, "shift");
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(g_pow2[32 - S]));
+    return r;
+}
+
 __device__ __forceinline__ u64x2 mul_const(u64x2 a, uint64_t c)
 {
     const uint32_t clo = (uint32_t)c, chi = (uint32_t)(c >> 32);
@@ -25,6 +61,14 @@ __device__ __forceinline__ u64x2 rotl(u64x2 a)
 {
     u64x2 r;
     if constexpr (R == 32) { r.lo = a.hi; r.hi = a.lo; }
+    else if constexpr (MG_ROT_FMA) {
+        // rotl by R' = R mod 32 of (h:l) [halves pre-swapped when R > 32]:  l*2^R' (wide) + {h >> (32-R'), h << R'}
+        const uint32_t l = R < 32 ? a.lo : a.hi, h = R < 32 ? a.hi : a.lo;
+        const uint32_t c = g_pow2[R & 31];
+        asm("{\n\t.reg .u64 t;\n\t.reg .u32 x, y;\n\tmul.hi.u32 x, %3, %4;\n\tmul.lo.u32 y, %3, %4;\n\tmov.b64 t, {x, y};\n\t"
+            "mad.wide.u32 t, %2, %4, t;\n\tmov.b64 {%0, %1}, t;\n\t}"
+            : "=r"(r.lo), "=r"(r.hi) : "r"(l), "r"(h), "r"(c));
+    }
     else if constexpr (R < 32) { r.hi = __funnelshift_l(a.lo, a.hi, R); r.lo = __funnelshift_l(a.hi, a.lo, R); }
     else { r.hi = __funnelshift_l(a.hi, a.lo, R - 32); r.lo = __funnelshift_l(a.lo, a.hi, R - 32); }
     return r;
@@ -33,7 +77,13 @@ __device__ __forceinline__ u64x2 rotl(u64x2 a)
 __device__ __forceinline__ u64x2 add64(u64x2 a, u64x2 b)
 {
     u64x2 r;
+#if MG_ADD_FMA
+    // a.lo * 1 + b (wide) carries into the high word; then + a.hi
+    asm("{\n\t.reg .u64 t;\n\tmov.b64 t, {%4, %5};\n\tmad.wide.u32 t, %2, %6, t;\n\tmov.b64 {%0, %1}, t;\n\tmad.lo.u32 %1, %3, %6, %1;\n\t}"
+        : "=r"(r.lo), "=&r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(g_pow2[0]));
+#else
     asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+#endif
     return r;
 }
 
@@ -49,13 +99,22 @@ __device__ __forceinline__ u64x2 mul5_add(u64x2 a, uint32_t c)
     return r;
 }
 
+__device__ __forceinline__ uint32_t shr1(uint32_t x)
+{
+#if MG_SHR_FMA
+    return shr_fma<1>(x);
+#else
+    return x >> 1;
+#endif
+}
+
 __device__ __forceinline__ u64x2 fmix(u64x2 k)
 {
-    k.lo ^= k.hi >> 1;                       // k ^= k >> 33
+    k.lo ^= shr1(k.hi);                      // k ^= k >> 33
     k = mul_const(k, 0xff51afd7ed558ccdULL);
-    k.lo ^= k.hi >> 1;
+    k.lo ^= shr1(k.hi);
     k = mul_const(k, 0xc4ceb9fe1a85ec53ULL);
-    k.lo ^= k.hi >> 1;
+    k.lo ^= shr1(k.hi);
     return k;
 }
 

@@ -23,6 +23,10 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = 8192;              // window starts per tile
 constexpr int SCAN_HALO_WORDS = 8;           // extra nibble words (64 bases) staged past the tile
 constexpr int SCAN_WORDS = SCAN_TILE / 8 + SCAN_HALO_WORDS;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_WARP_TILE = 1024;         // window starts per warp tile (32 lanes x 4 blocks x 8)
+constexpr int SCAN_WARP_WORDS = SCAN_WARP_TILE / 8 + SCAN_HALO_WORDS;   // 136 nibble words
+constexpr int SCAN_WARP_VECS = SCAN_WARP_WORDS / 2;                     // 68 16-byte vectors
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
 
 enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2 };
@@ -114,6 +118,36 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
         atomicOr(&a.unit_flags[u], 1u);
 }
 
+// Warp-uniform wrapper around the slow path.  The hot loop never branches on a per-lane condition: a window's pass
+// flag is voted, and when any lane has a survivor the whole warp enters here and serialises the survivors with
+// ballot/shuffle (lane 0 does the table work).  Keeping the main loop free of divergent branches matters: with a
+// per-lane `if (pass) emit()` the warp kept running split into sub-warps between emits (ncu: 19 active lanes on
+// average, 1.6x the warp instructions).
+// The fast path does not even test window validity (2 instructions per k-mer saved): hashes of windows that contain
+// a non-alphabet byte are garbage, and the few that slip under the threshold are rejected here by re-reading the
+// window's nibbles from the warp's shared-memory tile.  The fast-path filter only compares the high word (k > 16)
+// or the low word (k <= 16) of the hash with the tile threshold; the exact 64-bit test is in scan_emit.
+static __device__ __noinline__ void scan_emit_warp(const ScanArgs &a, bool pass, uint32_t hash_lo, uint32_t hash_hi,
+                                                   uint64_t tile_base, uint32_t local_pos, const uint32_t *sm_tile, int k,
+                                                   uint64_t tmax)
+{
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+    const int lane = threadIdx.x & 31;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t lo = __shfl_sync(0xFFFFFFFFu, hash_lo, src);
+        const uint32_t hi = __shfl_sync(0xFFFFFFFFu, hash_hi, src);
+        const uint32_t lp = __shfl_sync(0xFFFFFFFFu, local_pos, src);
+        if (lane == 0) {
+            uint32_t bad = 0;
+            for (int i = 0; i < k; i++) bad |= sm_tile[(lp + i) >> 3] >> (4 * ((lp + i) & 7));
+            if (!(bad & 8u) && ((((uint64_t)hi) << 32) | lo) <= tmax) scan_emit(a, lo, hi, tile_base, lp);
+        }
+        __syncwarp();
+    }
+}
+
 // 4 ASCII bytes -> 4 nibbles (in the low 16 bits).  Codes: A=0 C=1 G=2 T=3 (order preserving, complement = xor 3),
 // anything else 8.  `fold` = 0xDFDFDFDF to upper-case first (a..z -> A..Z is the only effect that matters), or ~0.
 __device__ __forceinline__ uint32_t ascii4_to_nibbles(uint32_t w, uint32_t fold)
@@ -172,7 +206,11 @@ __device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::N
 #pragma unroll
     for (int i = 0; i < KmerShape<K>::NW; i++) {
         uint32_t lo = prmt(POOL, 0, c[i]);
+#if MG_SEL_FMA
+        uint32_t hi = prmt(POOL, 0, shr_fma<16>(c[i]));
+#else
         uint32_t hi = prmt(POOL, 0, c[i] >> 16);
+#endif
         const int rem_lo = K - 8 * i;      // bases left for word 2i
         const int rem_hi = K - 8 * i - 4;  // bases left for word 2i+1
         if (rem_lo < 4) lo &= (1u << (8 * rem_lo)) - 1u;
@@ -185,18 +223,16 @@ __device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::N
 
 template <int K, bool CANON, int J>
 __device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW],
-                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t tile_base, uint32_t local0, uint64_t tmax, uint32_t pool)
+                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t tile_base, uint32_t local0, uint64_t tmax, uint32_t pool,
+                                            const uint32_t *sm_tile)
 {
     using S = KmerShape<K>;
     uint32_t f[S::NW];
-    uint32_t any = 0;
 #pragma unroll
     for (int i = 0; i < S::NW; i++) {
         f[i] = block_word<J, S::BW>(b, i);
         if (i == S::NW - 1) f[i] &= S::LAST_MASK;
-        any |= f[i];
     }
-    const bool valid = (any & 0x88888888u) == 0;
     uint32_t c[S::NW];
     if (CANON) {
         constexpr int RO = 8 * S::BW - K - J;   // nibble offset of the reverse-complement window
@@ -232,41 +268,82 @@ __device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&
     expand_ascii<K>(c, asc, pool);
     u64x2 h = murmur3_h1<K, S::NA>(asc, a.seed);
     if (K <= 16) h.hi = 0;        // 32-bit hashes: |{A,C,G,T}|^k <= 2^32 (reference Sketch.cpp:1136, hash.cpp:31-35)
-    if (valid && (((uint64_t)h.hi << 32) | h.lo) <= tmax) scan_emit(a, h.lo, h.hi, tile_base, local0 + J);
+    // coarse filter on one 32-bit word; validity and the exact threshold are checked in the slow path
+    const bool pass = (K <= 16) ? (h.lo <= (uint32_t)tmax) : (h.hi <= (uint32_t)(tmax >> 32));
+    if (__any_sync(0xFFFFFFFFu, pass)) scan_emit_warp(a, pass, h.lo, h.hi, tile_base, local0 + J, sm_tile, K, tmax);
 }
 
+// 16 ASCII bytes at stream offset `off` -> two nibble words (bytes at or past stream_len become separators)
+__device__ __forceinline__ uint2 stage16(const uint4 q, uint64_t off, uint64_t stream_len, uint32_t fold)
+{
+    uint32_t w0 = 0x88888888u, w1 = 0x88888888u;
+    if (off < stream_len) {
+        w0 = ascii4_to_nibbles(q.x, fold) | (ascii4_to_nibbles(q.y, fold) << 16);
+        w1 = ascii4_to_nibbles(q.z, fold) | (ascii4_to_nibbles(q.w, fold) << 16);
+        if (off + 16 > stream_len) {   // ragged end
+            const int keep = (int)(stream_len - off);   // 1..15
+            if (keep < 8) { w0 |= 0x88888888u << (4 * keep); w1 = 0x88888888u; }
+            else if (keep > 8) w1 |= 0x88888888u << (4 * (keep - 8));
+            else w1 = 0x88888888u;
+        }
+    }
+    return make_uint2(w0, w1);
+}
+
+__device__ __forceinline__ uint4 load16(const uint8_t *stream, uint64_t off, uint64_t stream_len)
+{
+    if (off < stream_len) return __ldg(reinterpret_cast<const uint4 *>(stream + off));
+    return make_uint4(0, 0, 0, 0);
+}
+
+// Warp-private tiles: every warp owns WARP_TILE window starts at a time, staged in its own slice of shared memory,
+// so the only synchronisation is __syncwarp().  The next tile's bytes are prefetched into registers before the
+// current tile is hashed (global latency hidden behind ~4000 instructions of work per lane).
 template <int K, bool CANON>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ScanArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanArgs a)
 {
     using S = KmerShape<K>;
-    __shared__ uint32_t sm[SCAN_WORDS];
+    __shared__ __align__(16) uint32_t sm_all[SCAN_WARPS][SCAN_WARP_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *sm = sm_all[warp];
     const uint32_t fold = a.preserve_case ? 0xFFFFFFFFu : 0xDFDFDFDFu;
     uint32_t pool;   // bytes 'A','C','G','T' for PRMT; opaque to the compiler so that it stays in one register
     asm volatile("mov.u32 %0, 0x54474341;" : "=r"(pool));
 
-    for (uint64_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
-        const uint64_t base = tile * (uint64_t)SCAN_TILE;
-        // stage: 16 ASCII bytes -> 2 nibble words
-        for (int v = threadIdx.x; v < SCAN_WORDS / 2; v += SCAN_THREADS) {
-            const uint64_t off = base + 16ull * v;
-            uint32_t w0 = 0x88888888u, w1 = 0x88888888u;
-            if (off < a.stream_len) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.stream + off));
-                w0 = ascii4_to_nibbles(q.x, fold) | (ascii4_to_nibbles(q.y, fold) << 16);
-                w1 = ascii4_to_nibbles(q.z, fold) | (ascii4_to_nibbles(q.w, fold) << 16);
-                if (off + 16 > a.stream_len) {   // ragged end: bytes >= stream_len are separators
-                    const int keep = (int)(a.stream_len - off);   // 1..15
-                    if (keep < 8) { w0 |= 0x88888888u << (4 * keep); w1 = 0x88888888u; }
-                    else if (keep > 8) w1 |= 0x88888888u << (4 * (keep - 8));
-                    else w1 = 0x88888888u;
-                }
-            }
-            sm[2 * v] = w0;
-            sm[2 * v + 1] = w1;
+    const uint64_t wt_begin = a.tile_begin * (SCAN_TILE / SCAN_WARP_TILE);
+    const uint64_t wt_end = a.tile_end * (SCAN_TILE / SCAN_WARP_TILE);
+    const uint64_t wt_stride = (uint64_t)gridDim.x * SCAN_WARPS;
+    uint64_t wt = wt_begin + (uint64_t)blockIdx.x * SCAN_WARPS + warp;
+    if (wt >= wt_end) return;
+
+    // each lane stages vectors lane, lane+32 and one of the 4 halo vectors (64 + lane%4: eight lanes write the same
+    // words with the same values -- no lane-dependent branch, the warp never splits): 16 bytes -> 2 words each
+    static_assert(SCAN_WARP_VECS - 64 == 4, "halo = 4 vectors");
+    const int v2 = 64 + (lane & 3);
+    uint4 q0, q1, q2;
+    {
+        const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
+        q0 = load16(a.stream, base + 16ull * lane, a.stream_len);
+        q1 = load16(a.stream, base + 16ull * (lane + 32), a.stream_len);
+        q2 = load16(a.stream, base + 16ull * v2, a.stream_len);
+    }
+    for (; wt < wt_end; wt += wt_stride) {
+        const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
+        *reinterpret_cast<uint2 *>(sm + 2 * lane) = stage16(q0, base + 16ull * lane, a.stream_len, fold);
+        *reinterpret_cast<uint2 *>(sm + 2 * (lane + 32)) = stage16(q1, base + 16ull * (lane + 32), a.stream_len, fold);
+        *reinterpret_cast<uint2 *>(sm + 2 * v2) = stage16(q2, base + 16ull * v2, a.stream_len, fold);
+        __syncwarp();
+        const uint64_t next = wt + wt_stride;
+        if (next < wt_end) {   // prefetch
+            const uint64_t nb = next * (uint64_t)SCAN_WARP_TILE;
+            q0 = load16(a.stream, nb + 16ull * lane, a.stream_len);
+            q1 = load16(a.stream, nb + 16ull * (lane + 32), a.stream_len);
+            q2 = load16(a.stream, nb + 16ull * v2, a.stream_len);
         }
-        __syncthreads();
-        const uint64_t tmax = a.tile_tmax ? a.tile_tmax[tile] : a.coarse_t;
-        for (int g = threadIdx.x; g < SCAN_TILE / 8; g += SCAN_THREADS) {
+        __syncwarp();
+        const uint64_t tmax = a.tile_tmax ? a.tile_tmax[base / SCAN_TILE] : a.coarse_t;
+#pragma unroll 1
+        for (int g = lane; g < SCAN_WARP_TILE / 8; g += 32) {
             uint32_t b[S::BW], rb[S::BW];
 #pragma unroll
             for (int i = 0; i < S::BW; i++) b[i] = sm[g + i];
@@ -275,21 +352,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const ScanArgs a)
                 for (int i = 0; i < S::BW; i++) rb[i] = nibble_reverse(b[S::BW - 1 - i]) ^ 0x33333333u;
             }
             const uint32_t local0 = 8u * g;
-            scan_window<K, CANON, 0>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 1>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 2>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 3>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 4>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 5>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 6>(a, b, rb, base, local0, tmax, pool);
-            scan_window<K, CANON, 7>(a, b, rb, base, local0, tmax, pool);
+            scan_window<K, CANON, 0>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 1>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 2>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 3>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 4>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 5>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 6>(a, b, rb, base, local0, tmax, pool, sm);
+            scan_window<K, CANON, 7>(a, b, rb, base, local0, tmax, pool, sm);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 // Host-side launcher table (defined in scan_inst_*.cu)
 typedef void (*scan_launch_fn)(const ScanArgs &a, int grid, cudaStream_t stream);
+typedef int (*scan_occupancy_fn)();
 scan_launch_fn get_scan_launcher(int k, bool canonical);
 
 }  // namespace mashgpu

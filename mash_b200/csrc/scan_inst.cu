@@ -8,10 +8,24 @@
 
 namespace mashgpu {
 
+// grid <= 0: size the persistent grid to the resident CTAs (occupancy x SM count, queried once per kernel)
 template <int K, bool CANON>
 static void launch_scan(const ScanArgs &a, int grid, cudaStream_t stream)
 {
-    scan_kernel<K, CANON><<<grid, SCAN_THREADS, 0, stream>>>(a);
+    static int resident = 0;
+    if (resident == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<K, CANON>, SCAN_THREADS, 0);
+        resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    const uint64_t warp_tiles = (a.tile_end - a.tile_begin) * (SCAN_TILE / SCAN_WARP_TILE);
+    const uint64_t need = (warp_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+    int g = grid > 0 ? grid : resident;
+    if ((uint64_t)g > need) g = (int)need;
+    if (g < 1) g = 1;
+    scan_kernel<K, CANON><<<g, SCAN_THREADS, 0, stream>>>(a);
 }
 
 template <int K>

@@ -195,9 +195,8 @@ static int launch_scan(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     if (!fn) return fail(ctx, MASHGPU_ERR_INVALID, "no scan kernel for k=%d", p->kmer_size);
     uint64_t ntiles = a.tile_end - a.tile_begin;
     if (ntiles == 0) return MASHGPU_OK;
-    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
     time_begin(ctx, ctx->scan_events, st);
-    fn(a, grid, st);
+    fn(a, 0, st);     // grid = resident CTAs (persistent warps striding over warp tiles)
     time_end(ctx, ctx->scan_events, st);
     ctx->kernel_launches++;
     ctx->scan_launches++;
@@ -303,11 +302,12 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
         h_off[u] = slots;
         slots += 1ull << h_log2[u];
     }
-    DevBuf<uint64_t> d_start, d_t, d_off, d_keys, d_tmax;
-    DevBuf<uint32_t> d_log2, d_cnt, d_flags, d_maxhash;
-    if (d_start.alloc(n_units + 1) != cudaSuccess || d_t.alloc(n_units) != cudaSuccess || d_off.alloc(n_units) != cudaSuccess ||
-        d_log2.alloc(n_units) != cudaSuccess || d_flags.alloc(n_units) != cudaSuccess || d_maxhash.alloc(n_units) != cudaSuccess ||
-        d_keys.alloc(slots) != cudaSuccess || d_cnt.alloc(slots) != cudaSuccess || d_tmax.alloc(ntiles) != cudaSuccess)
+    struct P64 { uint64_t *p; } d_start, d_t, d_off, d_keys, d_tmax;
+    struct P32 { uint32_t *p; } d_log2, d_cnt, d_flags, d_maxhash;
+    d_start.p = ctx->sc_start.get<uint64_t>(n_units + 1); d_t.p = ctx->sc_t.get<uint64_t>(n_units); d_off.p = ctx->sc_off.get<uint64_t>(n_units);
+    d_log2.p = ctx->sc_log2.get<uint32_t>(n_units); d_flags.p = ctx->sc_flags.get<uint32_t>(n_units); d_maxhash.p = ctx->sc_maxhash.get<uint32_t>(n_units);
+    d_keys.p = ctx->sc_keys.get<uint64_t>(slots); d_cnt.p = ctx->sc_cnt.get<uint32_t>(slots); d_tmax.p = ctx->sc_tmax.get<uint64_t>(ntiles);
+    if (!d_start.p || !d_t.p || !d_off.p || !d_log2.p || !d_flags.p || !d_maxhash.p || !d_keys.p || !d_cnt.p || !d_tmax.p)
         return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (%llu candidate slots for %u units)", (unsigned long long)slots, n_units);
     MG_CUDA(ctx, cudaMemcpyAsync(d_start.p, S.unit_start, (n_units + 1) * 8ull, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaMemcpyAsync(d_t.p, h_t.data(), n_units * 8ull, cudaMemcpyHostToDevice, st));
@@ -482,17 +482,17 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
     const uint64_t buf_bytes = ((max_bytes + 15) / 16) * 16 + 16;
 
     const int nbuf = waves.size() > 1 ? 2 : 1;
-    DevBuf<uint8_t> d_stream[2];
-    PinnedBuf<uint8_t> staging[2];
-    DevBuf<uint64_t> d_hashes; DevBuf<uint32_t> d_counts, d_n;
-    cudaEvent_t copied[2] = {nullptr, nullptr};
+    struct { uint8_t *p; } d_stream[2] = {{nullptr}, {nullptr}};
+    struct { uint8_t *p; size_t n; } staging[2] = {{(uint8_t *)ctx->pinned[0], ctx->pinned_bytes[0]}, {(uint8_t *)ctx->pinned[1], ctx->pinned_bytes[1]}};
+    cudaEvent_t *copied = ctx->wave_copied;
     for (int b = 0; b < nbuf; b++) {
-        if (d_stream[b].alloc(buf_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (stream buffer %llu B)", (unsigned long long)buf_bytes);
-        MG_CUDA(ctx, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        d_stream[b].p = ctx->sc_wave[b].get<uint8_t>(buf_bytes);
+        if (!d_stream[b].p) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (stream buffer %llu B)", (unsigned long long)buf_bytes);
+        if (!copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
-    if (d_hashes.alloc(max_units * s) != cudaSuccess || d_n.alloc(max_units) != cudaSuccess ||
-        (out_counts && d_counts.alloc(max_units * s) != cudaSuccess))
-        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+    struct { uint64_t *p; } d_hashes{ctx->sc_out_hashes.get<uint64_t>(max_units * s)};
+    struct { uint32_t *p; } d_n{ctx->sc_out_n.get<uint32_t>(max_units)}, d_counts{out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr};
+    if (!d_hashes.p || !d_n.p || (out_counts && !d_counts.p)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
 
     std::vector<std::vector<uint64_t>> wave_unit_start(waves.size());
     auto issue_copy = [&](size_t wi) -> int {
@@ -503,8 +503,14 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         uint64_t small_bytes = 0;
         for (uint64_t r = w.rec_begin; r < w.rec_end; r++)
             if (len[r] >= k && len[r] < DIRECT_COPY_MIN) small_bytes += len[r] + 1;
-        if (staging[b].n < small_bytes && staging[b].alloc(small_bytes) != cudaSuccess)
-            return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)small_bytes);
+        if (staging[b].n < small_bytes) {
+            if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
+            ctx->pinned[b] = nullptr; ctx->pinned_bytes[b] = 0;
+            if (cudaMallocHost(&ctx->pinned[b], small_bytes + small_bytes / 8) != cudaSuccess)
+                return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)small_bytes);
+            ctx->pinned_bytes[b] = small_bytes + small_bytes / 8;
+            staging[b].p = (uint8_t *)ctx->pinned[b]; staging[b].n = ctx->pinned_bytes[b];
+        }
         std::vector<uint64_t> &us = wave_unit_start[wi];
         us.assign(w.unit_end - w.unit_begin + 1, 0);
         uint64_t off = 0, st_off = 0;
@@ -559,7 +565,6 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     cudaStreamSynchronize(ctx->copy_stream);
-    for (int b = 0; b < nbuf; b++) if (copied[b]) cudaEventDestroy(copied[b]);
     return rc;
 }
 
