@@ -27,6 +27,7 @@ constexpr int DIST_WARPS = 12;
 constexpr int DIST_ILP = 2;
 constexpr int DIST_THREADS = DIST_WARPS * 32;
 constexpr int DIST_TILE_R = 32;
+static_assert(DIST_TILE_R * 4 == 128, "the merge step's PTX hard-codes the 128-byte stride of the interleaved reference tile");
 
 struct DistArgs {
     const uint32_t *ranks;      // rows of P ranks: references first, then queries (or shared when self)
@@ -109,14 +110,23 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
             va[c] = lds32(pa[c]);
             vb[c] = lds32(pb[c]);
         }
+        // One merge step per chain = 6 instructions: 2 compares, 2 predicated pointer bumps, 2 predicated loads, written
+        // as one PTX block so that the pointer update stays in place (the C++ form compiled to 9 instructions).
+        // Measured (tools/dist_probe.py, ncu r01): 9 -> 6 instructions and a 2-deep register lookahead that takes the
+        // LDS latency out of the dependent chain both leave the rate at 2.9e9 pairs/s -- the kernel is bound by the
+        // shared-memory pipe: two half-populated LDS wavefronts per warp-step (lsu pipe 66 %), see DESIGN.md 3.3.
 #pragma unroll 4
         for (uint32_t t = 0; t < a.S; t++) {
 #pragma unroll
             for (int c = 0; c < DIST_ILP; c++) {
-                const bool adv_a = va[c] <= vb[c];
-                const bool adv_b = vb[c] <= va[c];
-                if (adv_a) { pa[c] += DIST_TILE_R * 4; va[c] = lds32(pa[c]); }
-                if (adv_b) { pb[c] += 4; vb[c] = lds32(pb[c]); }
+                asm volatile("{\n\t.reg .pred pa, pb;\n\t"
+                             "setp.le.u32 pa, %0, %1;\n\t"
+                             "setp.le.u32 pb, %1, %0;\n\t"
+                             "@pa add.u32 %2, %2, 128;\n\t"
+                             "@pb add.u32 %3, %3, 4;\n\t"
+                             "@pa ld.shared.u32 %0, [%2];\n\t"
+                             "@pb ld.shared.u32 %1, [%3];\n\t}"
+                             : "+r"(va[c]), "+r"(vb[c]), "+r"(pa[c]), "+r"(pb[c]));
             }
         }
         // epilogue
