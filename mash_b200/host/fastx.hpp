@@ -1,0 +1,128 @@
+// fastx.hpp -- FASTA/FASTQ reader with the record semantics of the reference's kseq.h (kseq_read, kseq.h:170-208),
+// over zlib's gzread (plain or gzipped input):
+//   * a header starts at '>' or '@'; name = up to the first white-space character, comment = rest of that line;
+//   * the sequence runs until the next '>', '+' or '@' byte (anywhere, as in kseq) and keeps only isgraph() bytes;
+//   * after '+' the rest of the line is skipped and as many quality characters (33..127) as sequence bytes are read;
+//   * return value = sequence length, -1 at end of file, -2 for a truncated quality string.
+// Implementation differs (block-wise scanning with a byte-class table instead of one ks_getc call per byte).
+#pragma once
+#include <zlib.h>
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace mashhost {
+
+class FastxReader {
+public:
+    std::string name, comment, seq;
+
+    explicit FastxReader(gzFile f) : f_(f), buf_(1 << 20)
+    {
+        for (int c = 0; c < 256; c++) cls_[c] = (c == '>' || c == '+' || c == '@') ? 2 : (isgraph(c) ? 0 : 1);
+    }
+    ~FastxReader() {}
+
+    static gzFile openPath(const std::string &path)
+    {
+        if (path == "-") return gzdopen(fileno(stdin), "r");
+        return gzopen(path.c_str(), "r");
+    }
+
+    int read()
+    {
+        int c;
+        if (lastChar_ == 0) {   // jump to the next header line
+            while ((c = getc()) != -1 && c != '>' && c != '@') {}
+            if (c == -1) return -1;
+            lastChar_ = c;
+        }
+        comment.clear(); seq.clear();
+        size_t qual = 0;
+        if (!getUntilSpace(name, c)) return -1;
+        if (c != '\n') getUntilNewline(comment);
+        // sequence: append graph bytes until a terminator
+        for (;;) {
+            if (begin_ >= end_ && !fill()) { c = -1; break; }
+            const unsigned char *p = buf_.data() + begin_, *e = buf_.data() + end_;
+            const unsigned char *run = p;
+            int stop = 0;
+            while (p < e) {
+                int k = cls_[*p];
+                if (k == 0) { p++; continue; }
+                if (p > run) seq.append(reinterpret_cast<const char *>(run), p - run);
+                if (k == 2) { stop = *p; p++; break; }
+                p++;
+                run = p;
+            }
+            if (!stop && p > run) seq.append(reinterpret_cast<const char *>(run), p - run);
+            begin_ = p - buf_.data();
+            if (stop) { c = stop; break; }
+        }
+        if (c == '>' || c == '@') lastChar_ = c;
+        if (c != '+') return (int)seq.size();   // FASTA
+        while ((c = getc()) != -1 && c != '\n') {}
+        if (c == -1) return -2;
+        while ((c = getc()) != -1 && qual < seq.size())
+            if (c >= 33 && c <= 127) qual++;
+        lastChar_ = 0;
+        if (seq.size() != qual) return -2;
+        return (int)seq.size();
+    }
+
+private:
+    gzFile f_;
+    std::vector<unsigned char> buf_;
+    size_t begin_ = 0, end_ = 0;
+    bool eof_ = false;
+    int lastChar_ = 0;
+    unsigned char cls_[256];
+
+    bool fill()
+    {
+        if (eof_) return false;
+        int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+        begin_ = 0;
+        end_ = n > 0 ? (size_t)n : 0;
+        if (n < (int)buf_.size()) eof_ = true;
+        return end_ > 0;
+    }
+    int getc()
+    {
+        if (begin_ >= end_ && !fill()) return -1;
+        return buf_[begin_++];
+    }
+    // ks_getuntil(ks, KS_SEP_SPACE, ...): false when already at end of file
+    bool getUntilSpace(std::string &out, int &delim)
+    {
+        out.clear();
+        delim = 0;
+        if (begin_ >= end_ && eof_) return false;
+        for (;;) {
+            if (begin_ >= end_ && !fill()) break;
+            size_t i = begin_;
+            while (i < end_ && !isspace(buf_[i])) i++;
+            out.append(reinterpret_cast<const char *>(buf_.data() + begin_), i - begin_);
+            begin_ = i + 1;
+            if (i < end_) { delim = buf_[i]; break; }
+            begin_ = end_;
+        }
+        return true;
+    }
+    void getUntilNewline(std::string &out)
+    {
+        out.clear();
+        for (;;) {
+            if (begin_ >= end_ && !fill()) break;
+            const unsigned char *p = static_cast<const unsigned char *>(memchr(buf_.data() + begin_, '\n', end_ - begin_));
+            size_t i = p ? (size_t)(p - buf_.data()) : end_;
+            out.append(reinterpret_cast<const char *>(buf_.data() + begin_), i - begin_);
+            if (p) { begin_ = i + 1; break; }
+            begin_ = end_;
+        }
+    }
+};
+
+}  // namespace mashhost

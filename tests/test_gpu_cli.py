@@ -1,0 +1,109 @@
+"""Replays the reference's own `make test` (reference Makefile.in:94-115) with the host shim binary on the GPU:
+    mash sketch -o genomes.msh genome1.fna genome2.fna genome3.fna ; mash sketch -r -I reads reads1.fastq reads2.fastq -o reads.msh
+    mash info -d {genomes,reads}.msh   == test/ref/{genomes,reads}.json
+    mash dist genomes.msh reads.msh     == test/ref/genomes.dist
+    mash screen genomes.msh reads1.fastq reads2.fastq == test/ref/screen
+plus the tutorial commands (doc/sphinx/tutorials.rst:24,56-57) and triangle / -i / gz-input variants checked against the oracle."""
+import gzip
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import msh_reader
+from fixtures import GOLDEN, fmt_g
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MASH = os.path.join(ROOT, "mash_b200", "host", "mash")
+
+
+@pytest.fixture(scope="module")
+def work(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mashcli")
+    for f in ("genome1.fna", "genome2.fna", "genome3.fna", "reads1.fastq", "reads2.fastq"):
+        with gzip.open(os.path.join(GOLDEN, f + ".gz"), "rb") as src, open(d / f, "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    assert os.path.exists(MASH), "build the host shim first (__graft_entry__.build())"
+    subprocess.run([MASH, "sketch", "-o", "genomes.msh", "genome1.fna", "genome2.fna", "genome3.fna"], cwd=d, check=True, capture_output=True)
+    subprocess.run([MASH, "sketch", "-r", "-I", "reads", "reads1.fastq", "reads2.fastq", "-o", "reads.msh"], cwd=d, check=True, capture_output=True)
+    return d
+
+
+def out(work, *args):
+    return subprocess.run([MASH, *args], cwd=work, check=True, capture_output=True, text=True).stdout
+
+
+def test_make_testSketch(work):
+    assert out(work, "info", "-d", "genomes.msh") == open(os.path.join(GOLDEN, "ref_genomes.json")).read()
+    got = out(work, "info", "-d", "reads.msh")
+    # -r implies counts (sketchParameterSetup.cpp:62-65) and HEAD's `mash info -d` prints them; the shipped golden predates
+    # that (stale on this one section) -- compare everything but the counts block
+    assert '"counts" :' in got
+    stripped = re.sub(r'\t\t\t"counts" :\n\t\t\t\[\n(?:\t\t\t\t\d+,?\n)*\t\t\t\]\n', "", got)
+    assert stripped == open(os.path.join(GOLDEN, "ref_reads.json")).read()
+
+
+def test_make_testDist(work):
+    assert out(work, "dist", "genomes.msh", "reads.msh") == open(os.path.join(GOLDEN, "ref_genomes.dist")).read()
+
+
+def test_make_testScreen(work):
+    assert out(work, "screen", "genomes.msh", "reads1.fastq", "reads2.fastq") == open(os.path.join(GOLDEN, "ref_screen")).read()
+
+
+def test_tutorial_commands(work):
+    # doc/sphinx/tutorials.rst:24  `mash dist genome1.fna genome2.fna`
+    assert out(work, "dist", "genome1.fna", "genome2.fna") == "genome1.fna\tgenome2.fna\t0.0222766\t0\t456/1000\n"
+    # tutorials.rst:56-57  `mash dist reference.msh genome3.fna` with reference = sketch of genome1 + genome2
+    subprocess.run([MASH, "sketch", "-o", "reference", "genome1.fna", "genome2.fna"], cwd=work, check=True, capture_output=True)
+    assert out(work, "dist", "reference.msh", "genome3.fna") == "genome1.fna\tgenome3.fna\t0\t0\t1000/1000\ngenome2.fna\tgenome3.fna\t0.0222766\t0\t456/1000\n"
+
+
+def test_msh_written_on_gpu_has_reference_layout(work):
+    d = msh_reader.read_msh(str(work / "genomes.msh"))
+    assert d["segments"] == [77, 1001, 2002] and d["list"] == "referenceListOld"
+    r = msh_reader.read_msh(str(work / "reads.msh"))
+    assert r["references"][0]["name"] == "reads" and r["references"][0]["length"] == 502359
+    assert r["references"][0]["counts32Sorted"] and len(r["references"][0]["counts32"]) == 1000
+
+
+def test_gz_input_individual_mode_and_triangle(work, oracle):
+    # -i: one sketch per record; gz input; triangle output vs oracle compare
+    recs = []
+    rng = np.random.Generator(np.random.PCG64(9))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    base = acgt[rng.integers(0, 4, 60_000)]
+    with gzip.open(work / "multi.fa.gz", "wb") as f:
+        for i in range(6):
+            s = base.copy()
+            m = rng.random(s.size) < 0.01 * i
+            s[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+            recs.append(bytes(s))
+            f.write(b">rec%d some comment %d\n" % (i, i))
+            for a in range(0, len(s), 70):
+                f.write(bytes(s[a:a + 70]) + b"\n")
+        f.write(b">tiny\nACGT\n")                      # shorter than k: skipped
+    p = oracle.params(k=21)
+    want = [oracle.sketch_unit([r], p, s=400) for r in recs]
+    subprocess.run([MASH, "sketch", "-i", "-s", "400", "-o", "multi", "multi.fa.gz"], cwd=work, check=True, capture_output=True)
+    d = msh_reader.read_msh(str(work / "multi.msh"))
+    assert [r["name"] for r in d["references"]] == [f"rec{i}" for i in range(6)]
+    assert d["references"][2]["comment"] == "some comment 2" and not d["concatenated"]
+    for r, (h, _, length) in zip(d["references"], want):
+        assert r["length"] == length and r["hashes64"] == [int(x) for x in h]
+    tri = out(work, "triangle", "multi.msh").splitlines()
+    assert tri[0] == "\t6" and tri[1] == "rec0"
+    ks = oracle.kmer_space(p)
+    for i in range(1, 6):
+        cells = tri[1 + i].split("\t")
+        assert cells[0] == f"rec{i}"
+        for j in range(i):
+            o = oracle.compare_sketches(want[i][0], want[i][2], want[j][0], want[j][2], 400, 21, ks)
+            assert cells[1 + j] == fmt_g(o.distance)
+    edges = out(work, "triangle", "-E", "multi.msh").splitlines()
+    assert len(edges) == 15 and edges[0].split("\t")[:2] == ["rec1", "rec0"]
