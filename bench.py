@@ -262,6 +262,7 @@ def main():
         return float(t.item())
 
     eng = mash_b200.Engine(local)
+    eng_sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     p = eng.params(k=K, s=S, seed=SEED)
     peaks, peak_kind = measured_peaks()
     W, Ksteps = args.warmup, args.steps
@@ -304,7 +305,21 @@ def main():
     roofline = {"bound": "hbm", "kernel": "scan_kernel<21,canonical>", "achieved": scan_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": scan_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": bases_per_step, "launch_ms": scan_ms,
-                "note": "ALU-bound by exact MurmurHash3_x64_128 per k-mer; see int_issue"}
+                "note": "integer-issue bound by the exact MurmurHash3_x64_128 per k-mer, not HBM bound; see int_issue and DESIGN.md 2.4"}
+    model_path = os.path.join(ROOT, "profiles", "r01_scan_model.json")
+    if os.path.exists(model_path):
+        model = json.load(open(model_path))
+        # DRAM traffic per launch: bytes/base measured by one `ncu --set full` capture of this kernel, scaled to this launch
+        roofline["traffic"] = model["dram_bytes_per_base"] * bases_per_step
+        roofline["traffic_source"] = "profiles/r01_scan_kernel_ncu.csv (dram__bytes_read+write per base at 400 units) x bases per launch"
+        sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        sm_hz *= 1e6
+        issue_peak = eng_sm_count * 4 * sm_hz                       # warp instructions / s (1 per SM sub-partition per clock)
+        warp_inst = bases_per_step / 32 * model["warp_instructions_per_32_kmers"] / (scan_ms * 1e-3)
+        roofline["int_issue"] = {"warp_instructions_per_32_kmers": model["warp_instructions_per_32_kmers"],
+                                 "achieved_warp_inst_per_s": warp_inst, "peak_warp_inst_per_s": issue_peak, "frac": warp_inst / issue_peak,
+                                 "alu_pipe_frac": warp_inst * model["alu_pipe_share"] / (issue_peak / 2),
+                                 "note": "ALU pipe (SHF/LOP3/IADD3/PRMT) issues one warp instruction per 2 clocks per sub-partition; instruction mix from the ncu source page"}
     sanity = {"sketches_full": int((d_n == S).sum().item()), "units": n_units}
 
     # ---------------- e2e: host buffers through mashgpu_sketch_batch --------------------------------------------------

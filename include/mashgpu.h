@@ -96,6 +96,14 @@ int mashgpu_sketch_stream_dev(mashgpu_ctx *ctx, const mashgpu_sketch_params *par
                               const void *d_stream, const uint64_t *unit_start, uint64_t n_units,
                               uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, void *stream);
 
+/* Host feed path, exposed for tests (no GPU involved): packs records the way mashgpu_sketch_batch does before the
+ * H2D copy -- every record followed by one separator position -- into 2-bit codes (A0 C1 G2 T3, 32 positions per
+ * uint64 word) plus the list of runs of positions that are not in the alphabet (upper-casing unless preserve_case;
+ * separators included).  codes must hold ceil(stream_len/32) words with stream_len = sum(len[r] + 1); runs receives
+ * up to runs_capacity {start, length} pairs; *n_runs is the number of runs found. */
+int mashgpu_host_pack(const mashgpu_sketch_params *params, uint64_t n_records, const char *const *seq, const uint64_t *len,
+                      int threads, uint64_t *codes, uint64_t *runs, uint64_t runs_capacity, uint64_t *n_runs);
+
 /* getHash over every window (hash.cpp:10-38 applied as in Sketch.cpp:540-576): out_hash[i]/out_valid[i] for each
  * window start i in [0, len-k]; invalid windows (a byte outside the alphabet) have out_valid[i] == 0.
  * Host buffers.  Diagnostic/test entry point of the scan+hash kernel. */

@@ -83,6 +83,7 @@ def load_library():
                                        u64p, u32p, u32p, u64p]
     L.mashgpu_sketch_stream_dev.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, u64p, C.c_uint64,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_host_pack.argtypes = [C.POINTER(SketchParams), C.c_uint64, C.c_void_p, u64p, C.c_int, u64p, u64p, C.c_uint64, u64p]
     L.mashgpu_hash_windows.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, C.c_uint64, u64p, u8p]
     L.mashgpu_dist_open.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), C.POINTER(C.c_void_p)]
     L.mashgpu_dist_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u32p, u32p, f64p, f64p, u8p]

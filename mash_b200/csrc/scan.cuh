@@ -32,8 +32,10 @@ constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
 enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2 };
 
 struct ScanArgs {
-    const uint8_t *stream;        // flat byte stream
-    uint64_t stream_len;          // bytes >= stream_len are treated as separators
+    const uint8_t *stream;        // flat byte stream (ASCII source; NULL when the packed source is used)
+    const uint64_t *codes;        // packed source: 2-bit codes, 32 positions per word (A0 C1 G2 T3), see pack.cpp
+    const uint32_t *inval;        // packed source: 1 bit per position, set = not in the alphabet / separator / past the end
+    uint64_t stream_len;          // positions >= stream_len are treated as separators
     uint64_t tile_begin, tile_end;
     const uint64_t *tile_tmax;    // per-tile coarse threshold (indexed by absolute tile id); NULL -> coarse_t
     uint64_t coarse_t;
@@ -296,10 +298,36 @@ __device__ __forceinline__ uint4 load16(const uint8_t *stream, uint64_t off, uin
     return make_uint4(0, 0, 0, 0);
 }
 
+// 32 packed positions (2-bit codes + invalid bits) -> 4 nibble words
+__device__ __forceinline__ uint32_t spread_codes8(uint32_t x)   // 8 two-bit codes (16 bits) -> 8 nibbles
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return x;
+}
+__device__ __forceinline__ uint32_t spread_bits8(uint32_t y)    // 8 bits -> bit 3 of 8 nibbles
+{
+    y = (y | (y << 12)) & 0x000F000Fu;
+    y = (y | (y << 6)) & 0x03030303u;
+    y = (y | (y << 3)) & 0x11111111u;
+    return y << 3;
+}
+__device__ __forceinline__ uint4 expand32(uint64_t c, uint32_t m)
+{
+    const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+    uint4 r;
+    r.x = spread_codes8(lo & 0xFFFFu) | spread_bits8(m & 0xFFu);
+    r.y = spread_codes8(lo >> 16) | spread_bits8((m >> 8) & 0xFFu);
+    r.z = spread_codes8(hi & 0xFFFFu) | spread_bits8((m >> 16) & 0xFFu);
+    r.w = spread_codes8(hi >> 16) | spread_bits8(m >> 24);
+    return r;
+}
+
 // Warp-private tiles: every warp owns WARP_TILE window starts at a time, staged in its own slice of shared memory,
 // so the only synchronisation is __syncwarp().  The next tile's bytes are prefetched into registers before the
 // current tile is hashed (global latency hidden behind ~4000 instructions of work per lane).
-template <int K, bool CANON>
+template <int K, bool CANON, bool PACKED>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanArgs a)
 {
     using S = KmerShape<K>;
@@ -320,8 +348,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constan
     // words with the same values -- no lane-dependent branch, the warp never splits): 16 bytes -> 2 words each
     static_assert(SCAN_WARP_VECS - 64 == 4, "halo = 4 vectors");
     const int v2 = 64 + (lane & 3);
-    uint4 q0, q1, q2;
-    {
+    uint4 q0, q1, q2;                      // ASCII source: three 16-byte vectors per lane
+    uint64_t pc0 = 0, pc1 = 0;             // packed source: group (lane) and one of the 2 halo groups (32 + lane%2)
+    uint32_t pm0 = 0, pm1 = 0;
+    const int hg = 32 + (lane & 1);
+    if (PACKED) {
+        const uint64_t g0 = wt * (uint64_t)(SCAN_WARP_TILE / 32);
+        pc0 = __ldg(a.codes + g0 + lane); pm0 = __ldg(a.inval + g0 + lane);
+        pc1 = __ldg(a.codes + g0 + hg);   pm1 = __ldg(a.inval + g0 + hg);
+    } else {
         const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
         q0 = load16(a.stream, base + 16ull * lane, a.stream_len);
         q1 = load16(a.stream, base + 16ull * (lane + 32), a.stream_len);
@@ -329,16 +364,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constan
     }
     for (; wt < wt_end; wt += wt_stride) {
         const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
-        *reinterpret_cast<uint2 *>(sm + 2 * lane) = stage16(q0, base + 16ull * lane, a.stream_len, fold);
-        *reinterpret_cast<uint2 *>(sm + 2 * (lane + 32)) = stage16(q1, base + 16ull * (lane + 32), a.stream_len, fold);
-        *reinterpret_cast<uint2 *>(sm + 2 * v2) = stage16(q2, base + 16ull * v2, a.stream_len, fold);
+        if (PACKED) {
+            *reinterpret_cast<uint4 *>(sm + 4 * lane) = expand32(pc0, pm0);
+            *reinterpret_cast<uint4 *>(sm + 4 * hg) = expand32(pc1, pm1);
+        } else {
+            *reinterpret_cast<uint2 *>(sm + 2 * lane) = stage16(q0, base + 16ull * lane, a.stream_len, fold);
+            *reinterpret_cast<uint2 *>(sm + 2 * (lane + 32)) = stage16(q1, base + 16ull * (lane + 32), a.stream_len, fold);
+            *reinterpret_cast<uint2 *>(sm + 2 * v2) = stage16(q2, base + 16ull * v2, a.stream_len, fold);
+        }
         __syncwarp();
         const uint64_t next = wt + wt_stride;
         if (next < wt_end) {   // prefetch
-            const uint64_t nb = next * (uint64_t)SCAN_WARP_TILE;
-            q0 = load16(a.stream, nb + 16ull * lane, a.stream_len);
-            q1 = load16(a.stream, nb + 16ull * (lane + 32), a.stream_len);
-            q2 = load16(a.stream, nb + 16ull * v2, a.stream_len);
+            if (PACKED) {
+                const uint64_t g0 = next * (uint64_t)(SCAN_WARP_TILE / 32);
+                pc0 = __ldg(a.codes + g0 + lane); pm0 = __ldg(a.inval + g0 + lane);
+                pc1 = __ldg(a.codes + g0 + hg);   pm1 = __ldg(a.inval + g0 + hg);
+            } else {
+                const uint64_t nb = next * (uint64_t)SCAN_WARP_TILE;
+                q0 = load16(a.stream, nb + 16ull * lane, a.stream_len);
+                q1 = load16(a.stream, nb + 16ull * (lane + 32), a.stream_len);
+                q2 = load16(a.stream, nb + 16ull * v2, a.stream_len);
+            }
         }
         __syncwarp();
         const uint64_t tmax = a.tile_tmax ? a.tile_tmax[base / SCAN_TILE] : a.coarse_t;
@@ -368,6 +414,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constan
 // Host-side launcher table (defined in scan_inst_*.cu)
 typedef void (*scan_launch_fn)(const ScanArgs &a, int grid, cudaStream_t stream);
 typedef int (*scan_occupancy_fn)();
-scan_launch_fn get_scan_launcher(int k, bool canonical);
+scan_launch_fn get_scan_launcher(int k, bool canonical, bool packed);
 
 }  // namespace mashgpu

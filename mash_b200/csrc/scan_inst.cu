@@ -9,7 +9,7 @@
 namespace mashgpu {
 
 // grid <= 0: size the persistent grid to the resident CTAs (occupancy x SM count, queried once per kernel)
-template <int K, bool CANON>
+template <int K, bool CANON, bool PACKED>
 static void launch_scan(const ScanArgs &a, int grid, cudaStream_t stream)
 {
     static int resident = 0;
@@ -17,7 +17,7 @@ static void launch_scan(const ScanArgs &a, int grid, cudaStream_t stream)
         int per_sm = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<K, CANON>, SCAN_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<K, CANON, PACKED>, SCAN_THREADS, 0);
         resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     const uint64_t warp_tiles = (a.tile_end - a.tile_begin) * (SCAN_TILE / SCAN_WARP_TILE);
@@ -25,26 +25,29 @@ static void launch_scan(const ScanArgs &a, int grid, cudaStream_t stream)
     int g = grid > 0 ? grid : resident;
     if ((uint64_t)g > need) g = (int)need;
     if (g < 1) g = 1;
-    scan_kernel<K, CANON><<<g, SCAN_THREADS, 0, stream>>>(a);
+    scan_kernel<K, CANON, PACKED><<<g, SCAN_THREADS, 0, stream>>>(a);
 }
 
 template <int K>
-static scan_launch_fn pick(int k, bool canonical)
+static scan_launch_fn pick(int k, bool canonical, bool packed)
 {
     if constexpr (K > SCAN_K_HI) {
         return nullptr;
     } else {
-        if (k == K) return canonical ? &launch_scan<K, true> : &launch_scan<K, false>;
-        return pick<K + 1>(k, canonical);
+        if (k == K) {
+            if (packed) return canonical ? &launch_scan<K, true, true> : &launch_scan<K, false, true>;
+            return canonical ? &launch_scan<K, true, false> : &launch_scan<K, false, false>;
+        }
+        return pick<K + 1>(k, canonical, packed);
     }
 }
 
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
-scan_launch_fn CAT(get_scan_launcher_part, SCAN_PART)(int k, bool canonical)
+scan_launch_fn CAT(get_scan_launcher_part, SCAN_PART)(int k, bool canonical, bool packed)
 {
     if (k < SCAN_K_LO || k > SCAN_K_HI) return nullptr;
-    return pick<SCAN_K_LO>(k, canonical);
+    return pick<SCAN_K_LO>(k, canonical, packed);
 }
 
 }  // namespace mashgpu

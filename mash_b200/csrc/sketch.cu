@@ -15,20 +15,24 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "sketch_core.cuh"
+#include "pack.h"
+#include <future>
+#include <thread>
+#include <cstdlib>
 
 namespace mashgpu {
 
-scan_launch_fn get_scan_launcher_part0(int, bool);
-scan_launch_fn get_scan_launcher_part1(int, bool);
-scan_launch_fn get_scan_launcher_part2(int, bool);
-scan_launch_fn get_scan_launcher_part3(int, bool);
+scan_launch_fn get_scan_launcher_part0(int, bool, bool);
+scan_launch_fn get_scan_launcher_part1(int, bool, bool);
+scan_launch_fn get_scan_launcher_part2(int, bool, bool);
+scan_launch_fn get_scan_launcher_part3(int, bool, bool);
 
-scan_launch_fn get_scan_launcher(int k, bool canonical)
+scan_launch_fn get_scan_launcher(int k, bool canonical, bool packed)
 {
-    if (auto f = get_scan_launcher_part0(k, canonical)) return f;
-    if (auto f = get_scan_launcher_part1(k, canonical)) return f;
-    if (auto f = get_scan_launcher_part2(k, canonical)) return f;
-    return get_scan_launcher_part3(k, canonical);
+    if (auto f = get_scan_launcher_part0(k, canonical, packed)) return f;
+    if (auto f = get_scan_launcher_part1(k, canonical, packed)) return f;
+    if (auto f = get_scan_launcher_part2(k, canonical, packed)) return f;
+    return get_scan_launcher_part3(k, canonical, packed);
 }
 
 constexpr double SURVIVOR_FACTOR = 3.0;   // expected distinct survivors = 3 s
@@ -135,6 +139,24 @@ __global__ void compact_table_kernel(const uint64_t *keys, uint64_t cap, uint64_
     if (k != EMPTY_KEY) out[atomicAdd(out_n, 1ull)] = k;
 }
 
+// Packed source: expand the host's list of invalid runs into the 1-bit-per-position mask.  One warp per run; runs
+// are disjoint, so interior words are plain stores and only the two edge words need atomics.
+__global__ void apply_runs_kernel(const PackRun *runs, uint64_t n_runs, uint32_t *mask)
+{
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = warp; r < n_runs; r += n_warps) {
+        const uint64_t start = runs[r].start, end = start + runs[r].len;      // [start, end)
+        if (end == start) continue;
+        const uint64_t w0 = start >> 5, w1 = (end - 1) >> 5;
+        const uint32_t first = 0xFFFFFFFFu << (start & 31), last = 0xFFFFFFFFu >> (31 - ((end - 1) & 31));
+        if (w0 == w1) { if (lane == 0) atomicOr(&mask[w0], first & last); continue; }
+        if (lane == 0) atomicOr(&mask[w0], first);
+        if (lane == 1) atomicOr(&mask[w1], last);
+        for (uint64_t w = w0 + 1 + lane; w < w1; w += 32) mask[w] = 0xFFFFFFFFu;
+    }
+}
+
 __global__ void emit_sorted_kernel(const uint64_t *sorted, uint32_t m, const uint64_t *keys, const uint32_t *cnt, uint32_t log2cap,
                                    uint32_t maxhash_cnt, uint32_t n_sorted, uint64_t *out_hashes, uint32_t *out_counts)
 {
@@ -191,7 +213,7 @@ void plan_unit(const mashgpu_sketch_params *p, uint64_t span, double factor, uin
 
 static int launch_scan(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const ScanArgs &a, cudaStream_t st)
 {
-    scan_launch_fn fn = get_scan_launcher(p->kmer_size, !p->noncanonical);
+    scan_launch_fn fn = get_scan_launcher(p->kmer_size, !p->noncanonical, a.codes != nullptr);
     if (!fn) return fail(ctx, MASHGPU_ERR_INVALID, "no scan kernel for k=%d", p->kmer_size);
     uint64_t ntiles = a.tile_end - a.tile_begin;
     if (ntiles == 0) return MASHGPU_OK;
@@ -321,6 +343,8 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     ScanArgs a;
     memset(&a, 0, sizeof a);
     a.stream = (const uint8_t *)S.d_stream;
+    a.codes = S.d_codes;
+    a.inval = S.d_inval;
     a.stream_len = stream_len;
     a.tile_begin = 0;
     a.tile_end = ntiles;
@@ -477,6 +501,117 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         w.rec_end = n_records;
         waves.push_back(w);
     }
+    // ---- packed feed path (opt-in, MASHGPU_HOST_PACK=1): host threads pack each wave to 2 bits/base (+ invalid runs) while
+    // the GPU works on the previous wave; H2D moves a quarter of the bytes.  Measured on the B200 box of this pool (128
+    // vCPUs but ~16 cores' worth of host throughput, profiles/r01_feed_path.md): packing sustains 16.5 Gbp/s against
+    // 49 Gbp/s for the plain pinned ASCII copy below, so ASCII stays the default; on hosts with real cores to spare the
+    // packed path removes the PCIe bound (4x fewer bytes).
+    {
+        const char *env = getenv("MASHGPU_HOST_PACK");
+        if (env && env[0] == '1') {
+            uint64_t max_bytes = 32, max_units = 1;
+            for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
+            const uint64_t max_tiles = (max_bytes + SCAN_TILE - 1) / SCAN_TILE;
+            const uint64_t groups_alloc = max_tiles * (SCAN_TILE / 32) + 64;       // tile-padded + halo
+            int threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 96u);
+            if (const char *t = getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, atoi(t));
+            const int nbuf = waves.size() > 1 ? 2 : 1;
+            uint64_t *d_codes[2] = {nullptr, nullptr}; uint32_t *d_inval[2] = {nullptr, nullptr};
+            uint64_t *h_codes[2] = {nullptr, nullptr};
+            for (int b = 0; b < nbuf; b++) {
+                d_codes[b] = ctx->sc_wave[b].get<uint64_t>(groups_alloc);
+                d_inval[b] = ctx->sc_inval[b].get<uint32_t>(groups_alloc);
+                if (!d_codes[b] || !d_inval[b]) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (packed stream of %llu groups)", (unsigned long long)groups_alloc);
+                if (ctx->pinned_bytes[b] < groups_alloc * 8) {
+                    if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
+                    ctx->pinned[b] = nullptr; ctx->pinned_bytes[b] = 0;
+                    if (cudaMallocHost(&ctx->pinned[b], groups_alloc * 8) != cudaSuccess)
+                        return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)(groups_alloc * 8));
+                    ctx->pinned_bytes[b] = groups_alloc * 8;
+                }
+                h_codes[b] = (uint64_t *)ctx->pinned[b];
+                if (!ctx->wave_copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wave_copied[b], cudaEventDisableTiming));
+            }
+            uint64_t *d_hashes = ctx->sc_out_hashes.get<uint64_t>(max_units * s);
+            uint32_t *d_n = ctx->sc_out_n.get<uint32_t>(max_units);
+            uint32_t *d_counts = out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr;
+            if (!d_hashes || !d_n || (out_counts && !d_counts)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+
+            struct Packed { std::vector<uint64_t> unit_start; std::vector<PackRun> runs; uint64_t len = 0; };
+            std::vector<Packed> packed(waves.size());
+            auto pack_wave = [&](size_t wi) {
+                const Wave &w = waves[wi];
+                Packed &P = packed[wi];
+                std::vector<PackSegment> segs;
+                segs.reserve(w.rec_end - w.rec_begin);
+                P.unit_start.assign(w.unit_end - w.unit_begin + 1, 0);
+                uint64_t off = 0;
+                for (uint64_t u = w.unit_begin; u < w.unit_end; u++) {
+                    P.unit_start[u - w.unit_begin] = off;
+                    for (uint64_t r = unit_rec_begin[u]; r < unit_rec_begin[u + 1]; r++) {
+                        if (len[r] < k) continue;
+                        segs.push_back(PackSegment{(const uint8_t *)seq[r], off, len[r]});
+                        off += len[r] + 1;                     // one separator position after every record
+                    }
+                }
+                P.unit_start[w.unit_end - w.unit_begin] = off;
+                P.len = off;
+                pack_stream(segs.data(), segs.size(), off, params->preserve_case, threads, h_codes[wi % nbuf], P.runs);
+                // everything from the end of the stream to the end of the allocation is invalid
+                P.runs.push_back(PackRun{off, groups_alloc * 32 - off});
+            };
+            auto upload_wave = [&](size_t wi) -> int {
+                const int b = (int)(wi % nbuf);
+                Packed &P = packed[wi];
+                const uint64_t groups = (P.len + 31) / 32;
+                cudaStream_t cs = ctx->copy_stream;
+                if (groups) MG_CUDA(ctx, cudaMemcpyAsync(d_codes[b], h_codes[b], groups * 8, cudaMemcpyHostToDevice, cs));
+                MG_CUDA(ctx, cudaMemsetAsync(d_inval[b], 0, groups_alloc * 4, cs));
+                PackRun *d_runs = ctx->sc_runs[b].get<PackRun>(P.runs.size());
+                if (!d_runs) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (invalid runs)");
+                MG_CUDA(ctx, cudaMemcpyAsync(d_runs, P.runs.data(), P.runs.size() * sizeof(PackRun), cudaMemcpyHostToDevice, cs));
+                const uint64_t nr = P.runs.size();
+                const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, 148 * 16);
+                apply_runs_kernel<<<std::max(1u, blocks), 256, 0, cs>>>(d_runs, nr, d_inval[b]);
+                ctx->kernel_launches++;
+                MG_CUDA(ctx, cudaGetLastError());
+                MG_CUDA(ctx, cudaEventRecord(ctx->wave_copied[b], cs));
+                return MASHGPU_OK;
+            };
+
+            // three-stage software pipeline over waves: host pack (w+2) | H2D + mask build (w+1) | kernels (w)
+            pack_wave(0);
+            MG_TRY(upload_wave(0));
+            if (waves.size() > 1) pack_wave(1);
+            int rc = MASHGPU_OK;
+            for (size_t wi = 0; wi < waves.size() && rc == MASHGPU_OK; wi++) {
+                const Wave &w = waves[wi];
+                const int b = (int)(wi % nbuf);
+                if (wi + 1 < waves.size()) rc = upload_wave(wi + 1);       // device buffer (wi+1)%2 was last used by core(wi-1): done
+                if (rc != MASHGPU_OK) break;
+                std::future<void> next_pack;
+                if (wi + 2 < waves.size()) {
+                    MG_CUDA(ctx, cudaEventSynchronize(ctx->wave_copied[b]));   // upload(wi) must have drained pinned buffer b
+                    next_pack = std::async(std::launch::async, pack_wave, wi + 2);
+                }
+                MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->wave_copied[b], 0));
+                const uint64_t nu = w.unit_end - w.unit_begin;
+                SketchStream S;
+                S.d_codes = d_codes[b]; S.d_inval = d_inval[b]; S.unit_start = packed[wi].unit_start.data(); S.n_units = nu;
+                rc = sketch_stream_core(ctx, params, S, d_hashes, d_counts, d_n, ctx->stream, nullptr);
+                if (next_pack.valid()) next_pack.get();
+                if (rc != MASHGPU_OK) break;
+                MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.unit_begin * s, d_hashes, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+                MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.unit_begin, d_n, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+                if (out_counts)
+                    MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.unit_begin * s, d_counts, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+                MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            cudaStreamSynchronize(ctx->copy_stream);
+            return rc;
+        }
+    }
+
     uint64_t max_bytes = 16, max_units = 1;
     for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
     const uint64_t buf_bytes = ((max_bytes + 15) / 16) * 16 + 16;
@@ -566,6 +701,23 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
     }
     cudaStreamSynchronize(ctx->copy_stream);
     return rc;
+}
+
+extern "C" int mashgpu_host_pack(const mashgpu_sketch_params *params, uint64_t n_records, const char *const *seq, const uint64_t *len,
+                                 int threads, uint64_t *codes, uint64_t *runs, uint64_t runs_capacity, uint64_t *n_runs)
+{
+    if (!params || !codes || !n_runs || (n_records && (!seq || !len))) return MASHGPU_ERR_INVALID;
+    std::vector<PackSegment> segs;
+    uint64_t off = 0;
+    for (uint64_t r = 0; r < n_records; r++) {
+        segs.push_back(PackSegment{(const uint8_t *)seq[r], off, len[r]});
+        off += len[r] + 1;
+    }
+    std::vector<PackRun> found;
+    pack_stream(segs.data(), segs.size(), off, params->preserve_case, threads, codes, found);
+    *n_runs = found.size();
+    for (uint64_t i = 0; i < found.size() && i < runs_capacity; i++) { runs[2 * i] = found[i].start; runs[2 * i + 1] = found[i].len; }
+    return MASHGPU_OK;
 }
 
 extern "C" int mashgpu_hash_windows(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,

@@ -6,7 +6,9 @@ namespace mashgpu {
 
 // A device-resident byte stream split into sketch units.
 struct SketchStream {
-    const void *d_stream = nullptr;
+    const void *d_stream = nullptr;         // ASCII source, or
+    const uint64_t *d_codes = nullptr;      // packed source: 2-bit codes (32 positions per word) ...
+    const uint32_t *d_inval = nullptr;      // ... and the invalid-position bit mask (see pack.cpp)
     const uint64_t *unit_start = nullptr;   // host, n_units + 1
     uint64_t n_units = 0;
     bool force_keep_all = false;

@@ -146,3 +146,43 @@ def test_unsupported_alphabet_is_loud(gpu):
     p = gpu.params(k=9, s=100, alphabet=mash_b200.ALPHABET_PROTEIN, noncanonical=True)
     with pytest.raises(mash_b200.MashGpuError):
         gpu.sketch([b"MKVLAAGIVALLLAAGCSSAPQ"], p)
+
+
+def test_packed_feed_path_equals_ascii_path(gpu, oracle, monkeypatch):
+    # MASHGPU_HOST_PACK=1: mashgpu_sketch_batch packs to 2 bits/base (+ invalid runs) on the host and the scan kernel
+    # stages from the packed stream; default: pinned ASCII copy.  Same sketches either way.
+    p = gpu.params(k=21, s=500)
+    po = oracle.params(k=21)
+    g = synth_genome(31, 1_000_037, n_runs=40, lower_frac=0.07)
+    g[123456] = ord("*"); g[0] = ord("n"); g[-1] = 0
+    recs = [bytes(g), bytes(synth_genome(32, 33)), b"ACGTACGTACGTACGTACGTACGTACGTNNACGT", bytes(synth_genome(33, 777_777))]
+    uor = [0, 0, 1, 2]
+    ascii_ = gpu.sketch(recs, p, unit_of_record=uor, n_units=3, counts=True)
+    monkeypatch.setenv("MASHGPU_HOST_PACK", "1")
+    packed = gpu.sketch(recs, p, unit_of_record=uor, n_units=3, counts=True)
+    monkeypatch.delenv("MASHGPU_HOST_PACK")
+    for a, b in zip(packed, ascii_):
+        assert np.array_equal(a, b)
+    for u, rs in enumerate([[recs[0], recs[1]], [recs[2]], [recs[3]]]):
+        oh, _, olen = oracle.sketch_unit(rs, po, s=500)
+        assert packed[2][u] == olen
+        assert_sketch_equal(packed, u, oh)
+
+
+@pytest.mark.parametrize("pack", ["0", "1"])
+def test_multi_wave_batch(gpu, oracle, monkeypatch, pack):
+    # more than one wave (2^31 stream positions each): 3 units of ~0.9 Gbp would be slow for the oracle, so the wave
+    # size is not reachable here; instead check a batch whose units straddle many tiles and records
+    monkeypatch.setenv("MASHGPU_HOST_PACK", pack)
+    p = gpu.params(k=21, s=300)
+    po = oracle.params(k=21)
+    recs, uor = [], []
+    for u in range(12):
+        for r in range(1 + u % 3):
+            recs.append(bytes(synth_genome(500 + 10 * u + r, 40_000 + 7919 * u)))
+            uor.append(u)
+    out = gpu.sketch(recs, p, unit_of_record=uor, n_units=12)
+    for u in range(12):
+        oh, _, olen = oracle.sketch_unit([r for r, x in zip(recs, uor) if x == u], po, s=300)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)

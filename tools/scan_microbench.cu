@@ -34,13 +34,13 @@ int main(int argc, char **argv)
     a.stream = d; a.stream_len = n; a.tile_begin = 0; a.tile_end = (n + SCAN_TILE - 1) / SCAN_TILE; a.coarse_t = t;
     a.seed = 42; a.use64 = 1; a.mode = SCAN_SKETCH; a.unit_start = unit_start; a.n_units = 1; a.unit_t = unit_t; a.tab_off = tab_off;
     a.tab_log2 = log2c; a.tab_keys = keys; a.tab_cnt = cnt; a.unit_flags = flags; a.unit_maxhash = maxh; a.only_unit = -1;
-    int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<21, true>, SCAN_THREADS, 0);
+    int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<21, true, false>, SCAN_THREADS, 0);
     const int grid = per_sm * 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; i++) scan_kernel<21, true><<<grid, SCAN_THREADS>>>(a);
+    for (int i = 0; i < 2; i++) scan_kernel<21, true, false><<<grid, SCAN_THREADS>>>(a);
     cudaEventRecord(e0);
     const int reps = 5;
-    for (int i = 0; i < reps; i++) scan_kernel<21, true><<<grid, SCAN_THREADS>>>(a);
+    for (int i = 0; i < reps; i++) scan_kernel<21, true, false><<<grid, SCAN_THREADS>>>(a);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     uint32_t c0 = 0; std::vector<uint32_t> hc(cap); cudaMemcpy(hc.data(), cnt, cap * 4, cudaMemcpyDeviceToHost);
