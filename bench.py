@@ -45,7 +45,9 @@ def parse_args():
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
     ap.add_argument("--sketches", type=int, default=N_SKETCHES, help="sketches in the dist workload (default: the BASELINE config)")
     ap.add_argument("--e2e-units", type=int, default=0, help="genomes per e2e step (0 = as many of --units as pinned host memory allows)")
+    ap.add_argument("--reads", type=int, default=50_000_000, help="150 bp reads in the screen workload (default: the BASELINE config)")
     ap.add_argument("--skip-dist", action="store_true")
+    ap.add_argument("--skip-screen", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
@@ -370,6 +372,7 @@ def main():
 
     # ---------------- hot path 2: dist ---------------------------------------------------------------------------
     dist_obj = None
+    screen_obj = None
     if not args.skip_dist:
         del stream
         torch.cuda.empty_cache()
@@ -444,6 +447,57 @@ def main():
         dist_obj["roofline"]["frac"] = dist_obj["roofline"]["achieved"] / peaks["hbm_gbs"]
         job.close()
 
+        # ---------------- hot path 3: screen (configs[3], rank 0's sketches as the reference .msh) -----------------
+        if not args.skip_screen:
+            del o_numer, o_denom, o_dist, o_p, o_pass
+            torch.cuda.empty_cache()
+            n_reads, read_len = args.reads, 150
+            span_r = read_len + 1
+            # reads: '*' + 150 bases; half of them drawn as substrings of a synthetic "genome" pool so that the side bottom-s
+            # has real duplicates, all on the device
+            g = torch.Generator(device=dev); g.manual_seed(4242 + rank)
+            lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+            chunk_reads = min(n_reads, 2_000_000)
+            pool = lut[torch.randint(0, 4, (50_000_000,), generator=g, device=dev, dtype=torch.uint8).long()]
+            idx = torch.arange(read_len, device=dev)[None, :]
+            sset = mash_b200._capi._Set(H.data_ptr(), N.data_ptr(), L.data_ptr(), on_device=True, n=H.shape[0], stride=S)
+            chunk = torch.empty(chunk_reads * span_r + 64, dtype=torch.uint8, device=dev)
+
+            def make_chunk():
+                starts = torch.randint(0, pool.numel() - read_len, (chunk_reads,), generator=g, device=dev)
+                body = pool[(starts[:, None] + idx)]
+                err = torch.rand((chunk_reads, read_len), generator=g, device=dev) < 0.005
+                body = torch.where(err, lut[torch.randint(0, 4, (chunk_reads, read_len), generator=g, device=dev, dtype=torch.uint8).long()], body)
+                body = torch.where(torch.rand((chunk_reads, read_len), generator=g, device=dev) < 0.001, torch.full_like(body, ord("N")), body)
+                v = chunk[:chunk_reads * span_r].view(chunk_reads, span_r)
+                v[:, 0] = ord("*")
+                v[:, 1:] = body
+
+            make_chunk()
+            n_chunks = max(1, n_reads // chunk_reads)
+            sjob = mash_b200._capi.ScreenJob(eng, sset, None, p)
+            for _ in range(2):
+                sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)
+            eng.set_timing(True); eng.stats(reset=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)     # the same device chunk again: the table and mixture logic still run
+            res = sjob.finish()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            sstats = eng.stats(reset=True)
+            eng.set_timing(False)
+            sjob.close()
+            bases = n_chunks * chunk_reads * read_len
+            screen_obj = {"metric": "Gbp_per_s_screened", "value": world * bases / dt / 1e9, "unit": "Gbp/s",
+                          "workload": f"configs[3]: {H.shape[0]}-sketch reference table ({int(N.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
+                                      f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads (one chunk re-fed; inputs in HBM), finish() included",
+                          "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"], "gpu_launches": int(sstats["kernel_launches"]),
+                          "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum())}
+        else:
+            screen_obj = None
+
     # ---------------- CPU baseline on rank 0 --------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -464,7 +518,7 @@ def main():
                            "l2": "inputs larger than L2 (one step streams %.1f GB)" % (bases_per_step / 1e9),
                            "parallelism": f"records sharded over {world} rank(s), no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]),
-                "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "sanity": sanity,
+                "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "screen": screen_obj, "sanity": sanity,
                 "exact_reruns": int(stats["exact_reruns"])}
         print(json.dumps(line))
     if dist_on:

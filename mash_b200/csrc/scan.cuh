@@ -29,7 +29,7 @@ constexpr int SCAN_WARP_WORDS = SCAN_WARP_TILE / 8 + SCAN_HALO_WORDS;   // 136 n
 constexpr int SCAN_WARP_VECS = SCAN_WARP_WORDS / 2;                     // 68 16-byte vectors
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
 
-enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2 };
+enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2, SCAN_COUNT = 3 };
 
 struct ScanArgs {
     const uint8_t *stream;        // flat byte stream (ASCII source; NULL when the packed source is used)
@@ -51,6 +51,8 @@ struct ScanArgs {
     const uint32_t *tab_log2;     // per-unit log2(capacity)
     uint64_t *tab_keys;
     uint32_t *tab_cnt;
+    uint64_t *tab_first;          // optional (multiplicity counts): stream position of the first / last occurrence per slot,
+    uint64_t *tab_last;           //   needed to reproduce MinHashHeap's top-of-heap counting quirk (sketch.cu, quirk_kernel)
     uint32_t *unit_flags;         // bit0: table overflow
     uint32_t *unit_maxhash;       // occurrences of the hash value 2^64-1 (cannot be a table key)
     int64_t only_unit;            // >= 0: ignore every other unit (exact re-run)
@@ -62,6 +64,9 @@ struct ScanArgs {
     // dump
     uint64_t *out_hash;
     uint8_t *out_valid;
+    // SCAN_COUNT: occurrences of one hash at stream positions [count_lo, count_hi]
+    uint64_t count_target, count_lo, count_hi;
+    uint32_t *count_out;
 };
 
 __device__ __forceinline__ uint32_t slot_hash(uint64_t key, uint32_t log2cap)
@@ -69,8 +74,8 @@ __device__ __forceinline__ uint32_t slot_hash(uint64_t key, uint32_t log2cap)
     return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap));
 }
 
-// Insert-or-count into an open-addressing table. Returns false when the table is full.
-__device__ __forceinline__ bool table_add(uint64_t *keys, uint32_t *cnt, uint32_t log2cap, uint64_t key)
+// Insert-or-count into an open-addressing table. Returns the slot, or -1 when the table is full.
+__device__ __forceinline__ int64_t table_add(uint64_t *keys, uint32_t *cnt, uint32_t log2cap, uint64_t key)
 {
     const uint32_t mask = (1u << log2cap) - 1;
     uint32_t slot = slot_hash(key, log2cap);
@@ -78,11 +83,11 @@ __device__ __forceinline__ bool table_add(uint64_t *keys, uint32_t *cnt, uint32_
         unsigned long long prev = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
         if (prev == EMPTY_KEY || prev == key) {
             atomicAdd(&cnt[slot], 1u);
-            return true;
+            return slot;
         }
         slot = (slot + 1) & mask;
     }
-    return false;
+    return -1;
 }
 
 // Slow path: a hash passed the tile's coarse threshold.
@@ -93,6 +98,10 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
     if (a.mode == SCAN_DUMP) {
         a.out_hash[pos] = hash;
         a.out_valid[pos] = 1;
+        return;
+    }
+    if (a.mode == SCAN_COUNT) {
+        if (hash == a.count_target && pos >= a.count_lo && pos <= a.count_hi) atomicAdd(a.count_out, 1u);
         return;
     }
     if (a.mode == SCAN_SCREEN && hash <= a.ref_hmax) {
@@ -116,8 +125,12 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
     if (a.only_unit >= 0 && (int64_t)u != a.only_unit) return;
     if (hash > a.unit_t[u]) return;
     if (hash == EMPTY_KEY) { atomicAdd(&a.unit_maxhash[u], 1u); return; }
-    if (!table_add(a.tab_keys + a.tab_off[u], a.tab_cnt + a.tab_off[u], a.tab_log2[u], hash))
-        atomicOr(&a.unit_flags[u], 1u);
+    const int64_t slot = table_add(a.tab_keys + a.tab_off[u], a.tab_cnt + a.tab_off[u], a.tab_log2[u], hash);
+    if (slot < 0) { atomicOr(&a.unit_flags[u], 1u); return; }
+    if (a.tab_first) {
+        atomicMin((unsigned long long *)&a.tab_first[a.tab_off[u] + slot], (unsigned long long)pos);
+        atomicMax((unsigned long long *)&a.tab_last[a.tab_off[u] + slot], (unsigned long long)pos);
+    }
 }
 
 // Warp-uniform wrapper around the slow path.  The hot loop never branches on a per-lane condition: a window's pass

@@ -130,6 +130,61 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     }
 }
 
+__device__ __forceinline__ int64_t table_find(const uint64_t *keys, uint32_t log2cap, uint64_t key)
+{
+    const uint32_t mask = (1u << log2cap) - 1;
+    uint32_t slot = slot_hash(key, log2cap);
+    for (;;) {
+        uint64_t k = keys[slot];
+        if (k == key) return slot;
+        if (k == EMPTY_KEY) return -1;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// Multiplicity counts, the reference's way.  MinHashHeap::tryInsert (MinHashHeap.cpp:68-74) only accepts a hash when
+// the heap is not full or the hash is strictly below the current top, so once all s final hashes have been seen
+// (stream position t* = the latest first occurrence among them) further occurrences of the largest final hash are
+// neither inserted nor counted; every other count is the true multiplicity (oracle mo_heap_try_insert).
+// One CTA per full sketch: t* by max-reduction, then count[last] = occurrences of the largest hash at positions <= t*:
+// equal to the table count if its last occurrence is <= t*, 1 if it was the last hash to arrive, otherwise the unit
+// is flagged (bit 3) for a targeted recount over [unit start, t*].
+__global__ void __launch_bounds__(SEL_THREADS) quirk_kernel(
+    uint32_t unit_begin, uint32_t n_units, uint32_t s, const uint64_t *out_hashes, uint32_t *out_counts, const uint32_t *out_n,
+    const uint64_t *tab_off, const uint32_t *tab_log2, const uint64_t *tab_keys, const uint32_t *tab_cnt,
+    const uint64_t *tab_first, const uint64_t *tab_last, uint32_t *unit_flags, uint64_t *quirk_target, uint64_t *quirk_tstar)
+{
+    __shared__ unsigned long long tstar_s;
+    const uint32_t u = unit_begin + blockIdx.x;
+    if (u >= unit_begin + n_units) return;
+    if (unit_flags[u] & 7u) return;                 // will be re-run
+    if (out_n[u] < s) return;                       // heap never full: every count is exact
+    const uint64_t *keys = tab_keys + tab_off[u];
+    const uint32_t lg = tab_log2[u];
+    if (threadIdx.x == 0) tstar_s = 0;
+    __syncthreads();
+    unsigned long long local = 0;
+    for (uint32_t i = threadIdx.x; i < s; i += SEL_THREADS) {
+        int64_t slot = table_find(keys, lg, out_hashes[(uint64_t)u * s + i]);
+        if (slot >= 0) local = max(local, (unsigned long long)tab_first[tab_off[u] + slot]);
+    }
+    atomicMax(&tstar_s, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t tstar = tstar_s;
+        const uint64_t key = out_hashes[(uint64_t)u * s + s - 1];
+        int64_t slot = table_find(keys, lg, key);
+        if (slot >= 0) {
+            const uint32_t c = tab_cnt[tab_off[u] + slot];
+            const uint64_t f = tab_first[tab_off[u] + slot], l = tab_last[tab_off[u] + slot];
+            if (c > 1 && l > tstar) {
+                if (f == tstar) out_counts[(uint64_t)u * s + s - 1] = 1;
+                else { quirk_target[u] = key; quirk_tstar[u] = tstar; atomicOr(&unit_flags[u], 8u); }
+            }
+        }
+    }
+}
+
 // Large tables: compact non-empty keys to scratch (then cub radix sort on the host side of this file).
 __global__ void compact_table_kernel(const uint64_t *keys, uint64_t cap, uint64_t *out, unsigned long long *out_n)
 {
@@ -226,6 +281,21 @@ static int launch_scan(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     return MASHGPU_OK;
 }
 
+// Occurrences of `target` at stream positions [lo, hi] -> d_count_slot (one uint32 in device memory)
+static int recount_hash(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const ScanArgs &base, uint64_t lo, uint64_t hi, uint64_t target,
+                        uint32_t *d_count_slot, cudaStream_t st)
+{
+    ScanArgs c = base;
+    c.mode = SCAN_COUNT;
+    c.tile_begin = lo / SCAN_TILE;
+    c.tile_end = hi / SCAN_TILE + 1;
+    c.tile_tmax = nullptr;
+    c.coarse_t = target;
+    c.count_target = target; c.count_lo = lo; c.count_hi = hi; c.count_out = d_count_slot;
+    MG_CUDA(ctx, cudaMemsetAsync(d_count_slot, 0, 4, st));
+    return launch_scan(ctx, p, c, st);
+}
+
 // Exact re-run of one unit with growing thresholds, ending at keep-all (always succeeds).
 static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S, uint32_t u,
                       uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
@@ -241,13 +311,20 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
         plan_unit(p, span, factor, &t, &lg);
         const bool keep_all = (t == EMPTY_KEY);
         const uint64_t cap = 1ull << lg;
-        DevBuf<uint64_t> keys; DevBuf<uint32_t> cnt; DevBuf<uint64_t> meta;   // meta: [t, off]
+        DevBuf<uint64_t> keys; DevBuf<uint32_t> cnt; DevBuf<uint64_t> meta;   // meta: [t, off, quirk target, quirk t*]
         DevBuf<uint32_t> small;                                                   // [log2, flags, maxhash]
-        if (keys.alloc(cap) != cudaSuccess || cnt.alloc(cap) != cudaSuccess || meta.alloc(2) != cudaSuccess || small.alloc(3) != cudaSuccess)
+        DevBuf<uint64_t> first, last;
+        const bool want_counts = d_out_counts != nullptr;
+        if (keys.alloc(cap) != cudaSuccess || cnt.alloc(cap) != cudaSuccess || meta.alloc(4) != cudaSuccess || small.alloc(3) != cudaSuccess ||
+            (want_counts && (first.alloc(cap) != cudaSuccess || last.alloc(cap) != cudaSuccess)))
             return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory in exact re-run (table of %llu slots)", (unsigned long long)cap);
         MG_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * 8, st));
         MG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, cap * 4, st));
-        uint64_t h_meta[2] = {t, 0};
+        if (want_counts) {
+            MG_CUDA(ctx, cudaMemsetAsync(first.p, 0xFF, cap * 8, st));
+            MG_CUDA(ctx, cudaMemsetAsync(last.p, 0, cap * 8, st));
+        }
+        uint64_t h_meta[4] = {t, 0, 0, 0};
         uint32_t h_small[3] = {lg, 0, 0};
         MG_CUDA(ctx, cudaMemcpyAsync(meta.p, h_meta, sizeof h_meta, cudaMemcpyHostToDevice, st));
         MG_CUDA(ctx, cudaMemcpyAsync(small.p, h_small, sizeof h_small, cudaMemcpyHostToDevice, st));
@@ -265,6 +342,8 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
         a.unit_maxhash = small.p + 2 - u;
         a.tab_keys = keys.p;
         a.tab_cnt = cnt.p;
+        a.tab_first = want_counts ? first.p : nullptr;
+        a.tab_last = want_counts ? last.p : nullptr;
         MG_TRY(launch_scan(ctx, p, a, st));
         MG_CUDA(ctx, cudaMemcpyAsync(h_small, small.p, sizeof h_small, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
@@ -296,6 +375,16 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
                                                                d_out_counts ? d_out_counts + (uint64_t)u * s : nullptr);
         ctx->kernel_launches++;
         MG_CUDA(ctx, cudaMemcpyAsync(d_out_n + u, &m, 4, cudaMemcpyHostToDevice, st));
+        if (want_counts && m == s) {   // the reference's top-of-heap counting quirk (see quirk_kernel)
+            quirk_kernel<<<1, SEL_THREADS, 0, st>>>(u, 1, s, d_out_hashes, d_out_counts, d_out_n, meta.p + 1 - u, small.p - u, keys.p, cnt.p,
+                                                    first.p, last.p, small.p + 1 - u, meta.p + 2 - u, meta.p + 3 - u);
+            ctx->kernel_launches++;
+            MG_CUDA(ctx, cudaMemcpyAsync(h_small, small.p, sizeof h_small, cudaMemcpyDeviceToHost, st));
+            MG_CUDA(ctx, cudaMemcpyAsync(h_meta, meta.p, sizeof h_meta, cudaMemcpyDeviceToHost, st));
+            MG_CUDA(ctx, cudaStreamSynchronize(st));
+            if (h_small[1] & 8u)
+                MG_TRY(recount_hash(ctx, p, base, S.unit_start[u], h_meta[3], h_meta[2], d_out_counts + (uint64_t)u * s + s - 1, st));
+        }
         MG_CUDA(ctx, cudaStreamSynchronize(st));
         return MASHGPU_OK;
     }
@@ -320,7 +409,10 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     for (uint32_t u = 0; u < n_units; u++) {
         uint64_t span = S.unit_start[u + 1] - S.unit_start[u];
         plan_unit(p, span, S.force_keep_all ? 0.0 : SURVIVOR_FACTOR, &h_t[u], &h_log2[u]);
-        if (S.t_cap && h_t[u] > S.t_cap_value) h_t[u] = S.t_cap_value;
+        // screen, mixture already holds s hashes: exactly the hashes <= its s-th smallest can still matter -- use that
+        // value as the threshold whether the planned one is larger (fewer candidates) or smaller (it would miss some and
+        // force an exact re-run when the chunk is full of repeats, e.g. reads at 5x coverage)
+        if (S.t_cap) h_t[u] = S.t_cap_value;
         h_off[u] = slots;
         slots += 1ull << h_log2[u];
     }
@@ -331,6 +423,15 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     d_keys.p = ctx->sc_keys.get<uint64_t>(slots); d_cnt.p = ctx->sc_cnt.get<uint32_t>(slots); d_tmax.p = ctx->sc_tmax.get<uint64_t>(ntiles);
     if (!d_start.p || !d_t.p || !d_off.p || !d_log2.p || !d_flags.p || !d_maxhash.p || !d_keys.p || !d_cnt.p || !d_tmax.p)
         return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (%llu candidate slots for %u units)", (unsigned long long)slots, n_units);
+    const bool want_counts = d_out_counts != nullptr;
+    uint64_t *d_first = nullptr, *d_last = nullptr, *d_qtarget = nullptr, *d_qtstar = nullptr;
+    if (want_counts) {
+        d_first = ctx->sc_first.get<uint64_t>(slots); d_last = ctx->sc_last.get<uint64_t>(slots);
+        d_qtarget = ctx->sc_qtarget.get<uint64_t>(n_units); d_qtstar = ctx->sc_qtstar.get<uint64_t>(n_units);
+        if (!d_first || !d_last || !d_qtarget || !d_qtstar) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (first/last occurrence tables)");
+        MG_CUDA(ctx, cudaMemsetAsync(d_first, 0xFF, slots * 8ull, st));
+        MG_CUDA(ctx, cudaMemsetAsync(d_last, 0, slots * 8ull, st));
+    }
     MG_CUDA(ctx, cudaMemcpyAsync(d_start.p, S.unit_start, (n_units + 1) * 8ull, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaMemcpyAsync(d_t.p, h_t.data(), n_units * 8ull, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_off.data(), n_units * 8ull, cudaMemcpyHostToDevice, st));
@@ -361,6 +462,8 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     a.tab_cnt = d_cnt.p;
     a.unit_flags = d_flags.p;
     a.unit_maxhash = d_maxhash.p;
+    a.tab_first = d_first;
+    a.tab_last = d_last;
     a.only_unit = -1;
     if (probe) {
         a.ref_keys = probe->keys; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
@@ -392,15 +495,32 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
                                                                      d_out_hashes, d_out_counts, d_out_n);
     ctx->kernel_launches++;
     MG_CUDA(ctx, cudaGetLastError());
+    if (want_counts) {
+        quirk_kernel<<<n_units, SEL_THREADS, 0, st>>>(0, n_units, s, d_out_hashes, d_out_counts, d_out_n, d_off.p, d_log2.p, d_keys.p, d_cnt.p,
+                                                      d_first, d_last, d_flags.p, d_qtarget, d_qtstar);
+        ctx->kernel_launches++;
+        MG_CUDA(ctx, cudaGetLastError());
+    }
 
     std::vector<uint32_t> h_flags(n_units);
     MG_CUDA(ctx, cudaMemcpyAsync(h_flags.data(), d_flags.p, n_units * 4ull, cudaMemcpyDeviceToHost, st));
     MG_CUDA(ctx, cudaStreamSynchronize(st));
+    bool any_recount = false;
+    for (uint32_t u = 0; u < n_units; u++) any_recount |= (h_flags[u] & 8u) && !(h_flags[u] & 7u);
+    std::vector<uint64_t> h_qtarget, h_qtstar;
+    if (any_recount) {
+        h_qtarget.resize(n_units); h_qtstar.resize(n_units);
+        MG_CUDA(ctx, cudaMemcpyAsync(h_qtarget.data(), d_qtarget, n_units * 8ull, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaMemcpyAsync(h_qtstar.data(), d_qtstar, n_units * 8ull, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     for (uint32_t u = 0; u < n_units; u++) {
         if (h_flags[u] == 0) continue;
         a.mode = SCAN_SKETCH;    // reference-table hits were already counted in the first pass
-        MG_TRY(rerun_unit(ctx, p, S, u, d_out_hashes, d_out_counts, d_out_n, st, a));
+        if (h_flags[u] & 7u) MG_TRY(rerun_unit(ctx, p, S, u, d_out_hashes, d_out_counts, d_out_n, st, a));
+        else MG_TRY(recount_hash(ctx, p, a, S.unit_start[u], h_qtstar[u], h_qtarget[u], d_out_counts + (uint64_t)u * s + s - 1, st));
     }
+    if (any_recount) MG_CUDA(ctx, cudaStreamSynchronize(st));
     return MASHGPU_OK;
 }
 
