@@ -64,6 +64,9 @@ struct ScanArgs {
     // dump
     uint64_t *out_hash;
     uint8_t *out_valid;
+    // byte-alphabet kernels (any alphabet, non-canonical): byte -> itself (upper-cased unless preserve_case) if it is in
+    // the alphabet, else 0
+    uint8_t byte_lut[256];
     // SCAN_COUNT: occurrences of one hash at stream positions [count_lo, count_hi]
     uint64_t count_target, count_lo, count_hi;
     uint32_t *count_out;
@@ -155,9 +158,16 @@ static __device__ __noinline__ void scan_emit_warp(const ScanArgs &a, bool pass,
         const uint32_t hi = __shfl_sync(0xFFFFFFFFu, hash_hi, src);
         const uint32_t lp = __shfl_sync(0xFFFFFFFFu, local_pos, src);
         if (lane == 0) {
-            uint32_t bad = 0;
-            for (int i = 0; i < k; i++) bad |= sm_tile[(lp + i) >> 3] >> (4 * ((lp + i) & 7));
-            if (!(bad & 8u) && ((((uint64_t)hi) << 32) | lo) <= tmax) scan_emit(a, lo, hi, tile_base, lp);
+            bool ok = true;
+            if (k > 0) {            // nibble tile (DNA kernels): bit 3 marks a position outside the alphabet
+                uint32_t bad = 0;
+                for (int i = 0; i < k; i++) bad |= sm_tile[(lp + i) >> 3] >> (4 * ((lp + i) & 7));
+                ok = !(bad & 8u);
+            } else {                // byte tile (byte-alphabet kernels): 0 marks a position outside the alphabet
+                const uint8_t *bytes = reinterpret_cast<const uint8_t *>(sm_tile);
+                for (int i = 0; i < -k; i++) ok &= bytes[lp + i] != 0;
+            }
+            if (ok && ((((uint64_t)hi) << 32) | lo) <= tmax) scan_emit(a, lo, hi, tile_base, lp);
         }
         __syncwarp();
     }
@@ -424,9 +434,86 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Byte-alphabet kernel: any alphabet (protein, custom -z), k-mers hashed as they stand (the reference makes every
+// non-nucleotide alphabet non-canonical, sketchParameterSetup.cpp:79-95).  Same warp-private tiling; the tile is kept
+// as bytes (alphabet bytes, 0 = outside the alphabet), a lane takes 4 consecutive window starts per block and builds each
+// window with PRMT byte funnels.  Validity, exact threshold and table work stay in the shared slow path.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GEN_WARP_WORDS = SCAN_WARP_TILE / 4 + 16;     // 1024 + 64 bytes
+
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_bytes_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int NWB = (K + 3) / 4;              // words per k-mer
+    constexpr int BWB = (K + 3 + 3) / 4;          // words per block of 4 window starts
+    constexpr int NA = 2 * ((K + 7) / 8);         // words murmur3_h1 expects
+    __shared__ __align__(16) uint32_t sm_all[SCAN_WARPS][GEN_WARP_WORDS];
+    __shared__ uint8_t lut[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *sm = sm_all[warp];
+    for (int i = threadIdx.x; i < 256; i += SCAN_THREADS) lut[i] = a.byte_lut[i];
+    __syncthreads();
+
+    const uint64_t wt_begin = a.tile_begin * (SCAN_TILE / SCAN_WARP_TILE), wt_end = a.tile_end * (SCAN_TILE / SCAN_WARP_TILE);
+    const uint64_t wt_stride = (uint64_t)gridDim.x * SCAN_WARPS;
+    for (uint64_t wt = wt_begin + (uint64_t)blockIdx.x * SCAN_WARPS + warp; wt < wt_end; wt += wt_stride) {
+        const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
+        // stage 1088 bytes = 68 vectors of 16: lanes take vectors lane, lane+32, 64 + lane%4
+        const int vec[3] = {lane, lane + 32, 64 + (lane & 3)};
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const uint64_t off = base + 16ull * vec[t];
+            uint4 q = load16(a.stream, off, a.stream_len);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint64_t pos = off + 4 * j + b;
+                    const uint32_t c = pos < a.stream_len ? lut[(w[j] >> (8 * b)) & 0xFFu] : 0u;
+                    o |= c << (8 * b);
+                }
+                w[j] = o;
+            }
+            *reinterpret_cast<uint4 *>(sm + 4 * vec[t]) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+        const uint64_t tmax = a.tile_tmax ? a.tile_tmax[base / SCAN_TILE] : a.coarse_t;
+#pragma unroll 1
+        for (int g = lane; g < SCAN_WARP_TILE / 4; g += 32) {
+            uint32_t b[BWB];
+#pragma unroll
+            for (int i = 0; i < BWB; i++) b[i] = sm[g + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t asc[NA];
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    uint32_t v = 0;
+                    if (i < NWB) {
+                        const uint32_t lo = b[i], hi = (i + 1 < BWB) ? b[i + 1] : 0u;
+                        v = j == 0 ? lo : __funnelshift_r(lo, hi, 8 * j);
+                        const int rem = K - 4 * i;
+                        if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+                    }
+                    asc[i] = v;
+                }
+                u64x2 h = murmur3_h1<K, NA>(asc, a.seed);
+                if (!a.use64) h.hi = 0;
+                const bool pass = a.use64 ? (h.hi <= (uint32_t)(tmax >> 32)) : (h.lo <= (uint32_t)tmax);
+                if (__any_sync(0xFFFFFFFFu, pass)) scan_emit_warp(a, pass, h.lo, h.hi, base, 4u * g + j, sm, -K, tmax);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Host-side launcher table (defined in scan_inst_*.cu)
 typedef void (*scan_launch_fn)(const ScanArgs &a, int grid, cudaStream_t stream);
 typedef int (*scan_occupancy_fn)();
 scan_launch_fn get_scan_launcher(int k, bool canonical, bool packed);
+scan_launch_fn get_bytes_launcher(int k);
 
 }  // namespace mashgpu

@@ -148,6 +148,9 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
     if (!refs || !job_out) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
     if (refs->n && (!refs->hashes || !refs->n_hashes)) return fail(ctx, MASHGPU_ERR_INVALID, "reference set has NULL arrays");
     if (params->sketch_size > (1u << 13)) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "screen supports sketch_size <= 8192");
+    if (!is_dna_alphabet(params))
+        return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "screen is only provided for nucleotide sketches (the reference 6-frame-translates "
+                                                  "the mixture for amino-acid sketches, CommandScreen.cpp:516-530: out of scope)");
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     mashgpu_screen_job *job = new mashgpu_screen_job();

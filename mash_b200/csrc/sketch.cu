@@ -27,6 +27,19 @@ scan_launch_fn get_scan_launcher_part1(int, bool, bool);
 scan_launch_fn get_scan_launcher_part2(int, bool, bool);
 scan_launch_fn get_scan_launcher_part3(int, bool, bool);
 
+scan_launch_fn get_bytes_launcher_part0(int);
+scan_launch_fn get_bytes_launcher_part1(int);
+scan_launch_fn get_bytes_launcher_part2(int);
+scan_launch_fn get_bytes_launcher_part3(int);
+
+scan_launch_fn get_bytes_launcher(int k)
+{
+    if (auto f = get_bytes_launcher_part0(k)) return f;
+    if (auto f = get_bytes_launcher_part1(k)) return f;
+    if (auto f = get_bytes_launcher_part2(k)) return f;
+    return get_bytes_launcher_part3(k);
+}
+
 scan_launch_fn get_scan_launcher(int k, bool canonical, bool packed)
 {
     if (auto f = get_scan_launcher_part0(k, canonical, packed)) return f;
@@ -233,12 +246,22 @@ int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p)
     int n = 0;
     for (int i = 0; i < 256; i++) n += p->alphabet[i] != 0;
     bool dna = n == 4 && p->alphabet['A'] && p->alphabet['C'] && p->alphabet['G'] && p->alphabet['T'];
-    if (dna && (p->use64 != 0) != (p->kmer_size > 16))
-        return fail(ctx, MASHGPU_ERR_INVALID, "use64=%d contradicts the reference rule alphabetSize^k > 2^32 for k=%d (Sketch.cpp:1136)", p->use64, p->kmer_size);
-    if (!dna)
+    if (n == 0) return fail(ctx, MASHGPU_ERR_INVALID, "empty alphabet");
+    if ((p->use64 != 0) != (std::pow((double)n, (double)p->kmer_size) > std::pow(2.0, 32.0)))
+        return fail(ctx, MASHGPU_ERR_INVALID, "use64=%d contradicts the reference rule alphabetSize^k > 2^32 for k=%d, %d letters (Sketch.cpp:1136)", p->use64, p->kmer_size, n);
+    if (p->alphabet[0]) return fail(ctx, MASHGPU_ERR_INVALID, "byte 0 cannot be an alphabet letter");
+    if (!dna && !p->noncanonical)
         return fail(ctx, MASHGPU_ERR_UNSUPPORTED,
-                    "alphabet other than {A,C,G,T} is not on the GPU path yet (byte-alphabet kernels pending)");
+                    "canonical k-mers are only defined for the alphabet {A,C,G,T}; other alphabets must be non-canonical "
+                    "(the reference forces -n for -a / -z, sketchParameterSetup.cpp:79-95)");
     return MASHGPU_OK;
+}
+
+bool is_dna_alphabet(const mashgpu_sketch_params *p)
+{
+    int n = 0;
+    for (int i = 0; i < 256; i++) n += p->alphabet[i] != 0;
+    return n == 4 && p->alphabet['A'] && p->alphabet['C'] && p->alphabet['G'] && p->alphabet['T'];
 }
 
 static double kmer_space_of(const mashgpu_sketch_params *p)
@@ -266,9 +289,19 @@ void plan_unit(const mashgpu_sketch_params *p, uint64_t span, double factor, uin
     *log2_out = std::max(4u, ceil_log2((uint64_t)(TABLE_SLACK * expect) + 2));
 }
 
+void fill_byte_lut(ScanArgs &a, const mashgpu_sketch_params *p)
+{
+    for (int b = 0; b < 256; b++) {
+        int u = (!p->preserve_case && b > 96 && b < 123) ? b - 32 : b;     // reference Sketch.cpp:524-530
+        a.byte_lut[b] = p->alphabet[u] ? (uint8_t)u : 0;
+    }
+}
+
 static int launch_scan(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const ScanArgs &a, cudaStream_t st)
 {
-    scan_launch_fn fn = get_scan_launcher(p->kmer_size, !p->noncanonical, a.codes != nullptr);
+    const bool dna = is_dna_alphabet(p);
+    if (!dna && !a.stream) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "the packed source only carries the alphabet {A,C,G,T}");
+    scan_launch_fn fn = dna ? get_scan_launcher(p->kmer_size, !p->noncanonical, a.codes != nullptr) : get_bytes_launcher(p->kmer_size);
     if (!fn) return fail(ctx, MASHGPU_ERR_INVALID, "no scan kernel for k=%d", p->kmer_size);
     uint64_t ntiles = a.tile_end - a.tile_begin;
     if (ntiles == 0) return MASHGPU_OK;
@@ -452,6 +485,7 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     a.seed = p->seed;
     a.use64 = p->use64;
     a.preserve_case = p->preserve_case;
+    fill_byte_lut(a, p);
     a.mode = probe ? SCAN_SCREEN : SCAN_SKETCH;
     a.unit_start = d_start.p;
     a.n_units = n_units;
@@ -628,7 +662,7 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
     // packed path removes the PCIe bound (4x fewer bytes).
     {
         const char *env = getenv("MASHGPU_HOST_PACK");
-        if (env && env[0] == '1') {
+        if (env && env[0] == '1' && is_dna_alphabet(params)) {
             uint64_t max_bytes = 32, max_units = 1;
             for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
             const uint64_t max_tiles = (max_bytes + SCAN_TILE - 1) / SCAN_TILE;
@@ -864,6 +898,7 @@ extern "C" int mashgpu_hash_windows(mashgpu_ctx *ctx, const mashgpu_sketch_param
     a.tile_begin = 0; a.tile_end = (len + SCAN_TILE - 1) / SCAN_TILE;
     a.coarse_t = EMPTY_KEY;
     a.seed = params->seed; a.use64 = params->use64; a.preserve_case = params->preserve_case;
+    fill_byte_lut(a, params);
     a.mode = SCAN_DUMP; a.only_unit = -1;
     a.out_hash = d_hash.p; a.out_valid = d_valid.p;
     MG_TRY(launch_scan(ctx, params, a, st));

@@ -25,6 +25,7 @@ struct ScreenProbe {
 };
 
 int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p);
+bool is_dna_alphabet(const mashgpu_sketch_params *p);
 int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S,
                        uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
                        const ScreenProbe *probe);

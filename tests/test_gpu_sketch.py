@@ -155,11 +155,56 @@ def test_union_property_full_size(gpu):
     assert np.all(np.diff(h[2].astype(object)) > 0)      # ascending, distinct
 
 
-def test_unsupported_alphabet_is_loud(gpu):
+PROTEIN = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def synth_protein(seed, n):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = np.frombuffer((PROTEIN + "XBZ*acdefg").encode(), np.uint8)
+    w = np.array([1.0] * 20 + [0.02, 0.01, 0.01, 0.01] + [0.05] * 6)
+    return a[rng.choice(a.size, n, p=w / w.sum())]
+
+
+@pytest.mark.parametrize("k,alphabet,preserve_case", [(9, PROTEIN, False), (7, PROTEIN, False), (9, PROTEIN, True), (21, "ACGTN", False),
+                                                       (12, "ACGU", False), (32, PROTEIN, False), (1, "AB", False), (5, "acgt", True)])
+def test_byte_alphabets_every_window(gpu, oracle, k, alphabet, preserve_case):
+    # `mash sketch -a` (protein, k=9) and `-z <alphabet>`: non-canonical, any byte alphabet (sketchParameterSetup.cpp:79-95)
+    p = gpu.params(k=k, s=100, alphabet=alphabet, noncanonical=True, preserve_case=preserve_case)
+    po = oracle.params(k=k, alphabet=alphabet, noncanonical=True, preserve_case=preserve_case)
+    assert p.use64 == po.use64 and bytes(p.alphabet) == bytes(po.alphabet)
+    seq = synth_protein(k, 30_000) if "D" in alphabet else synth_genome(k, 30_000, n_runs=5, lower_frac=0.2)
+    if alphabet == "ACGU":
+        seq = seq.copy(); seq[seq == ord("T")] = ord("U")
+    h, v = gpu.hash_windows(seq, p)
+    want = oracle.all_hashes(bytes(seq), po)
+    assert int(v.sum()) == want.size and np.array_equal(h[v], want)
+
+
+@pytest.mark.parametrize("k,s", [(9, 1000), (7, 400), (5, 50)])
+def test_protein_sketches_match_oracle(gpu, oracle, k, s):
+    p = gpu.params(k=k, s=s, alphabet=PROTEIN, noncanonical=True)
+    po = oracle.params(k=k, alphabet=PROTEIN, noncanonical=True)
+    units = [[bytes(synth_protein(1, 400_000))], [bytes(synth_protein(2, 3_000)), b"MKV", bytes(synth_protein(3, 50_000))], [b"M" * 2000], []]
+    recs, uor = [], []
+    for u, rs in enumerate(units):
+        recs += rs; uor += [u] * len(rs)
+    out = gpu.sketch(recs, p, unit_of_record=uor, n_units=len(units), counts=True)
+    for u, rs in enumerate(units):
+        oh, oc, olen = oracle.sketch_unit(rs, po, s=s, counts=True)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)
+        assert np.array_equal(out[3][u, :out[1][u]], oc)
+    # murmur KAT from the reference object code: MKVLAAGIV, k=9 -> 10212611784005380714
+    h, v = gpu.hash_windows(b"MKVLAAGIV", gpu.params(k=9, s=1, alphabet=PROTEIN, noncanonical=True))
+    assert v[0] and int(h[0]) == 10212611784005380714
+
+
+def test_canonical_needs_nucleotide_alphabet(gpu):
     import mash_b200
-    p = gpu.params(k=9, s=100, alphabet=mash_b200.ALPHABET_PROTEIN, noncanonical=True)
-    with pytest.raises(mash_b200.MashGpuError):
+    p = gpu.params(k=9, s=100, alphabet=PROTEIN, noncanonical=False)
+    with pytest.raises(mash_b200.MashGpuError) as e:
         gpu.sketch([b"MKVLAAGIVALLLAAGCSSAPQ"], p)
+    assert e.value.code == 3
 
 
 def test_packed_feed_path_equals_ascii_path(gpu, oracle, monkeypatch):
