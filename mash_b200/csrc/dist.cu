@@ -160,6 +160,42 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
     }
 }
 
+// General fallback for sketch sizes whose tiles do not fit in shared memory (s > ~1035): one thread per pair, rows read
+// straight from global memory (L1/L2).  Same arithmetic, an order of magnitude slower; large -s is the rare case.
+__global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)a.q_count * a.n_ref;
+    if (t >= total) return;
+    const uint32_t q = a.q_begin + (uint32_t)(t / a.n_ref), r = (uint32_t)(t % a.n_ref);
+    const uint32_t *A = a.ranks + (a.ref_row0 + r) * (uint64_t)a.P;
+    const uint32_t *B = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
+    uint32_t i = 0, j = 0;
+    uint32_t va = A[0], vb = B[0];
+    for (uint32_t step = 0; step < a.S; step++) {
+        const bool adv_a = va <= vb, adv_b = vb <= va;
+        if (adv_a) va = A[++i];
+        if (adv_b) vb = B[++j];
+    }
+    const uint32_t nA = a.ref_n[r];
+    const uint32_t bogus = i > nA ? i - nA : 0;
+    const uint32_t denom = a.S - bogus;
+    const uint32_t common = (i - bogus) + (j - bogus) - denom;
+    const double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
+    bool pass = true;
+    double p = 0.0;
+    if (a.max_distance >= 0 && dist > a.max_distance) pass = false;
+    else {
+        p = mash_pvalue(common, a.ref_len[r], a.qry_len[q], a.kmer_space, denom);
+        if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;
+    }
+    if (a.numer) a.numer[t] = common;
+    if (a.denom) a.denom[t] = denom;
+    if (a.distance) a.distance[t] = dist;
+    if (a.pvalue) a.pvalue[t] = p;
+    if (a.pass) a.pass[t] = pass ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // dictionary encoding
 // ---------------------------------------------------------------------------------------------------------
@@ -208,6 +244,7 @@ struct mashgpu_dist_job {
     DevBuf<uint32_t> ranks, n_eff;
     DevBuf<uint64_t> lens;          // ref lengths then query lengths
     DevBuf<double> lut;
+    bool tiled = true;
 };
 
 namespace {
@@ -262,8 +299,7 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     auto bail = [&](int rc) { delete job; return rc; };
     if (total >= 0x7FFFFFFFull) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)rows, P));
     // shared memory needed by the merge kernel
-    const size_t smem = ((size_t)P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * P) * 4;
-    if (smem > 227 * 1024) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "sketch_size %llu needs %zu B of shared memory per CTA (max 232448)", (unsigned long long)params->sketch_size, smem));
+    job->tiled = ((size_t)P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * P) * 4 <= 227 * 1024;   // else: dist_kernel_general
 
     SetOnDevice dr, dq;
     int rc = stage_set(ctx, ref, dr, st);
@@ -340,6 +376,16 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.max_distance = job->params.max_distance; a.max_pvalue = job->params.max_pvalue;
     a.dist_lut = job->lut.p;
     a.numer = d_numer; a.denom = d_denom; a.distance = d_distance; a.pvalue = d_pvalue; a.pass = d_pass;
+    if (!job->tiled) {
+        const uint64_t total = q_count * job->n_ref;
+        time_begin(ctx, ctx->dist_events, st);
+        dist_kernel_general<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        time_end(ctx, ctx->dist_events, st);
+        ctx->kernel_launches++;
+        ctx->dist_launches++;
+        MG_CUDA(ctx, cudaGetLastError());
+        return MASHGPU_OK;
+    }
     const uint32_t r_tiles = (uint32_t)((job->n_ref + DIST_TILE_R - 1) / DIST_TILE_R);
     // slice the query range so that about 2 waves of CTAs cover the machine, at least one full round of warps each
     const uint32_t round = DIST_WARPS * DIST_ILP;

@@ -43,7 +43,7 @@ def test_golden_dist_lines(gpu, oracle, golden):
     assert (fmt_g(res["distance"][2, 0]), res["numer"][2, 0], res["denom"][2, 0]) == ("0", 1000, 1000)
 
 
-@pytest.mark.parametrize("s,k", [(1000, 21), (400, 16), (50, 11), (1, 21), (1030, 32)])
+@pytest.mark.parametrize("s,k", [(1000, 21), (400, 16), (50, 11), (1, 21), (1030, 32), (1036, 21), (5000, 21)])
 def test_grid_matches_oracle(gpu, oracle, s, k):
     H, N, L = synth_sketches(70, s, seed=3 + s, n_families=3, ragged=True)
     Hq, Nq, Lq = synth_sketches(45, s, seed=99 + s, n_families=3, ragged=True)
