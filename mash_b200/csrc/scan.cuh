@@ -350,8 +350,12 @@ __device__ __forceinline__ uint4 expand32(uint64_t c, uint32_t m)
 // Warp-private tiles: every warp owns WARP_TILE window starts at a time, staged in its own slice of shared memory,
 // so the only synchronisation is __syncwarp().  The next tile's bytes are prefetched into registers before the
 // current tile is hashed (global latency hidden behind ~4000 instructions of work per lane).
+#ifndef SCAN_MIN_BLOCKS
+#define SCAN_MIN_BLOCKS 4      // resident CTAs per SM requested from ptxas (=> 64 registers).  tools/scan_microbench.cu on B200:
+                               // 1 -> 181 Gbp/s (96 regs, 2 CTAs), 3 -> 186, 4 -> 188, 5 -> 183 (spills), 6 -> 177
+#endif
 template <int K, bool CANON, bool PACKED>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) scan_kernel(const __grid_constant__ ScanArgs a)
 {
     using S = KmerShape<K>;
     __shared__ __align__(16) uint32_t sm_all[SCAN_WARPS][SCAN_WARP_WORDS];
