@@ -355,7 +355,7 @@ __device__ __forceinline__ uint4 expand32(uint64_t c, uint32_t m)
                                // 1 -> 181 Gbp/s (96 regs, 2 CTAs), 3 -> 186, 4 -> 188, 5 -> 183 (spills), 6 -> 177
 #endif
 template <int K, bool CANON, bool PACKED>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) scan_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS, (K > 24 && SCAN_MIN_BLOCKS > 3) ? 3 : SCAN_MIN_BLOCKS) scan_kernel(const __grid_constant__ ScanArgs a)
 {
     using S = KmerShape<K>;
     __shared__ __align__(16) uint32_t sm_all[SCAN_WARPS][SCAN_WARP_WORDS];
