@@ -179,6 +179,14 @@ int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64
  * mixture_hashes (nullable, sketch_size slots) / mixture_n receive that bottom-s list.  Host buffers. */
 int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, uint64_t *median, double *identity,
                           double *pvalue, uint64_t *set_size, uint64_t *mixture_hashes, uint32_t *mixture_n);
+/* Multi-GPU screening (reads sharded over ranks, table replicated): the hit counters live in device memory as one
+ * uint32 per distinct reference hash, in ascending hash order, so counter i means the same hash on every rank that
+ * opened the job with the same sketches.  *d_counters / *n_counters expose that array for an all-reduce(sum) (NCCL via torch.distributed); the
+ * mixture bottom-s lists of the other ranks are folded in with mashgpu_screen_merge_mixture (ascending distinct hashes,
+ * host buffer) -- bottom-s of a union is the bottom-s of the union of bottom-s lists (the reference merges its
+ * per-thread heaps the same way, CommandScreen.cpp:288-302).  Then mashgpu_screen_finish as usual. */
+int mashgpu_screen_counters(mashgpu_screen_job *job, uint32_t **d_counters, uint64_t *n_counters);
+int mashgpu_screen_merge_mixture(mashgpu_screen_job *job, const uint64_t *hashes, uint32_t n);
 int mashgpu_screen_close(mashgpu_screen_job *job);
 
 /* ---------------------------------------------------------------------------------------------------------

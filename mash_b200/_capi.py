@@ -94,6 +94,8 @@ def load_library():
     L.mashgpu_screen_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.mashgpu_screen_feed_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.mashgpu_screen_finish.argtypes = [C.c_void_p, u64p, u64p, f64p, f64p, u64p, u64p, u32p]
+    L.mashgpu_screen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), u64p]
+    L.mashgpu_screen_merge_mixture.argtypes = [C.c_void_p, u64p, C.c_uint32]
     L.mashgpu_screen_close.argtypes = [C.c_void_p]
     L.mashgpu_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
@@ -279,6 +281,26 @@ class ScreenJob:
 
     def feed_dev(self, d_ptr, length):
         self.eng._check(self.eng.lib.mashgpu_screen_feed_dev(self.h, d_ptr, length))
+
+    def counters(self):
+        """(device pointer, slot count) of the uint32 hit counters, for an all-reduce across ranks."""
+        ptr = C.c_void_p(); n = C.c_uint64(0)
+        self.eng._check(self.eng.lib.mashgpu_screen_counters(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def merge_mixture(self, hashes):
+        h = np.ascontiguousarray(hashes, np.uint64)
+        self.eng._check(self.eng.lib.mashgpu_screen_merge_mixture(self.h, _p(h, u64p), h.size))
+
+    def mixture(self):
+        """The running bottom-s list of the mixture (ascending u64)."""
+        return self.finish_mixture_only()
+
+    def finish_mixture_only(self):
+        s = self.p.sketch_size
+        set_size = C.c_uint64(0); mix = np.zeros(s, np.uint64); mix_n = C.c_uint32(0)
+        self.eng._check(self.eng.lib.mashgpu_screen_finish(self.h, None, None, None, None, C.byref(set_size), _p(mix, u64p), C.byref(mix_n)))
+        return mix[:mix_n.value].copy()
 
     def finish(self):
         n, s = self.n_ref, self.p.sketch_size

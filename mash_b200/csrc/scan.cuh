@@ -58,7 +58,8 @@ struct ScanArgs {
     int64_t only_unit;            // >= 0: ignore every other unit (exact re-run)
     // screen: reference hash table (distinct keys, EMPTY_KEY when free) with u32 hit counters
     const uint64_t *ref_keys;
-    uint32_t *ref_cnt;
+    const uint32_t *ref_idx;      // slot -> index of the key in the sorted distinct key list (deterministic across ranks)
+    uint32_t *ref_cnt;            // hit counters, indexed by that key index
     uint32_t ref_log2;
     uint64_t ref_hmax;            // largest reference hash (probe prefilter)
     // dump
@@ -113,7 +114,7 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
         uint32_t slot = slot_hash(hash, a.ref_log2);
         for (;;) {
             uint64_t k = a.ref_keys[slot];
-            if (k == hash) { atomicAdd(&a.ref_cnt[slot], 1u); break; }
+            if (k == hash) { atomicAdd(&a.ref_cnt[a.ref_idx[slot]], 1u); break; }
             if (k == EMPTY_KEY) break;
             slot = (slot + 1) & mask;
         }

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -20,8 +22,9 @@ namespace mashgpu {
 
 constexpr int SCR_THREADS = 256;
 
-__global__ void screen_insert_kernel(const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, uint64_t n_rows,
-                                     uint64_t *keys, uint32_t log2cap, unsigned long long *hmax, uint32_t *err)
+// valid hashes of all reference sketches -> dense list (order irrelevant: sorted next)
+__global__ void screen_gather_kernel(const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, uint64_t n_rows,
+                                     uint64_t *out, unsigned long long *out_n, uint32_t *err)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= n_rows * stride) return;
@@ -29,12 +32,21 @@ __global__ void screen_insert_kernel(const uint64_t *hashes, uint64_t stride, co
     if (i >= n_hashes[row]) return;
     const uint64_t key = hashes[t];
     if (key == EMPTY_KEY) { atomicOr(err, 1u); return; }   // 2^64-1 cannot be a table key (probability 2^-64 per hash)
-    atomicMax(hmax, (unsigned long long)key);
+    out[atomicAdd(out_n, 1ull)] = key;
+}
+
+// distinct keys (ascending) -> open-addressing table; slot_idx[slot] = index of the key in the sorted list, so that the
+// counter array (indexed by key index) has the same layout on every rank however the insertion races resolve
+__global__ void screen_insert_kernel(const uint64_t *distinct, uint64_t n_distinct, uint64_t *keys, uint32_t *slot_idx, uint32_t log2cap)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_distinct) return;
+    const uint64_t key = distinct[t];
     const uint32_t mask = (1u << log2cap) - 1;
     uint32_t slot = slot_hash(key, log2cap);
     for (;;) {
         unsigned long long prev = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-        if (prev == EMPTY_KEY || prev == key) return;
+        if (prev == EMPTY_KEY) { slot_idx[slot] = (uint32_t)t; return; }
         slot = (slot + 1) & mask;
     }
 }
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(SCR_THREADS) merge_bottom_s_kernel(uint64_t *m
 
 // One CTA per reference sketch: shared count, sorted depths -> median, identity, p-value.
 __global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
-    const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, const uint64_t *keys, const uint32_t *cnt, uint32_t log2cap,
+    const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, const uint64_t *keys, const uint32_t *slot_idx, const uint32_t *cnt, uint32_t log2cap,
     uint64_t set_size, int kmer_size, double kmer_space,
     uint64_t *shared_out, uint64_t *median_out, double *identity_out, double *pvalue_out)
 {
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
         uint32_t slot = slot_hash(key, log2cap), c = 0;
         for (;;) {
             uint64_t k = keys[slot];
-            if (k == key) { c = cnt[slot]; break; }
+            if (k == key) { c = cnt[slot_idx[slot]]; break; }
             if (k == EMPTY_KEY) break;
             slot = (slot + 1) & mask;
         }
@@ -132,7 +144,8 @@ struct mashgpu_screen_job {
     uint64_t n_ref = 0, stride = 0;
     const uint64_t *ref_hashes = nullptr; const uint32_t *ref_n = nullptr;   // device
     DevBuf<uint64_t> own_hashes; DevBuf<uint32_t> own_n;
-    DevBuf<uint64_t> keys; DevBuf<uint32_t> cnt;
+    DevBuf<uint64_t> keys; DevBuf<uint32_t> slot_idx, cnt;      // table slots; counters indexed by distinct-key index
+    uint64_t n_distinct = 0;
     uint32_t log2cap = 4;
     uint64_t hmax = 0;
     DevBuf<uint64_t> mix, chunk_hashes; DevBuf<uint32_t> mix_n, chunk_n;
@@ -168,25 +181,47 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
     if (job->log2cap > 31) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference table too large"));
     const uint64_t cap = 1ull << job->log2cap;
     const uint32_t s = params->sketch_size;
-    DevBuf<unsigned long long> d_hmax; DevBuf<uint32_t> d_err;
-    if (job->keys.alloc(cap) != cudaSuccess || job->cnt.alloc(cap) != cudaSuccess || job->mix.alloc(s) != cudaSuccess || job->chunk_hashes.alloc(s) != cudaSuccess ||
-        job->mix_n.alloc(1) != cudaSuccess || job->chunk_n.alloc(1) != cudaSuccess || d_hmax.alloc(1) != cudaSuccess || d_err.alloc(1) != cudaSuccess)
+    DevBuf<unsigned long long> d_count; DevBuf<uint32_t> d_err;
+    DevBuf<uint64_t> gathered, sorted, distinct; DevBuf<uint8_t> tmp; DevBuf<uint64_t> d_nsel;
+    if (job->keys.alloc(cap) != cudaSuccess || job->slot_idx.alloc(cap) != cudaSuccess || job->mix.alloc(s) != cudaSuccess || job->chunk_hashes.alloc(s) != cudaSuccess ||
+        job->mix_n.alloc(1) != cudaSuccess || job->chunk_n.alloc(1) != cudaSuccess || d_count.alloc(1) != cudaSuccess || d_err.alloc(1) != cudaSuccess ||
+        gathered.alloc(total) != cudaSuccess || sorted.alloc(total) != cudaSuccess || distinct.alloc(total) != cudaSuccess || d_nsel.alloc(1) != cudaSuccess)
         return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen table of %llu slots)", (unsigned long long)cap));
     cudaMemsetAsync(job->keys.p, 0xFF, cap * 8, st);
-    cudaMemsetAsync(job->cnt.p, 0, cap * 4, st);
     cudaMemsetAsync(job->mix_n.p, 0, 4, st);
-    cudaMemsetAsync(d_hmax.p, 0, 8, st);
+    cudaMemsetAsync(d_count.p, 0, 8, st);
     cudaMemsetAsync(d_err.p, 0, 4, st);
+    unsigned long long n_valid = 0; uint32_t err = 0; uint64_t n_distinct = 0; unsigned long long hmax = 0;
     if (total) {
-        screen_insert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(job->ref_hashes, refs->stride, job->ref_n, refs->n, job->keys.p, job->log2cap, d_hmax.p, d_err.p);
-        ctx->kernel_launches++;
+        screen_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(job->ref_hashes, refs->stride, job->ref_n, refs->n, gathered.p, d_count.p, d_err.p);
+        cudaMemcpyAsync(&n_valid, d_count.p, 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
+        if (err) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketch contains the hash value 2^64-1"));
+        if (n_valid >= 0x7FFFFFFFull) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 reference hashes"));
+        if (n_valid) {
+            size_t tb1 = 0, tb2 = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tb1, gathered.p, sorted.p, (int)n_valid, 0, 64, st);
+            cub::DeviceSelect::Unique(nullptr, tb2, sorted.p, distinct.p, d_nsel.p, (int)n_valid, st);
+            if (tmp.alloc(std::max(tb1, tb2)) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)"));
+            cub::DeviceRadixSort::SortKeys(tmp.p, tb1, gathered.p, sorted.p, (int)n_valid, 0, 64, st);
+            cub::DeviceSelect::Unique(tmp.p, tb2, sorted.p, distinct.p, d_nsel.p, (int)n_valid, st);
+            cudaMemcpyAsync(&n_distinct, d_nsel.p, 8, cudaMemcpyDeviceToHost, st);
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table sort failed: %s", cudaGetErrorString(e)));
+            screen_insert_kernel<<<(unsigned)((n_distinct + 255) / 256), 256, 0, st>>>(distinct.p, n_distinct, job->keys.p, job->slot_idx.p, job->log2cap);
+            cudaMemcpyAsync(&hmax, distinct.p + (n_distinct - 1), 8, cudaMemcpyDeviceToHost, st);     // ascending: the last one is the largest
+            ctx->kernel_launches += 12;
+        }
     }
-    unsigned long long hmax = 0; uint32_t err = 0;
-    cudaMemcpyAsync(&hmax, d_hmax.p, 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
-    if (err) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketch contains the hash value 2^64-1"));
+    job->n_distinct = n_distinct;
+    if (job->cnt.alloc(n_distinct) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (hit counters)"));
+    cudaMemsetAsync(job->cnt.p, 0, std::max<uint64_t>(1, n_distinct) * 4, st);
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
+    }
     job->hmax = hmax;
     static bool attr_set = false;
     if (!attr_set) {
@@ -209,7 +244,7 @@ extern "C" int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_ch
     SketchStream S;
     S.d_stream = d_chunk; S.unit_start = unit_start; S.n_units = 1;
     if (job->h_mix_n == s) { S.t_cap = true; S.t_cap_value = job->h_mix_top; }   // nothing above the running s-th smallest can matter
-    ScreenProbe probe{job->keys.p, job->cnt.p, job->log2cap, job->hmax};
+    ScreenProbe probe{job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, job->hmax};
     MG_TRY(sketch_stream_core(ctx, &job->params, S, job->chunk_hashes.p, nullptr, job->chunk_n.p, st, &probe));
     uint32_t N = 2;
     while (N < 2 * s) N <<= 1;
@@ -268,7 +303,7 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
         if ((size_t)N * 4 > 200 * 1024) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketches larger than 51200 hashes");
         if ((size_t)N * 4 > 48 * 1024)
             MG_CUDA(ctx, cudaFuncSetAttribute(screen_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)N * 4)));
-        screen_reduce_kernel<<<(unsigned)n, SCR_THREADS, (size_t)N * 4, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->cnt.p, job->log2cap,
+        screen_reduce_kernel<<<(unsigned)n, SCR_THREADS, (size_t)N * 4, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap,
                                                                             set_size, k, kmer_space, d_shared.p, d_median.p, d_ident.p, d_p.p);
         ctx->kernel_launches++;
         MG_CUDA(ctx, cudaGetLastError());
@@ -278,6 +313,42 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
         if (pvalue) MG_CUDA(ctx, cudaMemcpyAsync(pvalue, d_p.p, n * 8, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     } else {
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_counters(mashgpu_screen_job *job, uint32_t **d_counters, uint64_t *n_slots)
+{
+    if (!job || !d_counters || !n_slots) return MASHGPU_ERR_INVALID;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    *d_counters = job->cnt.p;
+    *n_slots = job->n_distinct;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_merge_mixture(mashgpu_screen_job *job, const uint64_t *hashes, uint32_t n)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    const uint32_t s = job->params.sketch_size;
+    if (n > s) return fail(ctx, MASHGPU_ERR_INVALID, "a mixture list holds at most sketch_size hashes");
+    if (n == 0) return MASHGPU_OK;
+    if (!hashes) return fail(ctx, MASHGPU_ERR_INVALID, "hashes is NULL");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    MG_CUDA(ctx, cudaMemcpyAsync(job->chunk_hashes.p, hashes, n * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(job->chunk_n.p, &n, 4, cudaMemcpyHostToDevice, st));
+    uint32_t N = 2;
+    while (N < 2 * s) N <<= 1;
+    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, s);
+    ctx->kernel_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (job->h_mix_n) {
+        MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_top, job->mix.p + (job->h_mix_n - 1), 8, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     }
     return MASHGPU_OK;

@@ -500,7 +500,7 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     a.tab_last = d_last;
     a.only_unit = -1;
     if (probe) {
-        a.ref_keys = probe->keys; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
+        a.ref_keys = probe->keys; a.ref_idx = probe->idx; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
     }
     if (ntiles) {
         tile_tmax_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(d_start.p, n_units, d_t.p, stream_len, p->kmer_size, 0, ntiles, d_tmax.p);

@@ -19,6 +19,7 @@ struct SketchStream {
 // Reference hash table of a screen job (distinct keys + hit counters)
 struct ScreenProbe {
     const uint64_t *keys;
+    const uint32_t *idx;
     uint32_t *cnt;
     uint32_t log2cap;
     uint64_t hmax;

@@ -50,6 +50,37 @@ def exchange_query_tiles(hashes, n_hashes, lengths, counts=None, group=None):
     return torch.cat(out_h), torch.cat(out_n), torch.cat(out_l), counts
 
 
+def screen_allreduce(job, group=None):
+    """Multi-GPU screen: reads are sharded over ranks, every rank holds the same reference table.  Sums the hit counters
+    over ranks in place (NCCL all-reduce on the job's device counter array) and folds every other rank's mixture bottom-s
+    list into this rank's job, after which job.finish() returns the global result on every rank."""
+    ptr, n_slots = job.counters()
+    dev = torch.device("cuda", job.eng.device)
+
+    class _Cai:        # expose the library's device buffer to torch without a copy (CUDA array interface)
+        __cuda_array_interface__ = {"shape": (n_slots,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    counters = torch.as_tensor(_Cai(), device=dev)
+    td.all_reduce(counters, op=td.ReduceOp.SUM, group=group)
+    s = job.p.sketch_size
+    mine = job.mixture()
+    padded = torch.full((s,), -1, dtype=torch.int64, device=dev)
+    padded[:mine.size] = torch.from_numpy(mine.view("int64")).to(dev)
+    count = torch.tensor([mine.size], dtype=torch.int64, device=dev)
+    world = td.get_world_size(group)
+    all_lists = [torch.empty_like(padded) for _ in range(world)]
+    all_counts = [torch.empty_like(count) for _ in range(world)]
+    td.all_gather(all_lists, padded, group=group)
+    td.all_gather(all_counts, count, group=group)
+    rank = td.get_rank(group)
+    for r in range(world):
+        if r != rank:
+            m = int(all_counts[r].item())
+            if m:
+                job.merge_mixture(all_lists[r][:m].cpu().numpy().view("uint64"))
+    torch.cuda.synchronize(dev)
+
+
 def assemble_grid(blocks):
     """blocks[r]: (n_qry, n_ref_r) block computed by rank r -> (n_qry, n_ref) in global reference order."""
     return torch.cat(list(blocks), dim=1)
