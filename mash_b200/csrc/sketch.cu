@@ -158,7 +158,7 @@ __device__ __forceinline__ int64_t table_find(const uint64_t *keys, uint32_t log
 // Multiplicity counts, the reference's way.  MinHashHeap::tryInsert (MinHashHeap.cpp:68-74) only accepts a hash when
 // the heap is not full or the hash is strictly below the current top, so once all s final hashes have been seen
 // (stream position t* = the latest first occurrence among them) further occurrences of the largest final hash are
-// neither inserted nor counted; every other count is the true multiplicity (oracle mo_heap_try_insert).
+// neither inserted nor counted; every other count is the true multiplicity.
 // One CTA per full sketch: t* by max-reduction, then count[last] = occurrences of the largest hash at positions <= t*:
 // equal to the table count if its last occurrence is <= t*, 1 if it was the last hash to arrive, otherwise the unit
 // is flagged (bit 3) for a targeted recount over [unit start, t*].
