@@ -134,3 +134,39 @@ def test_pvalue_device_vs_mpmath(gpu, golden):
             worst = max(worst, abs(got - truth) / truth)
             assert abs(got - truth) <= TOL * truth, (c, got, truth)
     assert worst < 1e-12
+
+
+def test_full_size_symmetry_property(gpu):
+    # BASELINE configs[2] size (100 000 sketches, s=1000): size-independent property instead of an oracle run --
+    # rows of a random subset Q against everything must equal the columns of everything against Q (merge symmetry),
+    # self pairs have numer == denom == s, distance 0, and every distance/p-value is in [0, 1].
+    n, s = 100_000, 1000
+    rng = np.random.Generator(np.random.PCG64(77))
+    hi = np.uint64(2**64 * s // 5_000_000)
+    base = np.sort(rng.integers(0, int(hi), (40, 2 * s), dtype=np.uint64), axis=1)
+    H = np.empty((n, s), np.uint64)
+    fam = rng.integers(0, 40, n)
+    keep = rng.random((n, 1)) < 0.5
+    for lo in range(0, n, 5000):
+        sl = slice(lo, lo + 5000)
+        fresh = rng.integers(0, int(hi), (5000, 2 * s), dtype=np.uint64)
+        mask = rng.random((5000, 2 * s)) < rng.choice([1.0, 0.9, 0.5, 0.0], (5000, 1))
+        v = np.sort(np.where(mask, base[fam[sl]], fresh), axis=1)
+        dup = np.zeros_like(v, dtype=bool); dup[:, 1:] = v[:, 1:] <= v[:, :-1]
+        v = v + np.cumsum(dup, axis=1, dtype=np.uint64)
+        H[sl] = np.sort(v, axis=1)[:, :s]
+    N = np.full(n, s, np.uint32); L = rng.integers(4_000_000, 6_000_000, n).astype(np.uint64)
+    ks = 4.0 ** 21
+    q = np.sort(rng.choice(n, 96, replace=False))
+    job = gpu.dist_open(H, N, L, H[q], N[q], L[q], sketch_size=s, k=21, kmer_space=ks)
+    rows = job.run(0, 96)                      # (96, n): query = Q[i], reference = all
+    job.close()
+    job = gpu.dist_open(H[q], N[q], L[q], H, N, L, sketch_size=s, k=21, kmer_space=ks)
+    cols = job.run(0, n)                       # (n, 96): query = all, reference = Q[j]
+    job.close()
+    assert np.array_equal(rows["numer"], cols["numer"].T) and np.array_equal(rows["denom"], cols["denom"].T)
+    assert np.array_equal(rows["distance"], cols["distance"].T)
+    assert np.all(np.abs(rows["pvalue"] - cols["pvalue"].T) <= 1e-12 * np.maximum(rows["pvalue"], 1e-300))
+    assert np.all(rows["numer"][np.arange(96), q] == s) and np.all(rows["distance"][np.arange(96), q] == 0)
+    assert np.all((rows["distance"] >= 0) & (rows["distance"] <= 1)) and np.all((rows["pvalue"] >= 0) & (rows["pvalue"] <= 1))
+    assert np.all(rows["denom"] == s)
