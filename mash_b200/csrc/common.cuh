@@ -49,6 +49,7 @@ struct mashgpu_ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D staging
     std::string err;
+    bool attr_dist = false, attr_merge = false, attr_select = false;
     // instrumentation
     bool timing = false;
     uint64_t kernel_launches = 0;

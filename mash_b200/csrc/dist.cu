@@ -346,11 +346,10 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
         cudaError_t es = cudaStreamSynchronize(st);
         if (es != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(es)));
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_dist) {   // per context: function attributes are per device
         cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
-        attr_set = true;
+        ctx->attr_dist = true;
     }
     *job_out = job;
     return MASHGPU_OK;

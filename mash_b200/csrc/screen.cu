@@ -223,10 +223,9 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
     }
     job->hmax = hmax;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_merge) {   // per context: function attributes are per device
         cudaFuncSetAttribute(merge_bottom_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        attr_set = true;
+        ctx->attr_merge = true;
     }
     *job_out = job;
     return MASHGPU_OK;

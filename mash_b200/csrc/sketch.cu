@@ -516,11 +516,10 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     }
     MG_TRY(launch_scan(ctx, p, a, st));
 
-    static bool attr_set = false;
     const size_t sel_smem = (size_t)8 << SEL_MAX_LOG2;
-    if (!attr_set) {
+    if (!ctx->attr_select) {   // per context: function attributes are per device
         MG_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-        attr_set = true;
+        ctx->attr_select = true;
     }
     uint32_t max_log2 = 4;
     for (uint32_t u = 0; u < n_units; u++) max_log2 = std::max(max_log2, std::min(h_log2[u], SEL_MAX_LOG2));
