@@ -337,6 +337,8 @@ def main():
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
         budget = max(1 << 30, int(avail * 0.35 / max(1, local_world)))
         e2e_units = args.e2e_units or max(1, min(n_units, budget // (glen + 1)))
+        if world > 1 and not args.e2e_units:
+            e2e_units = min(e2e_units, 4000)      # N > 1: 20 GB of pinned host memory per rank instead of 50 GB (stated in e2e.units_per_step)
         span = glen + 1
         host = torch.empty(e2e_units * span, dtype=torch.uint8, pin_memory=True)
         host.copy_(stream[:e2e_units * span])
@@ -483,6 +485,9 @@ def main():
             t0 = time.perf_counter()
             for _ in range(n_chunks):
                 sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)     # the same device chunk again: the table and mixture logic still run
+            if dist_on:
+                from mash_b200.shard import screen_allreduce
+                screen_allreduce(sjob)                                    # reads sharded over ranks: sum the counters, merge the mixtures
             res = sjob.finish()
             torch.cuda.synchronize()
             dt = max_over_ranks(time.perf_counter() - t0)
@@ -492,7 +497,8 @@ def main():
             bases = n_chunks * chunk_reads * read_len
             screen_obj = {"metric": "Gbp_per_s_screened", "value": world * bases / dt / 1e9, "unit": "Gbp/s",
                           "workload": f"configs[3]: {H.shape[0]}-sketch reference table ({int(N.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
-                                      f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads (one chunk re-fed; inputs in HBM), finish() included",
+                                      f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads per rank (one chunk re-fed; inputs in HBM); "
+                                      f"{'counters all-reduced over NCCL + mixtures merged, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"], "gpu_launches": int(sstats["kernel_launches"]),
                           "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum())}
         else:
