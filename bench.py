@@ -462,7 +462,8 @@ def main():
             chunk_reads = min(n_reads, 2_000_000)
             pool = lut[torch.randint(0, 4, (50_000_000,), generator=g, device=dev, dtype=torch.uint8).long()]
             idx = torch.arange(read_len, device=dev)[None, :]
-            sset = mash_b200._capi._Set(H.data_ptr(), N.data_ptr(), L.data_ptr(), on_device=True, n=H.shape[0], stride=S)
+            # the reference table is replicated: every rank screens its reads against ALL sketches (QH = the gathered set)
+            sset = mash_b200._capi._Set(QH.data_ptr(), QN.data_ptr(), QL.data_ptr(), on_device=True, n=QH.shape[0], stride=S)
             chunk = torch.empty(chunk_reads * span_r + 64, dtype=torch.uint8, device=dev)
 
             def make_chunk():
@@ -496,7 +497,7 @@ def main():
             sjob.close()
             bases = n_chunks * chunk_reads * read_len
             screen_obj = {"metric": "Gbp_per_s_screened", "value": world * bases / dt / 1e9, "unit": "Gbp/s",
-                          "workload": f"configs[3]: {H.shape[0]}-sketch reference table ({int(N.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
+                          "workload": f"configs[3]: {QH.shape[0]}-sketch reference table ({int(QN.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
                                       f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads per rank (one chunk re-fed; inputs in HBM); "
                                       f"{'counters all-reduced over NCCL + mixtures merged, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"], "gpu_launches": int(sstats["kernel_launches"]),
