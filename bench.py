@@ -227,12 +227,27 @@ def run_reference_arm(args):
                                    "reference MurmurHash3/hash/MinHashHeap object code, restated addMinHashes loop, in-memory input (no FASTA parse)"},
         "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_json_line(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def emit_json_line(line):
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, torchrun) also write to fd 1, so main()
+    points fd 1 at stderr for the whole run and the result line is written to the saved real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -527,7 +542,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]),
                 "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "screen": screen_obj, "sanity": sanity,
                 "exact_reruns": int(stats["exact_reruns"])}
-        print(json.dumps(line))
+        emit_json_line(line)
     if dist_on:
         td.destroy_process_group()
 
