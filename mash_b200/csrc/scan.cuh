@@ -247,10 +247,14 @@ __device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::N
     }
 }
 
+#ifndef SCAN_VOTE_GROUP
+#define SCAN_VOTE_GROUP 4      // windows hashed back to back before one warp vote (1, 2, 4 or 8); see scan_group.
+                               // tools/scan_microbench.cu on B200 (k=21 canonical, 4 CTAs/SM): 1 -> 187.7, 2 -> 192.4, 4 -> 193.0, 8 -> 193.6 Gbp/s
+#endif
+
 template <int K, bool CANON, int J>
-__device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW],
-                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t tile_base, uint32_t local0, uint64_t tmax, uint32_t pool,
-                                            const uint32_t *sm_tile)
+__device__ __forceinline__ bool scan_window(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW],
+                                            const uint32_t (&rb)[KmerShape<K>::BW], uint64_t tmax, uint32_t pool, u64x2 &h_out)
 {
     using S = KmerShape<K>;
     uint32_t f[S::NW];
@@ -295,8 +299,38 @@ __device__ __forceinline__ void scan_window(const ScanArgs &a, const uint32_t (&
     u64x2 h = murmur3_h1<K, S::NA>(asc, a.seed);
     if (K <= 16) h.hi = 0;        // 32-bit hashes: |{A,C,G,T}|^k <= 2^32 (reference Sketch.cpp:1136, hash.cpp:31-35)
     // coarse filter on one 32-bit word; validity and the exact threshold are checked in the slow path
-    const bool pass = (K <= 16) ? (h.lo <= (uint32_t)tmax) : (h.hi <= (uint32_t)(tmax >> 32));
-    if (__any_sync(0xFFFFFFFFu, pass)) scan_emit_warp(a, pass, h.lo, h.hi, tile_base, local0 + J, sm_tile, K, tmax);
+    h_out = h;
+    return (K <= 16) ? (h.lo <= (uint32_t)tmax) : (h.hi <= (uint32_t)(tmax >> 32));
+}
+
+// G consecutive windows (J0 .. J0+G-1) are hashed without a control-flow break in between, which lets ptxas interleave
+// their independent multiply chains, then ONE warp vote decides whether anybody has a survivor.
+template <int K, bool CANON, int J0, int G>
+__device__ __forceinline__ void scan_group(const ScanArgs &a, const uint32_t (&b)[KmerShape<K>::BW], const uint32_t (&rb)[KmerShape<K>::BW],
+                                           uint64_t tile_base, uint32_t local0, uint64_t tmax, uint32_t pool, const uint32_t *sm_tile)
+{
+    u64x2 h[G];
+    bool pass[G];
+    bool any = false;
+    pass[0] = scan_window<K, CANON, J0>(a, b, rb, tmax, pool, h[0]);
+    if constexpr (G > 1) pass[1] = scan_window<K, CANON, J0 + (G > 1 ? 1 : 0)>(a, b, rb, tmax, pool, h[G > 1 ? 1 : 0]);
+    if constexpr (G > 2) {
+        pass[2] = scan_window<K, CANON, J0 + (G > 2 ? 2 : 0)>(a, b, rb, tmax, pool, h[G > 2 ? 2 : 0]);
+        pass[3] = scan_window<K, CANON, J0 + (G > 2 ? 3 : 0)>(a, b, rb, tmax, pool, h[G > 2 ? 3 : 0]);
+    }
+    if constexpr (G > 4) {
+        pass[4] = scan_window<K, CANON, J0 + (G > 4 ? 4 : 0)>(a, b, rb, tmax, pool, h[G > 4 ? 4 : 0]);
+        pass[5] = scan_window<K, CANON, J0 + (G > 4 ? 5 : 0)>(a, b, rb, tmax, pool, h[G > 4 ? 5 : 0]);
+        pass[6] = scan_window<K, CANON, J0 + (G > 4 ? 6 : 0)>(a, b, rb, tmax, pool, h[G > 4 ? 6 : 0]);
+        pass[7] = scan_window<K, CANON, J0 + (G > 4 ? 7 : 0)>(a, b, rb, tmax, pool, h[G > 4 ? 7 : 0]);
+    }
+#pragma unroll
+    for (int j = 0; j < G; j++) any |= pass[j];
+    if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+        for (int j = 0; j < G; j++)
+            if (__any_sync(0xFFFFFFFFu, pass[j])) scan_emit_warp(a, pass[j], h[j].lo, h[j].hi, tile_base, local0 + J0 + j, sm_tile, K, tmax);
+    }
 }
 
 // 16 ASCII bytes at stream offset `off` -> two nibble words (bytes at or past stream_len become separators)
@@ -426,14 +460,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K > 24 && SCAN_MIN_BLOCKS > 3) 
                 for (int i = 0; i < S::BW; i++) rb[i] = nibble_reverse(b[S::BW - 1 - i]) ^ 0x33333333u;
             }
             const uint32_t local0 = 8u * g;
-            scan_window<K, CANON, 0>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 1>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 2>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 3>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 4>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 5>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 6>(a, b, rb, base, local0, tmax, pool, sm);
-            scan_window<K, CANON, 7>(a, b, rb, base, local0, tmax, pool, sm);
+            constexpr int G = SCAN_VOTE_GROUP;
+            scan_group<K, CANON, 0, G>(a, b, rb, base, local0, tmax, pool, sm);
+            if constexpr (G < 8) scan_group<K, CANON, (G < 8 ? G : 0), G>(a, b, rb, base, local0, tmax, pool, sm);
+            if constexpr (G < 4) {
+                scan_group<K, CANON, (G < 4 ? 2 * G : 0), G>(a, b, rb, base, local0, tmax, pool, sm);
+                scan_group<K, CANON, (G < 4 ? 3 * G : 0), G>(a, b, rb, base, local0, tmax, pool, sm);
+            }
+            if constexpr (G < 2) {
+                scan_group<K, CANON, 4, 1>(a, b, rb, base, local0, tmax, pool, sm);
+                scan_group<K, CANON, 5, 1>(a, b, rb, base, local0, tmax, pool, sm);
+                scan_group<K, CANON, 6, 1>(a, b, rb, base, local0, tmax, pool, sm);
+                scan_group<K, CANON, 7, 1>(a, b, rb, base, local0, tmax, pool, sm);
+            }
         }
         __syncwarp();
     }
