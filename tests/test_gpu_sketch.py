@@ -245,3 +245,18 @@ def test_multi_wave_batch(gpu, oracle, monkeypatch, pack):
         oh, _, olen = oracle.sketch_unit([r for r, x in zip(recs, uor) if x == u], po, s=300)
         assert out[2][u] == olen
         assert_sketch_equal(out, u, oh)
+
+
+def test_large_sketch_size_goes_through_global_sort(gpu, oracle):
+    # s = 5000: the unit's candidate table (2^16 slots) does not fit select_kernel's shared-memory sort, so the unit takes
+    # the exact re-run path (global-memory table + radix sort) -- same answer, `mash sketch -s 5000`
+    p = gpu.params(k=21, s=5000)
+    po = oracle.params(k=21)
+    g = bytes(synth_genome(1234, 400_000))
+    short = bytes(synth_genome(1235, 3_000))          # fewer k-mers than s
+    out = gpu.sketch([g, short], p, counts=True)
+    for u, r in enumerate((g, short)):
+        oh, oc, olen = oracle.sketch_unit([r], po, s=5000, counts=True)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)
+        assert np.array_equal(out[3][u, :out[1][u]], oc)
