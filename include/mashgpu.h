@@ -153,6 +153,12 @@ int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
 int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
                          uint32_t *d_numer, uint32_t *d_denom, double *d_distance, double *d_pvalue, uint8_t *d_pass,
                          void *stream);
+/* Filtered runs (-d / -v): only the pairs with pass == 1, which is all that writeOutput prints
+ * (CommandDistance.cpp:270-287), as a compact list sorted by pair index (q - q_begin) * n_ref + r, i.e. in the
+ * reference's output order.  *n_pass = number of passing pairs; if it exceeds `capacity` nothing is returned and the
+ * caller retries with a larger capacity (or uses mashgpu_dist_run).  Host buffers of `capacity` entries. */
+int mashgpu_dist_run_list(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count, uint64_t capacity,
+                          uint64_t *pair_index, uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint64_t *n_pass);
 int mashgpu_dist_close(mashgpu_dist_job *job);
 
 /* One-shot convenience: open + run over all queries + close (the whole `compare` grid). */

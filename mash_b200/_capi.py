@@ -88,6 +88,7 @@ def load_library():
     L.mashgpu_dist_open.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), C.POINTER(C.c_void_p)]
     L.mashgpu_dist_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u32p, u32p, f64p, f64p, u8p]
     L.mashgpu_dist_run_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_dist_run_list.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u32p, u32p, f64p, f64p, u64p]
     L.mashgpu_dist_close.argtypes = [C.c_void_p]
     L.mashgpu_dist.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), u32p, u32p, f64p, f64p, u8p]
     L.mashgpu_screen_open.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.POINTER(SketchSet), C.POINTER(C.c_void_p)]
@@ -255,6 +256,15 @@ class DistJob:
         shp = (q_count, self.n_ref)
         return {"numer": numer.reshape(shp), "denom": denom.reshape(shp), "distance": dist.reshape(shp),
                 "pvalue": pv.reshape(shp), "pass": ok.reshape(shp).astype(bool)}
+
+    def run_list(self, q_begin, q_count, capacity):
+        """Passing pairs only, sorted by pair index. Returns (n_pass, dict of arrays) -- arrays empty when n_pass > capacity."""
+        idx = np.zeros(capacity, np.uint64); numer = np.zeros(capacity, np.uint32); denom = np.zeros(capacity, np.uint32)
+        dist = np.zeros(capacity, np.float64); pv = np.zeros(capacity, np.float64); n = C.c_uint64(0)
+        self.eng._check(self.eng.lib.mashgpu_dist_run_list(self.h, q_begin, q_count, capacity, _p(idx, u64p), _p(numer, u32p), _p(denom, u32p),
+                                                           _p(dist, f64p), _p(pv, f64p), C.byref(n)))
+        m = n.value if n.value <= capacity else 0
+        return n.value, {"index": idx[:m], "numer": numer[:m], "denom": denom[:m], "distance": dist[:m], "pvalue": pv[:m]}
 
     def run_dev(self, q_begin, q_count, d_numer=None, d_denom=None, d_distance=None, d_pvalue=None, d_pass=None, stream=None):
         self.eng._check(self.eng.lib.mashgpu_dist_run_dev(self.h, q_begin, q_count, d_numer, d_denom, d_distance, d_pvalue, d_pass, stream))

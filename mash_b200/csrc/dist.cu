@@ -45,7 +45,18 @@ struct DistArgs {
     double kmer_space, max_distance, max_pvalue;
     const double *dist_lut;     // distance for (common, denom == S), S+1 entries
     uint32_t *numer; uint32_t *denom; double *distance; double *pvalue; uint8_t *pass;   // outputs, (q - q_begin) * n_ref + r
+    // compacted pass-list (filtered runs): passing pairs are appended in arbitrary order, then sorted by pair index
+    uint64_t *list_idx; uint32_t *list_numer; uint32_t *list_denom; double *list_distance; double *list_pvalue;
+    unsigned long long *list_count; uint64_t list_capacity;
 };
+
+__device__ __forceinline__ void dist_list_append(const DistArgs &a, uint64_t o, uint32_t common, uint32_t denom, double dist, double p)
+{
+    const unsigned long long at = atomicAdd(a.list_count, 1ull);
+    if (at < a.list_capacity) {
+        a.list_idx[at] = o; a.list_numer[at] = common; a.list_denom[at] = denom; a.list_distance[at] = dist; a.list_pvalue[at] = p;
+    }
+}
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
                 if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;        // :419-422
             }
             (void)nB;
+            if (a.list_idx && pass) dist_list_append(a, o, common, denom, dist, p);
             if (a.numer) a.numer[o] = common;
             if (a.denom) a.denom[o] = denom;
             if (a.distance) a.distance[o] = dist;
@@ -189,6 +201,7 @@ __global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
         p = mash_pvalue(common, a.ref_len[r], a.qry_len[q], a.kmer_space, denom);
         if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;
     }
+    if (a.list_idx && pass) dist_list_append(a, t, common, denom, dist, p);
     if (a.numer) a.numer[t] = common;
     if (a.denom) a.denom[t] = denom;
     if (a.distance) a.distance[t] = dist;
@@ -231,6 +244,21 @@ __global__ void dict_scatter_kernel(const uint32_t *sorted_idx, const uint32_t *
     ranks[slot] = (i < n_eff[row]) ? (scan[t] - 1u) : RANK_PAD;
 }
 
+__global__ void list_gather_kernel(const uint32_t *order, uint64_t n, const uint32_t *numer, const uint32_t *denom, const double *distance,
+                                   const double *pvalue, uint32_t *o_numer, uint32_t *o_denom, double *o_distance, double *o_pvalue)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t src = order[t];
+    o_numer[t] = numer[src]; o_denom[t] = denom[src]; o_distance[t] = distance[src]; o_pvalue[t] = pvalue[src];
+}
+
+__global__ void iota_kernel(uint32_t *v, uint64_t n)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t < n) v[t] = (uint32_t)t;
+}
+
 }  // namespace mashgpu
 
 using namespace mashgpu;
@@ -245,6 +273,9 @@ struct mashgpu_dist_job {
     DevBuf<uint64_t> lens;          // ref lengths then query lengths
     DevBuf<double> lut;
     bool tiled = true;
+    // pass-list target of the next run (set by mashgpu_dist_run_list only)
+    uint64_t *list_idx = nullptr; uint32_t *list_numer = nullptr, *list_denom = nullptr; double *list_distance = nullptr, *list_pvalue = nullptr;
+    unsigned long long *list_count = nullptr; uint64_t list_capacity = 0;
 };
 
 namespace {
@@ -375,6 +406,8 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.max_distance = job->params.max_distance; a.max_pvalue = job->params.max_pvalue;
     a.dist_lut = job->lut.p;
     a.numer = d_numer; a.denom = d_denom; a.distance = d_distance; a.pvalue = d_pvalue; a.pass = d_pass;
+    a.list_idx = job->list_idx; a.list_numer = job->list_numer; a.list_denom = job->list_denom; a.list_distance = job->list_distance;
+    a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
     if (!job->tiled) {
         const uint64_t total = q_count * job->n_ref;
         time_begin(ctx, ctx->dist_events, st);
@@ -435,6 +468,54 @@ extern "C" int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_
         if (pass) MG_CUDA(ctx, cudaMemcpyAsync(pass + o, dpass.p, np, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_run_list(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count, uint64_t capacity,
+                                     uint64_t *pair_index, uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint64_t *n_pass)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (!n_pass) return fail(ctx, MASHGPU_ERR_INVALID, "n_pass is NULL");
+    *n_pass = 0;
+    if (q_begin + q_count > job->n_qry) return fail(ctx, MASHGPU_ERR_INVALID, "query range exceeds query count");
+    if (q_count == 0 || job->n_ref == 0) return MASHGPU_OK;
+    if (capacity >= 0xFFFFFFFFull) return fail(ctx, MASHGPU_ERR_INVALID, "capacity must be below 2^32");
+    if (capacity && (!pair_index || !numer || !denom || !distance || !pvalue)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL output");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t cap = std::max<uint64_t>(capacity, 1);
+    DevBuf<uint64_t> l_idx, s_idx; DevBuf<uint32_t> l_n, l_d, order, s_order, o_n, o_d; DevBuf<double> l_D, l_P, o_D, o_P; DevBuf<unsigned long long> cnt; DevBuf<uint8_t> tmp;
+    if (l_idx.alloc(cap) != cudaSuccess || s_idx.alloc(cap) != cudaSuccess || l_n.alloc(cap) != cudaSuccess || l_d.alloc(cap) != cudaSuccess ||
+        l_D.alloc(cap) != cudaSuccess || l_P.alloc(cap) != cudaSuccess || order.alloc(cap) != cudaSuccess || s_order.alloc(cap) != cudaSuccess ||
+        o_n.alloc(cap) != cudaSuccess || o_d.alloc(cap) != cudaSuccess || o_D.alloc(cap) != cudaSuccess || o_P.alloc(cap) != cudaSuccess || cnt.alloc(1) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (pass list of %llu entries)", (unsigned long long)cap);
+    MG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, 8, st));
+    job->list_idx = l_idx.p; job->list_numer = l_n.p; job->list_denom = l_d.p; job->list_distance = l_D.p; job->list_pvalue = l_P.p;
+    job->list_count = cnt.p; job->list_capacity = capacity;
+    int rc = mashgpu_dist_run_dev(job, q_begin, q_count, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+    job->list_idx = nullptr; job->list_numer = job->list_denom = nullptr; job->list_distance = job->list_pvalue = nullptr; job->list_count = nullptr; job->list_capacity = 0;
+    MG_TRY(rc);
+    unsigned long long n = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&n, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_pass = n;
+    if (n == 0 || n > capacity) return MASHGPU_OK;      // overflow: the caller retries with a larger capacity (or the dense call)
+    // restore the reference's output order (query-major pair index): sort the list by pair index on the device
+    const unsigned tb = 256, nb = (unsigned)((n + tb - 1) / tb);
+    iota_kernel<<<nb, tb, 0, st>>>(order.p, n);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, l_idx.p, s_idx.p, order.p, s_order.p, (int)n, 0, 64, st);
+    if (tmp.alloc(tmp_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+    MG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, l_idx.p, s_idx.p, order.p, s_order.p, (int)n, 0, 64, st));
+    list_gather_kernel<<<nb, tb, 0, st>>>(s_order.p, n, l_n.p, l_d.p, l_D.p, l_P.p, o_n.p, o_d.p, o_D.p, o_P.p);
+    ctx->kernel_launches += 10;
+    MG_CUDA(ctx, cudaMemcpyAsync(pair_index, s_idx.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(numer, o_n.p, n * 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(denom, o_d.p, n * 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(distance, o_D.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(pvalue, o_P.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
     return MASHGPU_OK;
 }
 

@@ -334,8 +334,30 @@ int runDist(int argc, const char **argv)
         uint64_t rows = std::max<uint64_t>(1, (1ull << 24) / nRef);
         PairBlock out;
         out.resize(std::min(rows, nQry) * nRef);
+        // with -d / -v filters only the passing pairs are needed (writeOutput prints nothing else): ask the engine for the
+        // compacted pass-list, already in query-major order, instead of the dense grid
+        const bool filtered = !table && (distanceMax < 1.0 || pValueMax < 1.0);
+        const uint64_t listCapacity = 1ull << 22;
+        vector<uint64_t> lIdx; vector<uint32_t> lNumer, lDenom; vector<double> lDist, lP;
+        if (filtered) { lIdx.resize(listCapacity); lNumer.resize(listCapacity); lDenom.resize(listCapacity); lDist.resize(listCapacity); lP.resize(listCapacity); }
         for (uint64_t q = 0; q < nQry; q += rows) {
             uint64_t r = std::min(rows, nQry - q);
+            if (filtered) {
+                uint64_t nPass = 0;
+                if (mashgpu_dist_run_list(job, q, r, listCapacity, lIdx.data(), lNumer.data(), lDenom.data(), lDist.data(), lP.data(), &nPass) != MASHGPU_OK) gpuFail();
+                if (nPass <= listCapacity) {
+                    for (uint64_t e = 0; e < nPass; e++) {
+                        uint64_t i = lIdx[e] / nRef, j = lIdx[e] % nRef;
+                        cout << sketchRef.getReference(j).name;
+                        if (comment) cout << ':' << sketchRef.getReference(j).comment;
+                        cout << '\t' << sketchQuery.getReference(q + i).name;
+                        if (comment) cout << ':' << sketchQuery.getReference(q + i).comment;
+                        cout << '\t' << lDist[e] << '\t' << lP[e] << '\t' << lNumer[e] << '/' << lDenom[e] << endl;
+                    }
+                    continue;
+                }
+                // more passing pairs than the list holds: dense path for this block
+            }
             if (mashgpu_dist_run(job, q, r, out.numer.data(), out.denom.data(), out.distance.data(), out.pValue.data(), out.pass.data()) != MASHGPU_OK) gpuFail();
             for (uint64_t i = 0; i < r; i++) {                 // == writeOutput, reference CommandDistance.cpp:247-304
                 for (uint64_t j = 0; j < nRef; j++) {

@@ -107,3 +107,11 @@ def test_gz_input_individual_mode_and_triangle(work, oracle):
             assert cells[1 + j] == fmt_g(o.distance)
     edges = out(work, "triangle", "-E", "multi.msh").splitlines()
     assert len(edges) == 15 and edges[0].split("\t")[:2] == ["rec1", "rec0"]
+
+
+def test_filtered_dist_uses_pass_list(work):
+    # `mash dist -d 0.05 genomes.msh genomes.msh`: only pairs within distance 0.05, query-major order, same text as dense + filter
+    got = out(work, "dist", "-d", "0.05", "genomes.msh", "genomes.msh").splitlines()
+    full = out(work, "dist", "genomes.msh", "genomes.msh").splitlines()
+    want = [l for l in full if float(l.split("\t")[2]) <= 0.05]
+    assert got == want and 0 < len(got) < len(full)

@@ -170,3 +170,24 @@ def test_full_size_symmetry_property(gpu):
     assert np.all(rows["numer"][np.arange(96), q] == s) and np.all(rows["distance"][np.arange(96), q] == 0)
     assert np.all((rows["distance"] >= 0) & (rows["distance"] <= 1)) and np.all((rows["pvalue"] >= 0) & (rows["pvalue"] <= 1))
     assert np.all(rows["denom"] == s)
+
+
+def test_pass_list_equals_dense_filter(gpu, oracle):
+    # -d / -v filtered output as a compacted list in the reference's (query-major) order
+    H, N, L = synth_sketches(90, 600, seed=31, n_families=3, ragged=True)
+    ks = 4.0 ** 21
+    for md, mp in ((0.1, 1.0), (1.0, 1e-20), (0.05, 1e-5)):
+        job = gpu.dist_open(H, N, L, sketch_size=600, k=21, kmer_space=ks, max_distance=md, max_pvalue=mp)
+        try:
+            dense = job.run(10, 70)
+            n_pass, lst = job.run_list(10, 70, 70 * 90)
+            n_over, empty = job.run_list(10, 70, 3)
+        finally:
+            job.close()
+        flat = np.flatnonzero(dense["pass"].ravel())
+        assert n_pass == flat.size and np.array_equal(lst["index"], flat.astype(np.uint64))
+        for key in ("numer", "denom", "distance", "pvalue"):
+            assert np.array_equal(lst[key], dense[key].ravel()[flat])
+        assert n_over == flat.size and (flat.size <= 3 or empty["index"].size == 0)
+        want = oracle.compare_all(H, N, L, H, N, L, 600, 21, ks, max_distance=md, max_pvalue=mp, q_begin=10, q_end=80)[10:80]
+        assert np.array_equal(np.flatnonzero(want["pass"].ravel()), flat)
