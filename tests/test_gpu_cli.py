@@ -110,8 +110,8 @@ def test_gz_input_individual_mode_and_triangle(work, oracle):
 
 
 def test_filtered_dist_uses_pass_list(work):
-    # `mash dist -d 0.05 genomes.msh genomes.msh`: only pairs within distance 0.05, query-major order, same text as dense + filter
-    got = out(work, "dist", "-d", "0.05", "genomes.msh", "genomes.msh").splitlines()
+    # `mash dist -d 0.01 genomes.msh genomes.msh`: only pairs within distance 0.01, query-major order, same text as dense + filter
+    got = out(work, "dist", "-d", "0.01", "genomes.msh", "genomes.msh").splitlines()
     full = out(work, "dist", "genomes.msh", "genomes.msh").splitlines()
-    want = [l for l in full if float(l.split("\t")[2]) <= 0.05]
+    want = [l for l in full if float(l.split("\t")[2]) <= 0.01]
     assert got == want and 0 < len(got) < len(full)
