@@ -90,8 +90,8 @@ int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
  * back; unit u occupies bytes [unit_start[u], unit_start[u+1]) (host array of n_units+1 offsets); records inside
  * a unit are separated by at least one byte outside the alphabet (e.g. 0).  d_stream must be readable up to
  * unit_start[n_units] rounded up to 16 bytes.  d_out_* are device pointers (d_out_counts nullable).
- * `stream` is a cudaStream_t (NULL = the context's stream); the call returns after enqueueing unless a unit
- * needs the exact re-run (then it synchronises the stream). */
+ * `stream` is a cudaStream_t (NULL = the context's stream).  All work is enqueued on that stream; the call synchronises
+ * it once at the end (it has to read the per-unit status flags to decide whether a unit needs the exact re-run). */
 int mashgpu_sketch_stream_dev(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
                               const void *d_stream, const uint64_t *unit_start, uint64_t n_units,
                               uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, void *stream);
