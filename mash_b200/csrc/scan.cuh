@@ -247,6 +247,9 @@ __device__ __forceinline__ void expand_ascii(const uint32_t (&c)[KmerShape<K>::N
     }
 }
 
+#ifndef SCAN_RC_SMEM
+#define SCAN_RC_SMEM 1         // keep a reverse-complement image of the tile in shared memory (see scan_kernel)
+#endif
 #ifndef SCAN_VOTE_GROUP
 #define SCAN_VOTE_GROUP 4      // windows hashed back to back before one warp vote (1, 2, 4 or 8); see scan_group.
                                // tools/scan_microbench.cu on B200 (k=21 canonical, 4 CTAs/SM): 1 -> 187.7, 2 -> 192.4, 4 -> 193.0, 8 -> 193.6 Gbp/s
@@ -394,8 +397,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K > 24 && SCAN_MIN_BLOCKS > 3) 
 {
     using S = KmerShape<K>;
     __shared__ __align__(16) uint32_t sm_all[SCAN_WARPS][SCAN_WARP_WORDS];
+#if SCAN_RC_SMEM
+    // reverse-complement image of the tile (word i = nibble-reversed, complemented word NW-1-i), written once at staging so
+    // that a block's reverse-complement words are 4 more LDS (the LSU is idle) instead of ~16 ALU instructions per block
+    __shared__ __align__(16) uint32_t smr_all[CANON ? SCAN_WARPS : 1][SCAN_WARP_WORDS];
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *sm = sm_all[warp];
+#if SCAN_RC_SMEM
+    uint32_t *smr = smr_all[CANON ? warp : 0];
+#endif
     const uint32_t fold = a.preserve_case ? 0xFFFFFFFFu : 0xDFDFDFDFu;
     uint32_t pool;   // bytes 'A','C','G','T' for PRMT; opaque to the compiler so that it stays in one register
     asm volatile("mov.u32 %0, 0x54474341;" : "=r"(pool));
@@ -427,12 +438,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K > 24 && SCAN_MIN_BLOCKS > 3) 
     for (; wt < wt_end; wt += wt_stride) {
         const uint64_t base = wt * (uint64_t)SCAN_WARP_TILE;
         if (PACKED) {
-            *reinterpret_cast<uint4 *>(sm + 4 * lane) = expand32(pc0, pm0);
-            *reinterpret_cast<uint4 *>(sm + 4 * hg) = expand32(pc1, pm1);
+            const uint4 e0 = expand32(pc0, pm0), e1 = expand32(pc1, pm1);
+            *reinterpret_cast<uint4 *>(sm + 4 * lane) = e0;
+            *reinterpret_cast<uint4 *>(sm + 4 * hg) = e1;
+#if SCAN_RC_SMEM
+            if (CANON) {
+                *reinterpret_cast<uint4 *>(smr + (SCAN_WARP_WORDS - 4 - 4 * lane)) =
+                    make_uint4(nibble_reverse(e0.w) ^ 0x33333333u, nibble_reverse(e0.z) ^ 0x33333333u, nibble_reverse(e0.y) ^ 0x33333333u, nibble_reverse(e0.x) ^ 0x33333333u);
+                *reinterpret_cast<uint4 *>(smr + (SCAN_WARP_WORDS - 4 - 4 * hg)) =
+                    make_uint4(nibble_reverse(e1.w) ^ 0x33333333u, nibble_reverse(e1.z) ^ 0x33333333u, nibble_reverse(e1.y) ^ 0x33333333u, nibble_reverse(e1.x) ^ 0x33333333u);
+            }
+#endif
         } else {
-            *reinterpret_cast<uint2 *>(sm + 2 * lane) = stage16(q0, base + 16ull * lane, a.stream_len, fold);
-            *reinterpret_cast<uint2 *>(sm + 2 * (lane + 32)) = stage16(q1, base + 16ull * (lane + 32), a.stream_len, fold);
-            *reinterpret_cast<uint2 *>(sm + 2 * v2) = stage16(q2, base + 16ull * v2, a.stream_len, fold);
+            const uint2 s0 = stage16(q0, base + 16ull * lane, a.stream_len, fold);
+            const uint2 s1 = stage16(q1, base + 16ull * (lane + 32), a.stream_len, fold);
+            const uint2 s2 = stage16(q2, base + 16ull * v2, a.stream_len, fold);
+            *reinterpret_cast<uint2 *>(sm + 2 * lane) = s0;
+            *reinterpret_cast<uint2 *>(sm + 2 * (lane + 32)) = s1;
+            *reinterpret_cast<uint2 *>(sm + 2 * v2) = s2;
+#if SCAN_RC_SMEM
+            if (CANON) {
+                *reinterpret_cast<uint2 *>(smr + (SCAN_WARP_WORDS - 2 - 2 * lane)) = make_uint2(nibble_reverse(s0.y) ^ 0x33333333u, nibble_reverse(s0.x) ^ 0x33333333u);
+                *reinterpret_cast<uint2 *>(smr + (SCAN_WARP_WORDS - 2 - 2 * (lane + 32))) = make_uint2(nibble_reverse(s1.y) ^ 0x33333333u, nibble_reverse(s1.x) ^ 0x33333333u);
+                *reinterpret_cast<uint2 *>(smr + (SCAN_WARP_WORDS - 2 - 2 * v2)) = make_uint2(nibble_reverse(s2.y) ^ 0x33333333u, nibble_reverse(s2.x) ^ 0x33333333u);
+            }
+#endif
         }
         __syncwarp();
         const uint64_t next = wt + wt_stride;
@@ -456,8 +486,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K > 24 && SCAN_MIN_BLOCKS > 3) 
 #pragma unroll
             for (int i = 0; i < S::BW; i++) b[i] = sm[g + i];
             if (CANON) {
+#if SCAN_RC_SMEM
+#pragma unroll
+                for (int i = 0; i < S::BW; i++) rb[i] = smr[SCAN_WARP_WORDS - S::BW - g + i];
+#else
 #pragma unroll
                 for (int i = 0; i < S::BW; i++) rb[i] = nibble_reverse(b[S::BW - 1 - i]) ^ 0x33333333u;
+#endif
             }
             const uint32_t local0 = 8u * g;
             constexpr int G = SCAN_VOTE_GROUP;
