@@ -161,6 +161,18 @@ int mashgpu_dist_run_list(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_co
                           uint64_t *pair_index, uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint64_t *n_pass);
 int mashgpu_dist_close(mashgpu_dist_job *job);
 
+/* Tile prefilter of the merge (no counterpart in the reference, which merges every pair, CommandDistance.cpp:347-365;
+ * the results are identical).  Before a tile of 32 references is merged with a query, the query's hashes are looked up in
+ * a filter built over the tile's hashes; a query that shares no hash with any of the 32 references gets the closed form
+ * of an empty intersection (common 0, denom min(s, |A|+|B|), distance 1, p-value 1) for all 32 pairs and is not merged.
+ * mode: -1 auto (default: on, and switched off for the rest of the job once more than half of the probed
+ * (query, tile) combinations turned out to share hashes), 0 off, 1 on.  Environment MASHGPU_DIST_PREFILTER=0|1
+ * overrides the default at mashgpu_dist_open. */
+int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode);
+/* Counters of the prefilter since the job was opened: (query, tile) combinations probed, those that went on to the merge,
+ * and whether the next run would probe.  Synchronises the device.  Any pointer may be NULL. */
+int mashgpu_dist_prefilter_stats(mashgpu_dist_job *job, uint64_t *combos_probed, uint64_t *combos_flagged, int *active);
+
 /* One-shot convenience: open + run over all queries + close (the whole `compare` grid). */
 int mashgpu_dist(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
                  const mashgpu_dist_params *params,

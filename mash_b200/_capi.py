@@ -90,6 +90,8 @@ def load_library():
     L.mashgpu_dist_run_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mashgpu_dist_run_list.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u32p, u32p, f64p, f64p, u64p]
     L.mashgpu_dist_close.argtypes = [C.c_void_p]
+    L.mashgpu_dist_set_prefilter.argtypes = [C.c_void_p, C.c_int]
+    L.mashgpu_dist_prefilter_stats.argtypes = [C.c_void_p, u64p, u64p, C.POINTER(C.c_int)]
     L.mashgpu_dist.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), u32p, u32p, f64p, f64p, u8p]
     L.mashgpu_screen_open.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.POINTER(SketchSet), C.POINTER(C.c_void_p)]
     L.mashgpu_screen_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -268,6 +270,15 @@ class DistJob:
 
     def run_dev(self, q_begin, q_count, d_numer=None, d_denom=None, d_distance=None, d_pvalue=None, d_pass=None, stream=None):
         self.eng._check(self.eng.lib.mashgpu_dist_run_dev(self.h, q_begin, q_count, d_numer, d_denom, d_distance, d_pvalue, d_pass, stream))
+
+    def set_prefilter(self, mode):
+        """-1 = auto (default), 0 = merge every pair, 1 = always probe the reference tiles first."""
+        self.eng._check(self.eng.lib.mashgpu_dist_set_prefilter(self.h, int(mode)))
+
+    def prefilter_stats(self):
+        probed = C.c_uint64(0); flagged = C.c_uint64(0); active = C.c_int(0)
+        self.eng._check(self.eng.lib.mashgpu_dist_prefilter_stats(self.h, C.byref(probed), C.byref(flagged), C.byref(active)))
+        return {"combos_probed": probed.value, "combos_flagged": flagged.value, "active": bool(active.value)}
 
     def close(self):
         if self.h:

@@ -14,11 +14,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 #include "binom.cuh"
+#include "dist_filter.cuh"
 
 namespace mashgpu {
 
@@ -48,6 +50,9 @@ struct DistArgs {
     // compacted pass-list (filtered runs): passing pairs are appended in arbitrary order, then sorted by pair index
     uint64_t *list_idx; uint32_t *list_numer; uint32_t *list_denom; double *list_distance; double *list_pvalue;
     unsigned long long *list_count; uint64_t list_capacity;
+    // prefilter work lists (dist_probe_kernel -> dist_kernel): per reference tile the queries that share a hash with it
+    uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
+    int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
 };
 
 __device__ __forceinline__ void dist_list_append(const DistArgs &a, uint64_t o, uint32_t common, uint32_t denom, double dist, double p)
@@ -75,6 +80,26 @@ __device__ __forceinline__ double mash_distance(uint32_t common, uint32_t denom,
     return d > 1 ? 1.0 : d;
 }
 
+// Epilogue of compareSketches for one pair (CommandDistance.cpp:387-424) given the merge result.
+__device__ __forceinline__ void dist_emit(const DistArgs &a, uint32_t q, uint32_t r, uint32_t common, uint32_t denom, uint64_t lenA)
+{
+    double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
+    const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
+    bool pass = true;
+    double p = 0.0;
+    if (a.max_distance >= 0 && dist > a.max_distance) pass = false;     // CommandDistance.cpp:409-412
+    else {
+        p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
+        if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;        // :419-422
+    }
+    if (a.list_idx && pass) dist_list_append(a, o, common, denom, dist, p);
+    if (a.numer) a.numer[o] = common;
+    if (a.denom) a.denom[o] = denom;
+    if (a.distance) a.distance[o] = dist;
+    if (a.pvalue) a.pvalue[o] = p;
+    if (a.pass) a.pass[o] = pass ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 {
     extern __shared__ uint32_t smem[];
@@ -85,6 +110,12 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
     const uint32_t r = r0 + lane;
     const bool r_ok = r < a.n_ref;
 
+    // The CTA's items: the dense query range [q_begin, q_begin + q_count), or (prefiltered runs) the tile's work list.
+    // Item index -> query: q_begin + item, or qlist[tile][item].  A CTA takes q_per_cta items at a time, gridDim.y apart.
+    const uint32_t n_items = a.use_qlist ? a.qcount[blockIdx.x] : a.q_count;
+    const uint32_t *my_list = a.use_qlist ? a.qlist + (uint64_t)blockIdx.x * a.qlist_stride : nullptr;
+    if ((uint64_t)blockIdx.y * a.q_per_cta >= n_items) return;          // nothing to do: do not even stage the tile
+
     // stage the reference tile, interleaved: element i of reference (r0+l) at s_ref[i*32 + l]
     {
         const uint32_t *row = a.ranks + (a.ref_row0 + (r_ok ? r : r0)) * (uint64_t)a.P;
@@ -94,21 +125,23 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
     const uint32_t nA = r_ok ? a.ref_n[r] : 0;
     const uint64_t lenA = r_ok ? a.ref_len[r] : 1;
     const uint32_t sref_base = (uint32_t)__cvta_generic_to_shared(s_ref) + lane * 4;
-
-    const uint32_t q_lo = a.q_begin + blockIdx.y * a.q_per_cta;
-    const uint32_t q_hi = min(q_lo + a.q_per_cta, a.q_begin + a.q_count);
     uint32_t *my_q = s_qry + (size_t)warp * DIST_ILP * a.P;
 
-    for (uint32_t qb = q_lo + warp * DIST_ILP; qb < q_hi; qb += DIST_WARPS * DIST_ILP) {
+    for (uint64_t it_lo = (uint64_t)blockIdx.y * a.q_per_cta; it_lo < n_items; it_lo += (uint64_t)gridDim.y * a.q_per_cta) {
+    const uint32_t it_hi = (uint32_t)min((uint64_t)n_items, it_lo + a.q_per_cta);
+    for (uint32_t ib = (uint32_t)it_lo + warp * DIST_ILP; ib < it_hi; ib += DIST_WARPS * DIST_ILP) {
         // load DIST_ILP query rows (coalesced) into this warp's buffers
+        uint32_t qs[DIST_ILP];
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
-            const uint32_t q = qb + c;
+            const uint32_t item = ib + c;
             uint32_t *dst = my_q + (size_t)c * a.P;
-            if (q < q_hi) {
-                const uint32_t *row = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
+            if (item < it_hi) {
+                qs[c] = my_list ? my_list[item] : a.q_begin + item;
+                const uint32_t *row = a.ranks + (a.qry_row0 + qs[c]) * (uint64_t)a.P;
                 for (uint32_t i = lane; i < a.P; i += 32) dst[i] = row[i];
             } else {
+                qs[c] = 0xFFFFFFFFu;
                 for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
             }
         }
@@ -143,32 +176,116 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
         // epilogue
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
-            const uint32_t q = qb + c;
-            if (q >= q_hi || !r_ok) continue;
+            const uint32_t q = qs[c];
+            if (q == 0xFFFFFFFFu || !r_ok) continue;
             const uint32_t i_end = (pa[c] - sref_base) / (DIST_TILE_R * 4);
             const uint32_t j_end = (pb[c] - pb0[c]) / 4;
-            const uint32_t nB = a.qry_n[q];
             const uint32_t bogus = i_end > nA ? i_end - nA : 0;   // steps that consumed padding on both sides
             const uint32_t denom = a.S - bogus;
             const uint32_t common = (i_end - bogus) + (j_end - bogus) - denom;
-            double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
-            const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
-            bool pass = true;
-            double p = 0.0;
-            if (a.max_distance >= 0 && dist > a.max_distance) pass = false;     // CommandDistance.cpp:409-412
-            else {
-                p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
-                if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;        // :419-422
-            }
-            (void)nB;
-            if (a.list_idx && pass) dist_list_append(a, o, common, denom, dist, p);
-            if (a.numer) a.numer[o] = common;
-            if (a.denom) a.denom[o] = denom;
-            if (a.distance) a.distance[o] = dist;
-            if (a.pvalue) a.pvalue[o] = p;
-            if (a.pass) a.pass[o] = pass ? 1 : 0;
+            dist_emit(a, q, r, common, denom, lenA);
         }
         __syncwarp();
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Prefilter: which (query, reference tile) combinations share a hash at all?
+//
+// For most pairs of a large all-vs-all run the answer of the merge is "no shared hash": common = 0, denom =
+// min(s', |A| + |B|), distance 1, p-value 1 (CommandDistance.cpp:347-407 with an empty intersection).  One CTA builds a
+// cuckoo filter (dist_filter.cuh) over the <= 32 x s' ranks of its reference tile, then streams the queries through it:
+// a warp looks 32 ranks of a query up per step (two shared-memory loads each, no loop) instead of running 32 x s' merge
+// steps.  A filter hit is confirmed exactly (each lane binary-searches the rank in its reference's row); the first
+// confirmed hit puts the query on the tile's work list for dist_kernel and ends the query early.  Queries without a
+// confirmed hit get the closed-form result for all 32 pairs written here.  Only ranks at index < s' take part: the merge
+// cannot reach a match at a later index (it would need more than s' union steps).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PROBE_WARPS = 32;
+constexpr int PROBE_THREADS = PROBE_WARPS * 32;
+constexpr int PROBE_DEPTH = 4;          // 32-rank batches in flight per warp
+
+__global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const DistArgs a)
+{
+    extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words
+    __shared__ int s_fail;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r0 = blockIdx.x * DIST_TILE_R;
+    const uint32_t q_lo = a.q_begin + blockIdx.y * a.q_per_cta;
+    const uint32_t q_hi = min(q_lo + a.q_per_cta, a.q_begin + a.q_count);
+    if (q_lo >= q_hi) return;
+
+    for (uint32_t i = threadIdx.x; i < CF_BUCKETS; i += PROBE_THREADS) s_tab[i] = 0;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    for (uint32_t rr = warp; rr < DIST_TILE_R; rr += PROBE_WARPS) {
+        const uint32_t rb = r0 + rr;
+        if (rb >= a.n_ref) break;
+        const uint32_t n = min(a.ref_n[rb], a.S);
+        const uint32_t *row = a.ranks + (a.ref_row0 + rb) * (uint64_t)a.P;
+        for (uint32_t i = lane; i < n; i += 32)
+            if (!cf_insert(s_tab, row[i], threadIdx.x * 2654435761u + i)) s_fail = 1;
+    }
+    __syncthreads();
+    const bool tile_failed = s_fail != 0;       // filter overflow (cannot happen at <= 32 x 1035 ranks): merge everything
+
+    const uint32_t r = r0 + lane;
+    const bool r_ok = r < a.n_ref;
+    const uint32_t nA = r_ok ? a.ref_n[r] : 0;
+    const uint32_t nA_lim = min(nA, a.S);
+    const uint64_t lenA = r_ok ? a.ref_len[r] : 1;
+    const uint32_t *rowA = a.ranks + (a.ref_row0 + (r_ok ? r : r0)) * (uint64_t)a.P;
+
+    for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
+        const uint32_t nB_all = a.qry_n[q];
+        const uint32_t nB = min(nB_all, a.S);
+        const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
+        bool confirmed = tile_failed;
+        for (uint32_t base = 0; base < nB && !confirmed; base += 32 * PROBE_DEPTH) {
+            uint32_t b[PROBE_DEPTH];
+            bool hit[PROBE_DEPTH];
+#pragma unroll
+            for (int c = 0; c < PROBE_DEPTH; c++) {
+                const uint32_t j = base + 32 * c + lane;
+                b[c] = j < nB ? __ldg(rowB + j) : RANK_PAD;
+            }
+            bool any = false;
+#pragma unroll
+            for (int c = 0; c < PROBE_DEPTH; c++) {
+                hit[c] = cf_lookup(s_tab, b[c]) && (base + 32 * c + lane < nB);
+                any |= hit[c];
+            }
+            if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+                for (int c = 0; c < PROBE_DEPTH; c++) {
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, hit[c]);
+                    while (m && !confirmed) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t bb = __shfl_sync(0xFFFFFFFFu, b[c], src);
+                        uint32_t lo = 0, hi = nA_lim;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (rowA[mid] < bb) lo = mid + 1; else hi = mid;
+                        }
+                        const bool found = lo < nA_lim && rowA[lo] == bb;
+                        confirmed = __any_sync(0xFFFFFFFFu, found);
+                    }
+                }
+            }
+        }
+        if (confirmed) {
+            if (lane == 0) {
+                const uint32_t at = atomicAdd(&a.qcount[blockIdx.x], 1u);
+                a.qlist[(uint64_t)blockIdx.x * a.qlist_stride + at] = q;
+                atomicAdd(a.flag_total, 1ull);
+            }
+        } else if (r_ok) {
+            // empty intersection: the merge would take min(s', |A| + |B|) union steps and count nothing
+            const uint32_t denom = min(a.S, nA + nB_all);
+            dist_emit(a, q, r, 0u, denom, lenA);
+        }
     }
 }
 
@@ -276,6 +393,17 @@ struct mashgpu_dist_job {
     // pass-list target of the next run (set by mashgpu_dist_run_list only)
     uint64_t *list_idx = nullptr; uint32_t *list_numer = nullptr, *list_denom = nullptr; double *list_distance = nullptr, *list_pvalue = nullptr;
     unsigned long long *list_count = nullptr; uint64_t list_capacity = 0;
+    // prefilter (dist_probe_kernel): -1 = auto (on; switched off when most combinations turn out to share hashes), 0 = off, 1 = on
+    int prefilter_mode = -1;
+    bool auto_off = false;
+    DevBuf<uint32_t> qlist, qcount;
+    DevBuf<unsigned long long> flag_total;
+    PinnedBuf<unsigned long long> h_flag_total;
+    cudaEvent_t flag_event = nullptr;
+    bool flag_pending = false;          // a snapshot of the device counter is on its way to h_flag_total
+    uint64_t snap_combos = 0;           // combinations probed up to the run the snapshot was taken after
+    uint64_t combos_probed = 0;         // (query, tile) combinations probed so far; flag_total (device) counts the flagged ones
+    ~mashgpu_dist_job() { if (flag_event) cudaEventDestroy(flag_event); }
 };
 
 namespace {
@@ -380,9 +508,48 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     if (!ctx->attr_dist) {   // per context: function attributes are per device
         cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
+        e = cudaFuncSetAttribute(dist_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
         ctx->attr_dist = true;
     }
+    if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
     *job_out = job;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    job->prefilter_mode = mode > 0 ? 1 : (mode == 0 ? 0 : -1);
+    job->auto_off = false;
+    return MASHGPU_OK;
+}
+
+// auto mode: looks at the last snapshot of the flagged-combination counter, if it has arrived.  When most (query, tile)
+// combinations share hashes the probe is pure overhead -- merge everything from then on.
+static void dist_collect_flags(mashgpu_dist_job *job)
+{
+    if (!job->flag_pending) return;
+    if (cudaEventQuery(job->flag_event) != cudaSuccess) { cudaGetLastError(); return; }
+    job->flag_pending = false;
+    const uint64_t flagged = *job->h_flag_total.p;
+    if (job->prefilter_mode < 0 && job->snap_combos >= 64 && flagged * 2 > job->snap_combos) job->auto_off = true;
+}
+
+extern "C" int mashgpu_dist_prefilter_stats(mashgpu_dist_job *job, uint64_t *combos_probed, uint64_t *combos_flagged, int *active)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long flagged = 0;
+    if (job->flag_total.p) {
+        MG_CUDA(ctx, cudaDeviceSynchronize());
+        MG_CUDA(ctx, cudaMemcpy(&flagged, job->flag_total.p, 8, cudaMemcpyDeviceToHost));
+    }
+    dist_collect_flags(job);
+    if (combos_probed) *combos_probed = job->combos_probed;
+    if (combos_flagged) *combos_flagged = flagged;
+    if (active) *active = job->tiled && (job->prefilter_mode > 0 || (job->prefilter_mode < 0 && !job->auto_off));
     return MASHGPU_OK;
 }
 
@@ -408,6 +575,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.numer = d_numer; a.denom = d_denom; a.distance = d_distance; a.pvalue = d_pvalue; a.pass = d_pass;
     a.list_idx = job->list_idx; a.list_numer = job->list_numer; a.list_denom = job->list_denom; a.list_distance = job->list_distance;
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
+    a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
     if (!job->tiled) {
         const uint64_t total = q_count * job->n_ref;
         time_begin(ctx, ctx->dist_events, st);
@@ -419,14 +587,59 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         return MASHGPU_OK;
     }
     const uint32_t r_tiles = (uint32_t)((job->n_ref + DIST_TILE_R - 1) / DIST_TILE_R);
-    // slice the query range so that about 2 waves of CTAs cover the machine, at least one full round of warps each
     const uint32_t round = DIST_WARPS * DIST_ILP;
+    const size_t smem = ((size_t)a.P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * a.P) * 4;
+    a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0;
+    dist_collect_flags(job);
+    const bool prefilter = job->prefilter_mode > 0 || (job->prefilter_mode < 0 && !job->auto_off);
+    if (prefilter) {
+        // pass 1: dist_probe_kernel writes the closed form for (query, tile) combinations without a shared hash and
+        // lists the others per tile; pass 2: dist_kernel merges the listed ones.
+        const uint64_t need = (uint64_t)r_tiles * q_count;
+        if (job->qlist.n < need && job->qlist.alloc(need + need / 4) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (prefilter work lists)");
+        if (job->qcount.n < r_tiles && job->qcount.alloc(r_tiles) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (prefilter counters)");
+        if (!job->flag_total.p) {
+            if (job->flag_total.alloc(1) != cudaSuccess || job->h_flag_total.alloc(1) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of memory (prefilter counter)");
+            MG_CUDA(ctx, cudaEventCreateWithFlags(&job->flag_event, cudaEventDisableTiming));
+            MG_CUDA(ctx, cudaMemsetAsync(job->flag_total.p, 0, 8, st));
+        }
+        MG_CUDA(ctx, cudaMemsetAsync(job->qcount.p, 0, (size_t)r_tiles * 4, st));
+        a.qlist = job->qlist.p; a.qcount = job->qcount.p; a.qlist_stride = q_count; a.flag_total = job->flag_total.p;
+        // probe: one CTA keeps its filter for a long run of queries (the build costs about as much as probing ~100 queries)
+        uint32_t p_slices = std::max(1u, (uint32_t)(2 * ctx->sm_count + r_tiles - 1) / r_tiles);
+        uint32_t p_per_cta = (uint32_t)((q_count + p_slices - 1) / p_slices);
+        p_per_cta = std::max<uint32_t>(p_per_cta, PROBE_WARPS);
+        p_slices = (uint32_t)((q_count + p_per_cta - 1) / p_per_cta);
+        a.q_per_cta = p_per_cta;
+        time_begin(ctx, ctx->dist_events, st);
+        dist_probe_kernel<<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
+        time_end(ctx, ctx->dist_events, st);
+        MG_CUDA(ctx, cudaGetLastError());
+        // merge the listed combinations: a few CTAs per tile walk its list (CTAs of tiles with short lists exit at once)
+        a.use_qlist = 1;
+        a.q_per_cta = 2 * round;
+        const uint32_t m_slices = (uint32_t)std::min<uint64_t>(8, (q_count + a.q_per_cta - 1) / a.q_per_cta);
+        time_begin(ctx, ctx->dist_events, st);
+        dist_kernel<<<dim3(r_tiles, m_slices), DIST_THREADS, smem, st>>>(a);
+        time_end(ctx, ctx->dist_events, st);
+        MG_CUDA(ctx, cudaGetLastError());
+        job->combos_probed += need;
+        if (!job->flag_pending) {           // snapshot of the running flagged count for the auto switch (never waited for)
+            MG_CUDA(ctx, cudaMemcpyAsync(job->h_flag_total.p, job->flag_total.p, 8, cudaMemcpyDeviceToHost, st));
+            MG_CUDA(ctx, cudaEventRecord(job->flag_event, st));
+            job->flag_pending = true;
+            job->snap_combos = job->combos_probed;
+        }
+        ctx->kernel_launches += 2;
+        ctx->dist_launches += 2;
+        return MASHGPU_OK;
+    }
+    // slice the query range so that about 2 waves of CTAs cover the machine, at least one full round of warps each
     uint32_t want_slices = std::max(1u, (uint32_t)(2 * ctx->sm_count + r_tiles - 1) / r_tiles);
     uint32_t q_per_cta = (uint32_t)((q_count + want_slices - 1) / want_slices);
     q_per_cta = std::max(round, ((q_per_cta + round - 1) / round) * round);
     const uint32_t slices = (uint32_t)((q_count + q_per_cta - 1) / q_per_cta);
     a.q_per_cta = q_per_cta;
-    const size_t smem = ((size_t)a.P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * a.P) * 4;
     dim3 grid(r_tiles, slices);
     time_begin(ctx, ctx->dist_events, st);
     dist_kernel<<<grid, DIST_THREADS, smem, st>>>(a);

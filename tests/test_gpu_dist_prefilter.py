@@ -1,0 +1,116 @@
+"""GPU tests of the dist tile prefilter (dist_probe_kernel): pairs that share no hash get the closed form of the merge
+(CommandDistance.cpp:347-407 with an empty intersection) without being merged.  Every result must be identical to the
+merge-everything path and to the oracle, bit for bit (the doubles included: both paths run the same epilogue)."""
+import numpy as np
+import pytest
+
+from fixtures import synth_sketches
+from test_gpu_dist import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("numer", "denom", "distance", "pvalue", "pass")
+
+
+def mixed_sketches(n, s, seed, n_related=40, ragged=True):
+    """Mostly unrelated sketches (every one its own random draw) with a few related families and ragged / empty rows mixed in,
+    in shuffled order, so that reference tiles hold both kinds."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    hi = int(2 ** 64 * s / 5_000_000)
+    H = np.full((n, s), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    N = np.zeros(n, np.uint32)
+    Hf, Nf, _ = synth_sketches(n_related, s, seed + 1, n_families=3, ragged=ragged)
+    for g in range(n):
+        if g < n_related:
+            H[g], N[g] = Hf[g], Nf[g]
+            continue
+        m = s
+        if ragged and g % 7 == 0:
+            m = int(rng.integers(0, s + 1))
+        v = np.unique(rng.integers(0, hi, s + 8, dtype=np.uint64))[:m]
+        H[g, :v.size] = v
+        N[g] = v.size
+    perm = rng.permutation(n)
+    L = rng.integers(4_000_000, 6_000_000, n).astype(np.uint64)
+    return H[perm], N[perm], L
+
+
+def run_modes(gpu, H, N, L, Hq=None, Nq=None, Lq=None, *, s, k, q_begin=0, q_count=None, **kw):
+    out = {}
+    stats = None
+    for mode in (0, 1):
+        job = gpu.dist_open(H, N, L, Hq, Nq, Lq, sketch_size=s, k=k, kmer_space=4.0 ** k, **kw)
+        try:
+            job.set_prefilter(mode)
+            out[mode] = job.run(q_begin, job.n_qry - q_begin if q_count is None else q_count)
+            if mode == 1:
+                stats = job.prefilter_stats()
+        finally:
+            job.close()
+    for key in KEYS:
+        assert np.array_equal(out[0][key], out[1][key]), key
+    return out[1], stats
+
+
+@pytest.mark.parametrize("s,k", [(1000, 21), (200, 16), (13, 11), (1, 21)])
+def test_prefilter_equals_merge_and_oracle(gpu, oracle, s, k):
+    H, N, L = mixed_sketches(150, s, seed=11 + s)
+    Hq, Nq, Lq = mixed_sketches(77, s, seed=500 + s, n_related=20)
+    Hq[:5] = H[:5]; Nq[:5] = N[:5]
+    res, st = run_modes(gpu, H, N, L, Hq, Nq, Lq, s=s, k=k)
+    want = oracle.compare_all(H, N, L, Hq, Nq, Lq, s, k, 4.0 ** k)
+    check_against_oracle(res, want)
+    assert st["active"] and st["combos_probed"] == 77 * 5          # ceil(150 / 32) reference tiles
+    if s >= 200:
+        assert 0 < st["combos_flagged"] < st["combos_probed"]      # both the closed form and the merge were exercised
+
+
+def test_prefilter_self_ranges_and_thresholds(gpu, oracle):
+    s, k = 500, 21
+    H, N, L = mixed_sketches(200, s, seed=7)
+    for md, mp in ((1.0, 1.0), (0.1, 1.0), (1.0, 1e-10), (-1.0, -1.0)):
+        res, _ = run_modes(gpu, H, N, L, s=s, k=k, q_begin=23, q_count=131, max_distance=md, max_pvalue=mp)
+        want = oracle.compare_all(H, N, L, H, N, L, s, k, 4.0 ** k, max_distance=md, max_pvalue=mp, q_begin=23, q_end=154)[23:154]
+        check_against_oracle(res, want)
+
+
+def test_prefilter_lists_longer_than_sketch_size(gpu, oracle):
+    # s' = 300 < list lengths: only the first 300 ranks of a row can take part in a merge, and in the filter
+    H, N, L = mixed_sketches(120, 1000, seed=3)
+    res, st = run_modes(gpu, H, N, L, s=300, k=21)
+    want = oracle.compare_all(H, N, L, H, N, L, 300, 21, 4.0 ** 21)
+    check_against_oracle(res, want)
+
+
+def test_prefilter_pass_list(gpu):
+    s, k = 600, 21
+    H, N, L = mixed_sketches(180, s, seed=19)
+    lists = {}
+    for mode in (0, 1):
+        job = gpu.dist_open(H, N, L, sketch_size=s, k=k, kmer_space=4.0 ** k, max_distance=0.2, max_pvalue=1e-3)
+        try:
+            job.set_prefilter(mode)
+            lists[mode] = job.run_list(0, 180, 180 * 180)
+        finally:
+            job.close()
+    assert lists[0][0] == lists[1][0] > 0
+    for key in ("index", "numer", "denom", "distance", "pvalue"):
+        assert np.array_equal(lists[0][1][key], lists[1][1][key])
+
+
+def test_auto_mode_switches_off_on_dense_sets(gpu):
+    # every query shares hashes with every tile: after the first run the counters say so and later runs merge directly
+    s, k = 400, 21
+    H, N, L = synth_sketches(96, s, seed=2, n_families=1)
+    job = gpu.dist_open(H, N, L, sketch_size=s, k=k, kmer_space=4.0 ** k)
+    try:
+        first = job.run(0, 96)
+        st = job.prefilter_stats()
+        assert st["combos_probed"] == 96 * 3 and st["combos_flagged"] == 96 * 3
+        second = job.run(0, 96)
+        st2 = job.prefilter_stats()
+        assert not st2["active"] and st2["combos_probed"] == st["combos_probed"]
+        for key in KEYS:
+            assert np.array_equal(first[key], second[key])
+    finally:
+        job.close()
