@@ -452,17 +452,58 @@ def main():
         pairs_per_rank = n_ref * n_qry
         total_pairs = pairs_per_rank * world
         last_shared_nonzero = int((o_numer[: min(q_tile, n_qry) * n_ref] > 0).sum().item())
+        pf = job.prefilter_stats()
+
+        def one_tile_rate(j, reps=2):
+            """pairs/s of this rank on the first query tile only (side measurements: merge-only and shuffled order)."""
+            qc = min(q_tile, j.n_qry)
+            j.run_dev(0, qc, o_numer.data_ptr(), o_denom.data_ptr(), o_dist.data_ptr(), o_p.data_ptr(), o_pass.data_ptr(), stream=st_ptr)
+            torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(st)
+            for _ in range(reps):
+                j.run_dev(0, qc, o_numer.data_ptr(), o_denom.data_ptr(), o_dist.data_ptr(), o_p.data_ptr(), o_pass.data_ptr(), stream=st_ptr)
+            a1.record(st); torch.cuda.synchronize()
+            return qc * j.n_ref / (a0.elapsed_time(a1) / reps * 1e-3)
+
+        side = {}
+        if rank == 0:
+            side["first_query_tile_as_timed"] = one_tile_rate(job)
+            job.set_prefilter(0)
+            side["first_query_tile_merge_every_pair"] = one_tile_rate(job)
+            job.set_prefilter(-1)
         dist_obj = {"metric": "sketch_pairs_per_s", "value": total_pairs / (dms * 1e-3), "unit": "pairs/s", "ms_per_step": dms,
                     "steps": dK, "warmup": dW, "pairs_per_step": total_pairs, "enumeration": "all ordered pairs (full Q x R grid)",
-                    "workload": f"configs[2]: {n_sk} synthetic s={S} sketches all-vs-all, 100 families; reference axis sharded over {world} rank(s)",
+                    "workload": f"configs[2]: {n_sk} synthetic s={S} sketches all-vs-all, 100 families stored family by family (SURVEY.md 8d generator); "
+                                f"reference axis sharded over {world} rank(s)",
                     "outputs": "dense numer,denom (u32), distance,pvalue (f64), pass (u8) = 25 B/pair written to an HBM tile buffer that is reused per query tile",
+                    "algorithm": "tile prefilter (cuckoo filter per 32-reference tile; closed form for pairs without shared hashes) + sorted merge of the "
+                                 "rest + dense p-value pass; results identical to merging every pair (tests/test_gpu_dist_prefilter.py)",
+                    "prefilter": {"query_tile_combinations_probed": pf["combos_probed"], "sent_to_merge": pf["combos_flagged"],
+                                  "fraction_merged": (pf["combos_flagged"] / pf["combos_probed"]) if pf["combos_probed"] else None},
                     "dict_build_ms": open_ms, "query_broadcast_ms": bcast_ms,
                     "kernel_ms_per_step": dstats["dist_kernel_ms"] / dK, "gpu_launches": int(dstats["kernel_launches"]),
                     "pairs_with_shared_hashes_in_last_tile": last_shared_nonzero,
                     "roofline": {"bound": "hbm", "achieved": (total_pairs / world * 25 + (n_ref + n_qry) * S * 4) / (dstats["dist_kernel_ms"] / dK * 1e-3) / 1e9,
-                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "note": "shared-memory/issue bound merge, not HBM bound (DESIGN.md)"}}
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "note": "algorithmic bytes = 25 B/pair written + the rank rows read once; the probe kernel is ALU-pipe bound and the merge "
+                                         "kernel shared-memory bound, not HBM bound (DESIGN.md 3.3)"}}
         dist_obj["roofline"]["frac"] = dist_obj["roofline"]["achieved"] / peaks["hbm_gbs"]
         job.close()
+        if rank == 0:
+            # the same sketches in random order: related sketches no longer sit in the same reference tile, more tiles reach the merge
+            perm = torch.randperm(H.shape[0], device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+            Hs = H[perm].contiguous(); Ls = L[perm].contiguous()
+            sset = mash_b200._capi._Set(Hs.data_ptr(), N.data_ptr(), Ls.data_ptr(), on_device=True, n=Hs.shape[0], stride=S)
+            sjob2 = mash_b200._capi.DistJob(eng, sset, None, None, None, None, None, S, K, p.kmer_space, 1.0, 1.0)
+            side["first_query_tile_shuffled_order"] = one_tile_rate(sjob2)
+            sjob2.set_prefilter(0)
+            side["first_query_tile_shuffled_order_merge_every_pair"] = one_tile_rate(sjob2)
+            sjob2.close()
+            del Hs, Ls, sset
+            side["note"] = ("pairs/s of rank 0 on one query tile of its own shard (self comparison), outside the timed region; 'merge_every_pair' = prefilter off "
+                            "(the reference's algorithm for every pair)")
+        dist_obj["side_measurements"] = side
 
         # ---------------- hot path 3: screen (configs[3], rank 0's sketches as the reference .msh) -----------------
         if not args.skip_screen:

@@ -31,6 +31,7 @@ constexpr int DIST_THREADS = DIST_WARPS * 32;
 constexpr int DIST_TILE_R = 32;
 static_assert(DIST_TILE_R * 4 == 128, "the merge step's PTX hard-codes the 128-byte stride of the interleaved reference tile");
 
+struct FixEntry;
 struct DistArgs {
     const uint32_t *ranks;      // rows of P ranks: references first, then queries (or shared when self)
     uint32_t P;                 // row pitch = sketch_size + 1
@@ -53,7 +54,11 @@ struct DistArgs {
     // prefilter work lists (dist_probe_kernel -> dist_kernel): per reference tile the queries that share a hash with it
     uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
     int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
+    // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
+    struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
 };
+
+struct FixEntry { uint64_t o; uint32_t common, denom; };
 
 __device__ __forceinline__ void dist_list_append(const DistArgs &a, uint64_t o, uint32_t common, uint32_t denom, double dist, double p)
 {
@@ -81,23 +86,60 @@ __device__ __forceinline__ double mash_distance(uint32_t common, uint32_t denom,
 }
 
 // Epilogue of compareSketches for one pair (CommandDistance.cpp:387-424) given the merge result.
+// The binomial tail of a pair with shared hashes costs more than its merge (up to `common` multiply-divide steps), and such
+// pairs are a small, scattered minority of a large grid: evaluated in place they leave 31 lanes of the warp waiting (measured
+// on configs[2] in shuffled order: 94 of 275 ms).  They are queued instead and dist_fix_kernel evaluates them densely; when
+// the queue is full (data sets where most pairs share hashes -- then the lanes of a warp are busy together anyway) the tail
+// is evaluated here.
 __device__ __forceinline__ void dist_emit(const DistArgs &a, uint32_t q, uint32_t r, uint32_t common, uint32_t denom, uint64_t lenA)
 {
     double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
     const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
-    bool pass = true;
+    bool pass = true, deferred = false;
     double p = 0.0;
     if (a.max_distance >= 0 && dist > a.max_distance) pass = false;     // CommandDistance.cpp:409-412
-    else {
-        p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
-        if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;        // :419-422
+    else if (common == 0) {                                             // pValue: x == 0 -> 1 (:429-432)
+        p = 1.0;
+        if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;
+    } else {
+        if (a.fix_list) {
+            const unsigned long long at = atomicAdd(a.fix_count, 1ull);
+            if (at < a.fix_capacity) {
+                a.fix_list[at] = FixEntry{o, common, denom};
+                deferred = true;
+            }
+        }
+        if (!deferred) {
+            p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
+            if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;    // :419-422
+        }
     }
-    if (a.list_idx && pass) dist_list_append(a, o, common, denom, dist, p);
     if (a.numer) a.numer[o] = common;
     if (a.denom) a.denom[o] = denom;
     if (a.distance) a.distance[o] = dist;
+    if (deferred) return;
+    if (a.list_idx && pass) dist_list_append(a, o, common, denom, dist, p);
     if (a.pvalue) a.pvalue[o] = p;
     if (a.pass) a.pass[o] = pass ? 1 : 0;
+}
+
+// second pass over the queued pairs: p-value, pass flag, pass-list entry
+__global__ void __launch_bounds__(256) dist_fix_kernel(const DistArgs a)
+{
+    const unsigned long long queued = *a.fix_count;
+    const uint64_t n = queued < a.fix_capacity ? queued : a.fix_capacity;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const FixEntry e = a.fix_list[t];
+        const uint32_t q = a.q_begin + (uint32_t)(e.o / a.n_ref), r = (uint32_t)(e.o % a.n_ref);
+        const double p = mash_pvalue(e.common, a.ref_len[r], a.qry_len[q], a.kmer_space, e.denom);
+        const bool pass = !(a.max_pvalue >= 0 && p > a.max_pvalue);
+        if (a.list_idx && pass) {
+            const double dist = (e.denom == a.S) ? a.dist_lut[e.common] : mash_distance(e.common, e.denom, a.kmer_size);
+            dist_list_append(a, e.o, e.common, e.denom, dist, p);
+        }
+        if (a.pvalue) a.pvalue[e.o] = p;
+        if (a.pass) a.pass[e.o] = pass ? 1 : 0;
+    }
 }
 
 __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
@@ -206,6 +248,48 @@ constexpr int PROBE_WARPS = 32;
 constexpr int PROBE_THREADS = PROBE_WARPS * 32;
 constexpr int PROBE_DEPTH = 4;          // 32-rank batches in flight per warp
 
+// One group of PROBE_DEPTH x 32 ranks of a query against the filter.  FULL: the whole group lies inside the query's list.
+// Returns true when a rank is confirmed to be in one of the tile's references.
+template <bool FULL>
+__device__ __forceinline__ bool probe_group(const uint32_t *s_tab, const uint32_t *rowB, uint32_t base, uint32_t nB, int lane,
+                                            const uint32_t *rowA, uint32_t nA_lim)
+{
+    uint32_t b[PROBE_DEPTH];
+    bool hit[PROBE_DEPTH];
+#pragma unroll
+    for (int c = 0; c < PROBE_DEPTH; c++) {
+        const uint32_t j = base + 32 * c + lane;
+        b[c] = (FULL || j < nB) ? __ldg(rowB + j) : RANK_PAD;
+    }
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < PROBE_DEPTH; c++) {
+        hit[c] = cf_lookup(s_tab, b[c]) && (FULL || base + 32 * c + lane < nB);
+        any |= hit[c];
+    }
+    if (!__any_sync(0xFFFFFFFFu, any)) return false;
+    // filter hits are rare unless the query really shares hashes with the tile: confirm exactly, every lane searching the
+    // rank in its own reference's row (global memory)
+    bool confirmed = false;
+#pragma unroll
+    for (int c = 0; c < PROBE_DEPTH; c++) {
+        unsigned m = __ballot_sync(0xFFFFFFFFu, hit[c]);
+        while (m && !confirmed) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t bb = __shfl_sync(0xFFFFFFFFu, b[c], src);
+            uint32_t lo = 0, hi = nA_lim;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (rowA[mid] < bb) lo = mid + 1; else hi = mid;
+            }
+            const bool found = lo < nA_lim && rowA[lo] == bb;
+            confirmed = __any_sync(0xFFFFFFFFu, found);
+        }
+    }
+    return confirmed;
+}
+
 __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const DistArgs a)
 {
     extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words
@@ -236,45 +320,22 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     const uint32_t nA_lim = min(nA, a.S);
     const uint64_t lenA = r_ok ? a.ref_len[r] : 1;
     const uint32_t *rowA = a.ranks + (a.ref_row0 + (r_ok ? r : r0)) * (uint64_t)a.P;
+    // closed form of a pair without shared hashes whose union still reaches s' elements (the usual case): constants
+    const double lut0 = a.dist_lut[0];
+    const bool far = a.max_distance >= 0 && lut0 > a.max_distance;           // dist_emit: filtered by -d, p-value left 0
+    const double p_const = far ? 0.0 : 1.0;
+    const uint8_t pass_const = (far || (a.max_pvalue >= 0 && 1.0 > a.max_pvalue)) ? 0 : 1;
 
     for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
         const uint32_t nB_all = a.qry_n[q];
         const uint32_t nB = min(nB_all, a.S);
         const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
         bool confirmed = tile_failed;
-        for (uint32_t base = 0; base < nB && !confirmed; base += 32 * PROBE_DEPTH) {
-            uint32_t b[PROBE_DEPTH];
-            bool hit[PROBE_DEPTH];
-#pragma unroll
-            for (int c = 0; c < PROBE_DEPTH; c++) {
-                const uint32_t j = base + 32 * c + lane;
-                b[c] = j < nB ? __ldg(rowB + j) : RANK_PAD;
-            }
-            bool any = false;
-#pragma unroll
-            for (int c = 0; c < PROBE_DEPTH; c++) {
-                hit[c] = cf_lookup(s_tab, b[c]) && (base + 32 * c + lane < nB);
-                any |= hit[c];
-            }
-            if (__any_sync(0xFFFFFFFFu, any)) {
-#pragma unroll
-                for (int c = 0; c < PROBE_DEPTH; c++) {
-                    unsigned m = __ballot_sync(0xFFFFFFFFu, hit[c]);
-                    while (m && !confirmed) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint32_t bb = __shfl_sync(0xFFFFFFFFu, b[c], src);
-                        uint32_t lo = 0, hi = nA_lim;
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (rowA[mid] < bb) lo = mid + 1; else hi = mid;
-                        }
-                        const bool found = lo < nA_lim && rowA[lo] == bb;
-                        confirmed = __any_sync(0xFFFFFFFFu, found);
-                    }
-                }
-            }
-        }
+        uint32_t base = 0;
+        for (; base + 32 * PROBE_DEPTH <= nB && !confirmed; base += 32 * PROBE_DEPTH)
+            confirmed = probe_group<true>(s_tab, rowB, base, nB, lane, rowA, nA_lim);
+        for (; base < nB && !confirmed; base += 32 * PROBE_DEPTH)
+            confirmed = probe_group<false>(s_tab, rowB, base, nB, lane, rowA, nA_lim);
         if (confirmed) {
             if (lane == 0) {
                 const uint32_t at = atomicAdd(&a.qcount[blockIdx.x], 1u);
@@ -284,7 +345,16 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
         } else if (r_ok) {
             // empty intersection: the merge would take min(s', |A| + |B|) union steps and count nothing
             const uint32_t denom = min(a.S, nA + nB_all);
-            dist_emit(a, q, r, 0u, denom, lenA);
+            if (denom == a.S && !a.list_idx) {
+                const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
+                if (a.numer) a.numer[o] = 0;
+                if (a.denom) a.denom[o] = denom;
+                if (a.distance) a.distance[o] = lut0;
+                if (a.pvalue) a.pvalue[o] = p_const;
+                if (a.pass) a.pass[o] = pass_const;
+            } else {
+                dist_emit(a, q, r, 0u, denom, lenA);
+            }
         }
     }
 }
@@ -310,20 +380,7 @@ __global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
     const uint32_t bogus = i > nA ? i - nA : 0;
     const uint32_t denom = a.S - bogus;
     const uint32_t common = (i - bogus) + (j - bogus) - denom;
-    const double dist = (denom == a.S) ? a.dist_lut[common] : mash_distance(common, denom, a.kmer_size);
-    bool pass = true;
-    double p = 0.0;
-    if (a.max_distance >= 0 && dist > a.max_distance) pass = false;
-    else {
-        p = mash_pvalue(common, a.ref_len[r], a.qry_len[q], a.kmer_space, denom);
-        if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;
-    }
-    if (a.list_idx && pass) dist_list_append(a, t, common, denom, dist, p);
-    if (a.numer) a.numer[t] = common;
-    if (a.denom) a.denom[t] = denom;
-    if (a.distance) a.distance[t] = dist;
-    if (a.pvalue) a.pvalue[t] = p;
-    if (a.pass) a.pass[t] = pass ? 1 : 0;
+    dist_emit(a, q, r, common, denom, a.ref_len[r]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -397,6 +454,8 @@ struct mashgpu_dist_job {
     int prefilter_mode = -1;
     bool auto_off = false;
     DevBuf<uint32_t> qlist, qcount;
+    DevBuf<FixEntry> fix_list;
+    DevBuf<unsigned long long> fix_count;
     DevBuf<unsigned long long> flag_total;
     PinnedBuf<unsigned long long> h_flag_total;
     cudaEvent_t flag_event = nullptr;
@@ -576,14 +635,28 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.list_idx = job->list_idx; a.list_numer = job->list_numer; a.list_denom = job->list_denom; a.list_distance = job->list_distance;
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
+    {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
+        const uint64_t pairs = q_count * job->n_ref;
+        const uint64_t cap = std::min<uint64_t>(pairs, std::max<uint64_t>(1ull << 20, pairs / 16));
+        if (job->fix_list.n < cap && job->fix_list.alloc(cap) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (p-value queue)");
+        if (!job->fix_count.p && job->fix_count.alloc(1) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (p-value queue)");
+        MG_CUDA(ctx, cudaMemsetAsync(job->fix_count.p, 0, 8, st));
+        a.fix_list = job->fix_list.p; a.fix_count = job->fix_count.p; a.fix_capacity = cap;
+    }
+    auto launch_fix = [&]() {
+        dist_fix_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a);
+        ctx->kernel_launches++;
+        return cudaGetLastError();
+    };
     if (!job->tiled) {
         const uint64_t total = q_count * job->n_ref;
         time_begin(ctx, ctx->dist_events, st);
         dist_kernel_general<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        MG_CUDA(ctx, cudaGetLastError());
+        MG_CUDA(ctx, launch_fix());
         time_end(ctx, ctx->dist_events, st);
         ctx->kernel_launches++;
         ctx->dist_launches++;
-        MG_CUDA(ctx, cudaGetLastError());
         return MASHGPU_OK;
     }
     const uint32_t r_tiles = (uint32_t)((job->n_ref + DIST_TILE_R - 1) / DIST_TILE_R);
@@ -621,8 +694,9 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         const uint32_t m_slices = (uint32_t)std::min<uint64_t>(8, (q_count + a.q_per_cta - 1) / a.q_per_cta);
         time_begin(ctx, ctx->dist_events, st);
         dist_kernel<<<dim3(r_tiles, m_slices), DIST_THREADS, smem, st>>>(a);
-        time_end(ctx, ctx->dist_events, st);
         MG_CUDA(ctx, cudaGetLastError());
+        MG_CUDA(ctx, launch_fix());
+        time_end(ctx, ctx->dist_events, st);
         job->combos_probed += need;
         if (!job->flag_pending) {           // snapshot of the running flagged count for the auto switch (never waited for)
             MG_CUDA(ctx, cudaMemcpyAsync(job->h_flag_total.p, job->flag_total.p, 8, cudaMemcpyDeviceToHost, st));
@@ -643,10 +717,11 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     dim3 grid(r_tiles, slices);
     time_begin(ctx, ctx->dist_events, st);
     dist_kernel<<<grid, DIST_THREADS, smem, st>>>(a);
+    MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, launch_fix());
     time_end(ctx, ctx->dist_events, st);
     ctx->kernel_launches++;
     ctx->dist_launches++;
-    MG_CUDA(ctx, cudaGetLastError());
     return MASHGPU_OK;
 }
 

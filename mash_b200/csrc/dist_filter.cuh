@@ -7,9 +7,12 @@
 // confirmed by an exact binary search before the tile is handed to the merge kernel.
 //
 // Layout: 2^15 buckets of two 16-bit fingerprints (one 32-bit word per bucket, 128 KB of shared memory), 0 = free slot.
-// h = rank * odd constant is a bijection of the 32-bit rank: bucket = top 15 bits, fingerprint = low 16 bits (0 -> 1);
-// the alternate bucket is bucket ^ f(fingerprint) (partial-key cuckoo hashing), so a lookup is exactly two shared-memory
-// loads and no loop.  32 references x 1000 ranks fill 49 % of the slots (two-slot buckets work up to ~84 %).
+// h = rank * odd constant is a bijection of the 32-bit rank: bucket = low 15 bits (a bijection of the rank's low 15 bits,
+// which are uniform for dictionary ranks), fingerprint = top 16 bits (0 -> 1); the alternate bucket is
+// bucket ^ f(fingerprint) (partial-key cuckoo hashing), so a lookup is exactly two shared-memory loads and no loop.
+// The bit assignment is chosen for the lookup's instruction count: the byte offset of the bucket is (h << 2) & mask and
+// the alternate one xor-and of a product, one ALU-pipe instruction each (the probe kernel is bound by that pipe).
+// 32 references x 1000 ranks fill 49 % of the slots (two-slot buckets work up to ~84 %).
 //
 // The functions compile for the host too (tests/test_dist_filter.py drives them through tools/cf_host_test.cpp) --
 // there the "atomic" is a plain compare-and-swap.
@@ -29,9 +32,9 @@ constexpr uint32_t CF_BUCKETS = 1u << CF_LOG2_BUCKETS;
 constexpr uint32_t CF_MAX_KICKS = 256;
 
 MG_HD uint32_t cf_hash(uint32_t code) { return code * 0x9E3779B1u; }
-MG_HD uint32_t cf_fp(uint32_t h) { const uint32_t f = h & 0xFFFFu; return f ? f : 1u; }
-MG_HD uint32_t cf_bucket(uint32_t h) { return h >> (32 - CF_LOG2_BUCKETS); }
-MG_HD uint32_t cf_alt(uint32_t bucket, uint32_t fp) { return bucket ^ ((fp * 0x5BD1E995u) >> (32 - CF_LOG2_BUCKETS)); }
+MG_HD uint32_t cf_fp(uint32_t h) { const uint32_t f = h >> 16; return f ? f : 1u; }
+MG_HD uint32_t cf_bucket(uint32_t h) { return h & (CF_BUCKETS - 1u); }
+MG_HD uint32_t cf_alt(uint32_t bucket, uint32_t fp) { return bucket ^ ((fp * 0x5BD1E995u) & (CF_BUCKETS - 1u)); }
 
 // does one of the two 16-bit halves of w equal fp (fp != 0)
 MG_HD bool cf_word_has(uint32_t w, uint32_t fp)
@@ -111,9 +114,12 @@ MG_HD bool cf_lookup(const uint32_t *tab, uint32_t code)
 {
     const uint32_t h = cf_hash(code);
     const uint32_t fp = cf_fp(h);
-    const uint32_t b1 = cf_bucket(h), b2 = cf_alt(b1, fp);
+    // byte offsets of the two buckets (same values as 4 * cf_bucket(h) and 4 * cf_alt(cf_bucket(h), fp))
+    const uint32_t o1 = (h << 2) & (4u * CF_BUCKETS - 4u);
+    const uint32_t o2 = o1 ^ ((fp * (0x5BD1E995u << 2)) & (4u * CF_BUCKETS - 4u));
     const uint32_t f2 = fp * 0x00010001u;
-    const uint32_t x1 = tab[b1] ^ f2, x2 = tab[b2] ^ f2;
+    const uint32_t x1 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o1) ^ f2;
+    const uint32_t x2 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o2) ^ f2;
     return ((((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2)) & 0x80008000u) != 0;
 }
 
