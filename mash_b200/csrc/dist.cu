@@ -254,20 +254,23 @@ template <bool FULL>
 __device__ __forceinline__ bool probe_group(const uint32_t *s_tab, const uint32_t *rowB, uint32_t base, uint32_t nB, int lane,
                                             const uint32_t *rowA, uint32_t nA_lim)
 {
+    static_assert(PROBE_DEPTH == 4, "cf_group_any takes four probes");
     uint32_t b[PROBE_DEPTH];
-    bool hit[PROBE_DEPTH];
+    CfProbe pr[PROBE_DEPTH];
 #pragma unroll
     for (int c = 0; c < PROBE_DEPTH; c++) {
         const uint32_t j = base + 32 * c + lane;
         b[c] = (FULL || j < nB) ? __ldg(rowB + j) : RANK_PAD;
     }
-    bool any = false;
 #pragma unroll
     for (int c = 0; c < PROBE_DEPTH; c++) {
-        hit[c] = cf_lookup(s_tab, b[c]) && (FULL || base + 32 * c + lane < nB);
-        any |= hit[c];
+        pr[c] = cf_fetch(s_tab, b[c]);
+        if (!FULL && base + 32 * c + lane >= nB) pr[c].f2 = 0x7E007E00u;       // past the end of the list: never matches
     }
-    if (!__any_sync(0xFFFFFFFFu, any)) return false;
+    if (!cf_group_any(pr[0], pr[1], pr[2], pr[3])) return false;
+    bool hit[PROBE_DEPTH];
+#pragma unroll
+    for (int c = 0; c < PROBE_DEPTH; c++) hit[c] = cf_lookup(s_tab, b[c]) && (FULL || base + 32 * c + lane < nB);
     // filter hits are rare unless the query really shares hashes with the tile: confirm exactly, every lane searching the
     // rank in its own reference's row (global memory)
     bool confirmed = false;

@@ -8,10 +8,13 @@
 //
 // Layout: 2^15 buckets of two 16-bit fingerprints (one 32-bit word per bucket, 128 KB of shared memory), 0 = free slot.
 // h = rank * odd constant is a bijection of the 32-bit rank: bucket = low 15 bits (a bijection of the rank's low 15 bits,
-// which are uniform for dictionary ranks), fingerprint = top 16 bits (0 -> 1); the alternate bucket is
+// which are uniform for dictionary ranks), fingerprint = 14 of the bits 15..29 of h; the alternate bucket is
 // bucket ^ f(fingerprint) (partial-key cuckoo hashing), so a lookup is exactly two shared-memory loads and no loop.
-// The bit assignment is chosen for the lookup's instruction count: the byte offset of the bucket is (h << 2) & mask and
-// the alternate one xor-and of a product, one ALU-pipe instruction each (the probe kernel is bound by that pipe).
+// The bit assignment is chosen for the lookup's instruction count (the probe kernel is bound by the ALU pipe): the byte
+// offset of the bucket is (h << 2) & mask and the alternate one an xor-and of a product, one ALU instruction each; and a
+// fingerprint always has bit 14 clear and bit 0 set, which makes it, read as an IEEE half, a finite non-zero number --
+// so "is fp in this bucket" is ONE half2 compare (HSETP2, two predicates) instead of the xor / subtract / and-not
+// zero-halfword test, and the free slot 0x0000 (+0.0) never compares equal.
 // 32 references x 1000 ranks fill 49 % of the slots (two-slot buckets work up to ~84 %).
 //
 // The functions compile for the host too (tests/test_dist_filter.py drives them through tools/cf_host_test.cpp) --
@@ -32,7 +35,7 @@ constexpr uint32_t CF_BUCKETS = 1u << CF_LOG2_BUCKETS;
 constexpr uint32_t CF_MAX_KICKS = 256;
 
 MG_HD uint32_t cf_hash(uint32_t code) { return code * 0x9E3779B1u; }
-MG_HD uint32_t cf_fp(uint32_t h) { const uint32_t f = h >> 16; return f ? f : 1u; }
+MG_HD uint32_t cf_fp(uint32_t h) { return ((h >> 14) & 0xBFFEu) + 1u; }       // bits 15..27 and 29 of h, bit 0 set, bit 14 clear
 MG_HD uint32_t cf_bucket(uint32_t h) { return h & (CF_BUCKETS - 1u); }
 MG_HD uint32_t cf_alt(uint32_t bucket, uint32_t fp) { return bucket ^ ((fp * 0x5BD1E995u) & (CF_BUCKETS - 1u)); }
 
@@ -114,13 +117,61 @@ MG_HD bool cf_lookup(const uint32_t *tab, uint32_t code)
 {
     const uint32_t h = cf_hash(code);
     const uint32_t fp = cf_fp(h);
-    // byte offsets of the two buckets (same values as 4 * cf_bucket(h) and 4 * cf_alt(cf_bucket(h), fp))
-    const uint32_t o1 = (h << 2) & (4u * CF_BUCKETS - 4u);
-    const uint32_t o2 = o1 ^ ((fp * (0x5BD1E995u << 2)) & (4u * CF_BUCKETS - 4u));
-    const uint32_t f2 = fp * 0x00010001u;
-    const uint32_t x1 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o1) ^ f2;
-    const uint32_t x2 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o2) ^ f2;
-    return ((((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2)) & 0x80008000u) != 0;
+    const uint32_t w1 = tab[cf_bucket(h)], w2 = tab[cf_alt(cf_bucket(h), fp)];
+    return cf_word_has(w1, fp) || cf_word_has(w2, fp);
 }
+
+// The probe kernel's form of the lookup: everything derives from ONE product h4 = rank * (C << 2) = h << 2:
+//   byte offset of bucket 1 = h4 & mask;  x = (h4 >> 16) & 0xBFFE = fp - 1;  offset 2 = offset 1 ^ ((x * K + K) & mask)
+//   with K = (alt multiplier << 2);  f2 = x * 0x10001 + 0x10001 = fp in both halves.
+// Returns the two bucket words and f2; the comparison is done for a whole group by cf_group_any.
+struct CfProbe { uint32_t w1, w2, f2; };
+MG_HD void cf_offsets(uint32_t code, uint32_t &o1, uint32_t &o2, uint32_t &f2)
+{
+    constexpr uint32_t OFF_MASK = 4u * CF_BUCKETS - 4u;
+    const uint32_t h4 = code * (0x9E3779B1u << 2);
+    o1 = h4 & OFF_MASK;
+    const uint32_t x = (h4 >> 16) & 0xBFFEu;
+    o2 = o1 ^ ((x * (0x5BD1E995u << 2) + (0x5BD1E995u << 2)) & OFF_MASK);
+    f2 = x * 0x00010001u + 0x00010001u;
+}
+MG_HD CfProbe cf_fetch(const uint32_t *tab, uint32_t code)
+{
+    uint32_t o1, o2;
+    CfProbe r;
+    cf_offsets(code, o1, o2, r.f2);
+    r.w1 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o1);
+    r.w2 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab) + o2);
+    return r;
+}
+
+#if defined(__CUDACC__)
+
+// Does any lane of the warp have a fingerprint match in any of its four probes?  8 half2 compares (a fingerprint is a
+// finite non-zero half, the free slot is +0.0), predicate ors and one vote.  An f2 of 0x7E007E00 (NaN) never matches.
+__device__ __forceinline__ bool cf_group_any(const CfProbe &a, const CfProbe &b, const CfProbe &c, const CfProbe &d)
+{
+    uint32_t any;
+    asm volatile("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7, q;\n\t"
+                 "setp.eq.f16x2 p0|p1, %1, %3;\n\t"
+                 "setp.eq.f16x2 p2|p3, %2, %3;\n\t"
+                 "setp.eq.f16x2 p4|p5, %4, %6;\n\t"
+                 "setp.eq.f16x2 p6|p7, %5, %6;\n\t"
+                 "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p4, p4, p5;\n\tor.pred p6, p6, p7;\n\t"
+                 "or.pred p0, p0, p2;\n\tor.pred p4, p4, p6;\n\tor.pred q, p0, p4;\n\t"
+                 "setp.eq.f16x2 p0|p1, %7, %9;\n\t"
+                 "setp.eq.f16x2 p2|p3, %8, %9;\n\t"
+                 "setp.eq.f16x2 p4|p5, %10, %12;\n\t"
+                 "setp.eq.f16x2 p6|p7, %11, %12;\n\t"
+                 "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p4, p4, p5;\n\tor.pred p6, p6, p7;\n\t"
+                 "or.pred p0, p0, p2;\n\tor.pred p4, p4, p6;\n\tor.pred p0, p0, p4;\n\tor.pred q, q, p0;\n\t"
+                 "vote.sync.any.pred q, q, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(any)
+                 : "r"(a.w1), "r"(a.w2), "r"(a.f2), "r"(b.w1), "r"(b.w2), "r"(b.f2),
+                   "r"(c.w1), "r"(c.w2), "r"(c.f2), "r"(d.w1), "r"(d.w2), "r"(d.f2));
+    return any != 0;
+}
+#endif
 
 }  // namespace mashgpu

@@ -31,6 +31,16 @@ int main(int argc, char **argv)
     for (uint32_t c : stream) { members.insert(c); if (!cf_insert(tab.data(), c, salt++)) failed++; }
     int missing = 0;
     for (uint32_t c : members) if (!cf_lookup(tab.data(), c)) missing++;
+    // the probe kernel's one-product form must address the same buckets and carry the same fingerprint
+    int form_mismatch = 0;
+    for (int i = 0; i < 200000; i++) {
+        const uint32_t c = (uint32_t)rng();
+        uint32_t o1, o2, f2;
+        cf_offsets(c, o1, o2, f2);
+        const uint32_t h = cf_hash(c), fp = cf_fp(h);
+        form_mismatch += o1 != 4u * cf_bucket(h) || o2 != 4u * cf_alt(cf_bucket(h), fp) || f2 != fp * 0x00010001u ||
+                         (fp & 0x4000u) != 0 || (fp & 1u) == 0 || fp > 0xFFFFu;
+    }
     uint64_t used = 0;
     for (uint32_t w : tab) used += ((w & 0xFFFF) != 0) + ((w >> 16) != 0);
     uint64_t fp = 0, probes = 0;
@@ -40,7 +50,7 @@ int main(int argc, char **argv)
         probes++;
         fp += cf_lookup(tab.data(), c);
     }
-    printf("{\"distinct\": %zu, \"slots_used\": %llu, \"insert_failures\": %d, \"missing\": %d, \"false_positive_rate\": %.3g}\n",
-           members.size(), (unsigned long long)used, failed, missing, probes ? (double)fp / probes : 0.0);
-    return (missing == 0 && (failed == 0)) ? 0 : 1;
+    printf("{\"distinct\": %zu, \"slots_used\": %llu, \"insert_failures\": %d, \"missing\": %d, \"form_mismatch\": %d, \"false_positive_rate\": %.3g}\n",
+           members.size(), (unsigned long long)used, failed, missing, form_mismatch, probes ? (double)fp / probes : 0.0);
+    return (missing == 0 && failed == 0 && form_mismatch == 0) ? 0 : 1;
 }
