@@ -31,7 +31,46 @@ __device__ __forceinline__ void binom_pmf_scaled(uint64_t x, double r, uint64_t 
     expo = e;
 }
 
-__device__ __forceinline__ double binomial_upper_tail(uint64_t x, double r, uint64_t n)
+// Table of C(n0, x), x = 0..n0, as mant * 2^expo, built on the host in long double (dist.cu: n0 = the job's sketch size,
+// which is the denominator of almost every pair).  With it the first term costs a 2 log2(x)-step power instead of x
+// multiply-divide steps -- the p-value of a pair with many shared hashes used to cost more than its merge.
+struct BinomTable { const double *mant; const int *expo; uint64_t n0; };
+
+// r^x as mant * 2^expo by binary exponentiation on frexp-normalised factors (relative error <= ~x ulp, as the running product)
+__device__ __forceinline__ void pow_scaled(double r, uint64_t x, double &mant, int &expo)
+{
+    int er;
+    double base = frexp(r, &er);        // r = base * 2^er, base in [0.5, 1)
+    int ebase = 0, eacc = 0, k;
+    double acc = 1.0;
+    const long long e_lin = (long long)er * (long long)x;
+    while (x) {
+        if (x & 1) { acc = frexp(acc * base, &k); eacc += ebase + k; }
+        x >>= 1;
+        if (x) { base = frexp(base * base, &k); ebase = 2 * ebase + k; }
+    }
+    const long long e = e_lin + eacc;
+    mant = acc;
+    expo = e < -1000000 ? -1000000 : (int)e;
+}
+
+// same quantity as binom_pmf_scaled, C(n,x) taken from the table (requires n == tab.n0)
+__device__ __forceinline__ void binom_pmf_scaled_tab(uint64_t x, double r, uint64_t n, const BinomTable &tab, double &mant, int &expo)
+{
+    double pm; int pe;
+    pow_scaled(r, x, pm, pe);
+    double m = tab.mant[x] * pm;
+    int e = tab.expo[x] + pe;
+    const double base = (double)(n - x);
+    const double y = base * log1p(-r) * 1.4426950408889634074;   // 1/ln 2
+    const double yi = floor(y);
+    m *= exp2(y - yi);
+    e += (int)fmax(yi, -100000.0);
+    mant = m;
+    expo = e;
+}
+
+__device__ __forceinline__ double binomial_upper_tail(uint64_t x, double r, uint64_t n, const BinomTable *tab = nullptr)
 {
     if (x == 0) return 1.0;
     if (x > n) return 0.0;
@@ -40,7 +79,8 @@ __device__ __forceinline__ double binomial_upper_tail(uint64_t x, double r, uint
     const double odds = r / (1.0 - r);
     if ((double)x >= ((double)n + 1.0) * r) {
         double m; int e;
-        binom_pmf_scaled(x, r, n, m, e);
+        if (tab && tab->mant && n == tab->n0) binom_pmf_scaled_tab(x, r, n, *tab, m, e);
+        else binom_pmf_scaled(x, r, n, m, e);
         double sum = 1.0, t = 1.0;
         for (uint64_t i = x; i < n; i++) {
             t *= ((double)(n - i) / (double)(i + 1)) * odds;
@@ -63,13 +103,14 @@ __device__ __forceinline__ double binomial_upper_tail(uint64_t x, double r, uint
 }
 
 // pValue, reference CommandDistance.cpp:427-448
-__device__ __forceinline__ double mash_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t sketch_size)
+__device__ __forceinline__ double mash_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t sketch_size,
+                                              const BinomTable *tab = nullptr)
 {
     if (x == 0) return 1.0;
     const double pX = 1. / (1. + kmer_space / (double)len_ref);
     const double pY = 1. / (1. + kmer_space / (double)len_qry);
     const double r = pX * pY / (pX + pY - pX * pY);
-    return binomial_upper_tail(x, r, sketch_size);
+    return binomial_upper_tail(x, r, sketch_size, tab);
 }
 
 }  // namespace mashgpu

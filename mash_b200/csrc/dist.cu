@@ -47,6 +47,7 @@ struct DistArgs {
     int kmer_size;
     double kmer_space, max_distance, max_pvalue;
     const double *dist_lut;     // distance for (common, denom == S), S+1 entries
+    BinomTable binom;           // C(S, x) for the p-value of pairs with denom == S
     uint32_t *numer; uint32_t *denom; double *distance; double *pvalue; uint8_t *pass;   // outputs, (q - q_begin) * n_ref + r
     // compacted pass-list (filtered runs): passing pairs are appended in arbitrary order, then sorted by pair index
     uint64_t *list_idx; uint32_t *list_numer; uint32_t *list_denom; double *list_distance; double *list_pvalue;
@@ -110,7 +111,7 @@ __device__ __forceinline__ void dist_emit(const DistArgs &a, uint32_t q, uint32_
             }
         }
         if (!deferred) {
-            p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom);
+            p = mash_pvalue(common, lenA, a.qry_len[q], a.kmer_space, denom, &a.binom);
             if (a.max_pvalue >= 0 && p > a.max_pvalue) pass = false;    // :419-422
         }
     }
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) dist_fix_kernel(const DistArgs a)
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         const FixEntry e = a.fix_list[t];
         const uint32_t q = a.q_begin + (uint32_t)(e.o / a.n_ref), r = (uint32_t)(e.o % a.n_ref);
-        const double p = mash_pvalue(e.common, a.ref_len[r], a.qry_len[q], a.kmer_space, e.denom);
+        const double p = mash_pvalue(e.common, a.ref_len[r], a.qry_len[q], a.kmer_space, e.denom, &a.binom);
         const bool pass = !(a.max_pvalue >= 0 && p > a.max_pvalue);
         if (a.list_idx && pass) {
             const double dist = (e.denom == a.S) ? a.dist_lut[e.common] : mash_distance(e.common, e.denom, a.kmer_size);
@@ -448,7 +449,8 @@ struct mashgpu_dist_job {
     uint32_t P = 0;
     DevBuf<uint32_t> ranks, n_eff;
     DevBuf<uint64_t> lens;          // ref lengths then query lengths
-    DevBuf<double> lut;
+    DevBuf<double> lut, binom_m;
+    DevBuf<int> binom_e;
     bool tiled = true;
     // pass-list target of the next run (set by mashgpu_dist_run_list only)
     uint64_t *list_idx = nullptr; uint32_t *list_numer = nullptr, *list_denom = nullptr; double *list_distance = nullptr, *list_pvalue = nullptr;
@@ -564,6 +566,25 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
             lut[c] = d;
         }
         MG_CUDA(ctx, cudaMemcpyAsync(job->lut.p, lut.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+        // C(S, x) as mant * 2^expo for the device binomial tail (binom.cuh), running product in long double
+        std::vector<double> bm(S + 1);
+        std::vector<int> be(S + 1);
+        {
+            long double m = 1.0L;
+            int e = 0;
+            bm[0] = 1.0; be[0] = 0;
+            for (uint64_t x = 1; x <= S; x++) {
+                m *= (long double)(S - x + 1) / (long double)x;
+                int k;
+                m = frexpl(m, &k);
+                e += k;
+                bm[x] = (double)m; be[x] = e;
+            }
+        }
+        if (job->binom_m.alloc(S + 1) != cudaSuccess || job->binom_e.alloc(S + 1) != cudaSuccess)
+            return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (binomial table)"));
+        MG_CUDA(ctx, cudaMemcpyAsync(job->binom_m.p, bm.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+        MG_CUDA(ctx, cudaMemcpyAsync(job->binom_e.p, be.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
         cudaError_t es = cudaStreamSynchronize(st);
         if (es != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(es)));
     }
@@ -634,6 +655,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.kmer_size = job->params.kmer_size; a.kmer_space = job->params.kmer_space;
     a.max_distance = job->params.max_distance; a.max_pvalue = job->params.max_pvalue;
     a.dist_lut = job->lut.p;
+    a.binom.mant = job->binom_m.p; a.binom.expo = job->binom_e.p; a.binom.n0 = job->params.sketch_size;
     a.numer = d_numer; a.denom = d_denom; a.distance = d_distance; a.pvalue = d_pvalue; a.pass = d_pass;
     a.list_idx = job->list_idx; a.list_numer = job->list_numer; a.list_denom = job->list_denom; a.list_distance = job->list_distance;
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
