@@ -161,6 +161,12 @@ int mashgpu_dist_run_list(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_co
                           uint64_t *pair_index, uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint64_t *n_pass);
 int mashgpu_dist_close(mashgpu_dist_job *job);
 
+/* Lower-triangular enumeration for a self comparison (qry == NULL): `mash triangle` compares row i with rows 0..i-1 only
+ * (CommandTriangle.cpp:200-214).  on != 0: pairs with r >= q are neither computed nor written and never enter a pass list;
+ * whole reference tiles above the diagonal are skipped.  Their output slots are zero with mashgpu_dist_run (host buffers)
+ * and keep whatever they held with mashgpu_dist_run_dev (device buffers). */
+int mashgpu_dist_set_triangle(mashgpu_dist_job *job, int on);
+
 /* Tile prefilter of the merge (no counterpart in the reference, which merges every pair, CommandDistance.cpp:347-365;
  * the results are identical).  Before a tile of 32 references is merged with a query, the query's hashes are looked up in
  * a filter built over the tile's hashes; a query that shares no hash with any of the 32 references gets the closed form

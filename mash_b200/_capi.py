@@ -91,6 +91,7 @@ def load_library():
     L.mashgpu_dist_run_list.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u32p, u32p, f64p, f64p, u64p]
     L.mashgpu_dist_close.argtypes = [C.c_void_p]
     L.mashgpu_dist_set_prefilter.argtypes = [C.c_void_p, C.c_int]
+    L.mashgpu_dist_set_triangle.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_dist_prefilter_stats.argtypes = [C.c_void_p, u64p, u64p, C.POINTER(C.c_int)]
     L.mashgpu_dist.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), u32p, u32p, f64p, f64p, u8p]
     L.mashgpu_screen_open.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.POINTER(SketchSet), C.POINTER(C.c_void_p)]
@@ -274,6 +275,10 @@ class DistJob:
     def set_prefilter(self, mode):
         """-1 = auto (default), 0 = merge every pair, 1 = always probe the reference tiles first."""
         self.eng._check(self.eng.lib.mashgpu_dist_set_prefilter(self.h, int(mode)))
+
+    def set_triangle(self, on=True):
+        """Self comparison, lower triangle only (pairs with r >= q are not computed or written)."""
+        self.eng._check(self.eng.lib.mashgpu_dist_set_triangle(self.h, int(on)))
 
     def prefilter_stats(self):
         probed = C.c_uint64(0); flagged = C.c_uint64(0); active = C.c_int(0)

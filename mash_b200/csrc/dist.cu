@@ -55,6 +55,7 @@ struct DistArgs {
     // prefilter work lists (dist_probe_kernel -> dist_kernel): per reference tile the queries that share a hash with it
     uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
     int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
+    int triangle;               // self comparison, lower triangle only: pairs with r >= q are neither computed nor written
     // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
     struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
 };
@@ -173,18 +174,24 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
     for (uint64_t it_lo = (uint64_t)blockIdx.y * a.q_per_cta; it_lo < n_items; it_lo += (uint64_t)gridDim.y * a.q_per_cta) {
     const uint32_t it_hi = (uint32_t)min((uint64_t)n_items, it_lo + a.q_per_cta);
     for (uint32_t ib = (uint32_t)it_lo + warp * DIST_ILP; ib < it_hi; ib += DIST_WARPS * DIST_ILP) {
-        // load DIST_ILP query rows (coalesced) into this warp's buffers
         uint32_t qs[DIST_ILP];
+        bool all_skipped = true;
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
             const uint32_t item = ib + c;
+            qs[c] = item < it_hi ? (my_list ? my_list[item] : a.q_begin + item) : 0xFFFFFFFFu;
+            if (a.triangle && qs[c] <= r0) qs[c] = 0xFFFFFFFFu;        // the whole tile lies on or above the diagonal
+            all_skipped &= qs[c] == 0xFFFFFFFFu;
+        }
+        if (all_skipped) continue;                      // warp-uniform
+        // load DIST_ILP query rows (coalesced) into this warp's buffers
+#pragma unroll
+        for (int c = 0; c < DIST_ILP; c++) {
             uint32_t *dst = my_q + (size_t)c * a.P;
-            if (item < it_hi) {
-                qs[c] = my_list ? my_list[item] : a.q_begin + item;
+            if (qs[c] != 0xFFFFFFFFu) {
                 const uint32_t *row = a.ranks + (a.qry_row0 + qs[c]) * (uint64_t)a.P;
                 for (uint32_t i = lane; i < a.P; i += 32) dst[i] = row[i];
             } else {
-                qs[c] = 0xFFFFFFFFu;
                 for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
             }
         }
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
             const uint32_t q = qs[c];
-            if (q == 0xFFFFFFFFu || !r_ok) continue;
+            if (q == 0xFFFFFFFFu || !r_ok || (a.triangle && r >= q)) continue;
             const uint32_t i_end = (pa[c] - sref_base) / (DIST_TILE_R * 4);
             const uint32_t j_end = (pb[c] - pb0[c]) / 4;
             const uint32_t bogus = i_end > nA ? i_end - nA : 0;   // steps that consumed padding on both sides
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     const uint8_t pass_const = (far || (a.max_pvalue >= 0 && 1.0 > a.max_pvalue)) ? 0 : 1;
 
     for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
+        if (a.triangle && q <= r0) continue;            // the whole tile lies on or above the diagonal
         const uint32_t nB_all = a.qry_n[q];
         const uint32_t nB = min(nB_all, a.S);
         const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
                 a.qlist[(uint64_t)blockIdx.x * a.qlist_stride + at] = q;
                 atomicAdd(a.flag_total, 1ull);
             }
-        } else if (r_ok) {
+        } else if (r_ok && !(a.triangle && r >= q)) {
             // empty intersection: the merge would take min(s', |A| + |B|) union steps and count nothing
             const uint32_t denom = min(a.S, nA + nB_all);
             if (denom == a.S && !a.list_idx) {
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
     const uint64_t total = (uint64_t)a.q_count * a.n_ref;
     if (t >= total) return;
     const uint32_t q = a.q_begin + (uint32_t)(t / a.n_ref), r = (uint32_t)(t % a.n_ref);
+    if (a.triangle && r >= q) return;
     const uint32_t *A = a.ranks + (a.ref_row0 + r) * (uint64_t)a.P;
     const uint32_t *B = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
     uint32_t i = 0, j = 0;
@@ -457,6 +466,7 @@ struct mashgpu_dist_job {
     unsigned long long *list_count = nullptr; uint64_t list_capacity = 0;
     // prefilter (dist_probe_kernel): -1 = auto (on; switched off when most combinations turn out to share hashes), 0 = off, 1 = on
     int prefilter_mode = -1;
+    bool triangle = false;
     bool auto_off = false;
     DevBuf<uint32_t> qlist, qcount;
     DevBuf<FixEntry> fix_list;
@@ -608,6 +618,14 @@ extern "C" int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode)
     return MASHGPU_OK;
 }
 
+extern "C" int mashgpu_dist_set_triangle(mashgpu_dist_job *job, int on)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    if (on && !job->self) return fail(job->ctx, MASHGPU_ERR_INVALID, "triangle enumeration needs a self comparison (qry == NULL)");
+    job->triangle = on != 0;
+    return MASHGPU_OK;
+}
+
 // auto mode: looks at the last snapshot of the flagged-combination counter, if it has arrived.  When most (query, tile)
 // combinations share hashes the probe is pure overhead -- merge everything from then on.
 static void dist_collect_flags(mashgpu_dist_job *job)
@@ -660,6 +678,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.list_idx = job->list_idx; a.list_numer = job->list_numer; a.list_denom = job->list_denom; a.list_distance = job->list_distance;
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
+    a.triangle = job->triangle ? 1 : 0;
     {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
         const uint64_t pairs = q_count * job->n_ref;
         const uint64_t cap = std::min<uint64_t>(pairs, std::max<uint64_t>(1ull << 20, pairs / 16));
@@ -771,6 +790,14 @@ extern "C" int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_
     cudaStream_t st = ctx->stream;
     for (uint64_t q = 0; q < q_count; q += q_chunk) {
         const uint64_t qc = std::min(q_chunk, q_count - q);
+        if (job->triangle) {        // pairs on or above the diagonal are not written by the kernels: hand zeros back for them
+            const uint64_t np0 = qc * n_ref;
+            if (numer) MG_CUDA(ctx, cudaMemsetAsync(dn.p, 0, np0 * 4, st));
+            if (denom) MG_CUDA(ctx, cudaMemsetAsync(dd.p, 0, np0 * 4, st));
+            if (distance) MG_CUDA(ctx, cudaMemsetAsync(dD.p, 0, np0 * 8, st));
+            if (pvalue) MG_CUDA(ctx, cudaMemsetAsync(dP.p, 0, np0 * 8, st));
+            if (pass) MG_CUDA(ctx, cudaMemsetAsync(dpass.p, 0, np0, st));
+        }
         MG_TRY(mashgpu_dist_run_dev(job, q_begin + q, qc, numer ? dn.p : nullptr, denom ? dd.p : nullptr, distance ? dD.p : nullptr,
                                     pvalue ? dP.p : nullptr, pass ? dpass.p : nullptr, st));
         const uint64_t np = qc * n_ref, o = q * n_ref;

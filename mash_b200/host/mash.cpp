@@ -423,6 +423,7 @@ int runTriangle(int argc, const char **argv)
         sketch.toSketchSet(set, h, nn, l);
         mashgpu_dist_job *job = 0;
         if (mashgpu_dist_open(gpuContext(), &set, 0, &dp, &job) != MASHGPU_OK) gpuFail();
+        if (mashgpu_dist_set_triangle(job, 1) != MASHGPU_OK) gpuFail();     // only j < i is read below
         uint64_t rows = std::max<uint64_t>(1, (1ull << 24) / n);
         PairBlock out;
         out.resize(std::min(rows, n) * n);

@@ -114,3 +114,42 @@ def test_auto_mode_switches_off_on_dense_sets(gpu):
             assert np.array_equal(first[key], second[key])
     finally:
         job.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_triangle_enumeration(gpu, mode):
+    # `mash triangle` (CommandTriangle.cpp:200-214): row i against rows 0..i-1 -- pairs on or above the diagonal are not
+    # computed; the lower triangle equals the full grid's
+    s, k = 300, 21
+    H, N, L = mixed_sketches(210, s, seed=41)
+    job = gpu.dist_open(H, N, L, sketch_size=s, k=k, kmer_space=4.0 ** k, max_distance=0.3, max_pvalue=1.0)
+    try:
+        job.set_prefilter(mode)
+        full = job.run(0, 210)
+        n_full, lst_full = job.run_list(0, 210, 210 * 210)
+        job.set_triangle(True)
+        tri = job.run(0, 210)            # host buffers start zeroed (see _capi.DistJob.run)
+        n_tri, lst_tri = job.run_list(0, 210, 210 * 210)
+        part = job.run(100, 60)
+    finally:
+        job.close()
+    q, r = np.indices((210, 210))
+    low = r < q
+    for key in KEYS:
+        assert np.array_equal(tri[key][low], full[key][low]), key
+        assert np.array_equal(part[key][low[100:160]], full[key][100:160][low[100:160]]), key
+    assert not tri["numer"][~low].any() and not tri["pass"][~low].any()      # untouched
+    keep = low.ravel()[lst_full["index"].astype(np.int64)]
+    assert n_tri == int(keep.sum()) and np.array_equal(lst_tri["index"], lst_full["index"][keep])
+    for key in ("numer", "denom", "distance", "pvalue"):
+        assert np.array_equal(lst_tri[key], lst_full[key][keep])
+
+
+def test_triangle_needs_self_comparison(gpu):
+    H, N, L = mixed_sketches(40, 100, seed=5)
+    job = gpu.dist_open(H, N, L, H[:7], N[:7], L[:7], sketch_size=100, k=21, kmer_space=4.0 ** 21)
+    try:
+        with pytest.raises(Exception):
+            job.set_triangle(True)
+    finally:
+        job.close()
