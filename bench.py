@@ -472,6 +472,17 @@ def main():
             job.set_prefilter(0)
             side["first_query_tile_merge_every_pair"] = one_tile_rate(job)
             job.set_prefilter(-1)
+        tri = None
+        if world == 1:
+            # `mash triangle` enumeration of the same set (BASELINE configs[2] quotes it: n(n-1)/2 ~ 5e9 unordered pairs)
+            job.set_triangle(True)
+            dist_step(); torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(st); dist_step(); a1.record(st); torch.cuda.synchronize()
+            tri_pairs = n_ref * (n_ref - 1) // 2
+            tri = {"enumeration": "lower triangle, row i vs rows 0..i-1 (CommandTriangle.cpp:200-214)", "pairs": tri_pairs,
+                   "ms": a0.elapsed_time(a1), "pairs_per_s": tri_pairs / (a0.elapsed_time(a1) * 1e-3)}
+            job.set_triangle(False)
         dist_obj = {"metric": "sketch_pairs_per_s", "value": total_pairs / (dms * 1e-3), "unit": "pairs/s", "ms_per_step": dms,
                     "steps": dK, "warmup": dW, "pairs_per_step": total_pairs, "enumeration": "all ordered pairs (full Q x R grid)",
                     "workload": f"configs[2]: {n_sk} synthetic s={S} sketches all-vs-all, 100 families stored family by family (SURVEY.md 8d generator); "
@@ -504,6 +515,7 @@ def main():
             side["note"] = ("pairs/s of rank 0 on one query tile of its own shard (self comparison), outside the timed region; 'merge_every_pair' = prefilter off "
                             "(the reference's algorithm for every pair)")
         dist_obj["side_measurements"] = side
+        dist_obj["triangle"] = tri
 
         # ---------------- hot path 3: screen (configs[3], rank 0's sketches as the reference .msh) -----------------
         if not args.skip_screen:
