@@ -55,6 +55,7 @@ struct DistArgs {
     // prefilter work lists (dist_probe_kernel -> dist_kernel): per reference tile the queries that share a hash with it
     uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
     int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
+    int probe_prefetch;         // dist_probe_kernel: request the query lines two groups ahead into L1
     int triangle;               // self comparison, lower triangle only: pairs with r >= q are neither computed nor written
     // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
     struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
@@ -258,21 +259,16 @@ constexpr int PROBE_DEPTH = 4;          // 32-rank batches in flight per warp
 
 // One group of PROBE_DEPTH x 32 ranks of a query against the filter.  FULL: the whole group lies inside the query's list.
 // Returns true when a rank is confirmed to be in one of the tile's references.
-template <bool FULL>
-__device__ __forceinline__ bool probe_group(const uint32_t *s_tab, const uint32_t *rowB, uint32_t base, uint32_t nB, int lane,
+template <bool FULL, bool LAZY>
+__device__ __forceinline__ bool probe_group(const uint32_t *s_tab, uint32_t tab_s, const uint32_t (&b)[PROBE_DEPTH], uint32_t base, uint32_t nB, int lane,
                                             const uint32_t *rowA, uint32_t nA_lim)
 {
+    // b[c] = rank base + 32 c + lane of the query (RANK_PAD past the end of its list)
     static_assert(PROBE_DEPTH == 4, "cf_group_any takes four probes");
-    uint32_t b[PROBE_DEPTH];
     CfProbe pr[PROBE_DEPTH];
 #pragma unroll
     for (int c = 0; c < PROBE_DEPTH; c++) {
-        const uint32_t j = base + 32 * c + lane;
-        b[c] = (FULL || j < nB) ? __ldg(rowB + j) : RANK_PAD;
-    }
-#pragma unroll
-    for (int c = 0; c < PROBE_DEPTH; c++) {
-        pr[c] = cf_fetch(s_tab, b[c]);
+        pr[c] = cf_fetch_s<LAZY>(tab_s, b[c]);
         if (!FULL && base + 32 * c + lane >= nB) pr[c].f2 = 0x7E007E00u;       // past the end of the list: never matches
     }
     if (!cf_group_any(pr[0], pr[1], pr[2], pr[3])) return false;
@@ -301,6 +297,7 @@ __device__ __forceinline__ bool probe_group(const uint32_t *s_tab, const uint32_
     return confirmed;
 }
 
+template <bool LAZY>
 __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const DistArgs a)
 {
     extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words
@@ -323,6 +320,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
             if (!cf_insert(s_tab, row[i], threadIdx.x * 2654435761u + i)) s_fail = 1;
     }
     __syncthreads();
+    const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(s_tab);
     const bool tile_failed = s_fail != 0;       // filter overflow (cannot happen at <= 32 x 1035 ranks): merge everything
 
     const uint32_t r = r0 + lane;
@@ -344,10 +342,25 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
         const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
         bool confirmed = tile_failed;
         uint32_t base = 0;
-        for (; base + 32 * PROBE_DEPTH <= nB && !confirmed; base += 32 * PROBE_DEPTH)
-            confirmed = probe_group<true>(s_tab, rowB, base, nB, lane, rowA, nA_lim);
-        for (; base < nB && !confirmed; base += 32 * PROBE_DEPTH)
-            confirmed = probe_group<false>(s_tab, rowB, base, nB, lane, rowA, nA_lim);
+        const uint32_t *pB = rowB + lane;
+        constexpr uint32_t GROUP = 32 * PROBE_DEPTH;
+        // full groups; the lines of the group after next are requested into L1 first (one prefetch instruction, lanes 0-3
+        // name the four 128-byte lines): 8 warps per sub-partition do not cover the L2 latency on their own (ncu r01:
+        // long_scoreboard 5.8 per issue, issue active 67 %).  ptxas sinks register prefetches to the end of the body.
+        uint32_t cur[PROBE_DEPTH];
+        if (a.probe_prefetch && 2 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + GROUP + 32 * (lane & 3)));
+        while (base + GROUP <= nB && !confirmed) {
+            if (a.probe_prefetch && base + 3 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + base + 2 * GROUP + 32 * (lane & 3)));
+#pragma unroll
+            for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = __ldg(pB + 32 * c);
+            confirmed = probe_group<true, LAZY>(s_tab, tab_s, cur, base, nB, lane, rowA, nA_lim);
+            base += GROUP; pB += GROUP;
+        }
+        if (base < nB && !confirmed) {      // ragged last group
+#pragma unroll
+            for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = (base + 32 * c + lane < nB) ? __ldg(pB + 32 * c) : RANK_PAD;
+            confirmed = probe_group<false, LAZY>(s_tab, tab_s, cur, base, nB, lane, rowA, nA_lim);
+        }
         if (confirmed) {
             if (lane == 0) {
                 const uint32_t at = atomicAdd(&a.qcount[blockIdx.x], 1u);
@@ -467,6 +480,8 @@ struct mashgpu_dist_job {
     // prefilter (dist_probe_kernel): -1 = auto (on; switched off when most combinations turn out to share hashes), 0 = off, 1 = on
     int prefilter_mode = -1;
     bool triangle = false;
+    bool probe_prefetch = true;         // MASHGPU_PROBE_PREFETCH=0 to compare
+    bool lazy_second = true;            // probe kernel: load the second bucket only where the first one is full (MASHGPU_CF_LAZY=0 to compare)
     bool auto_off = false;
     DevBuf<uint32_t> qlist, qcount;
     DevBuf<FixEntry> fix_list;
@@ -601,10 +616,13 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     if (!ctx->attr_dist) {   // per context: function attributes are per device
         cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
-        e = cudaFuncSetAttribute(dist_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        e = cudaFuncSetAttribute(dist_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
         ctx->attr_dist = true;
     }
+    if (const char *env = getenv("MASHGPU_CF_LAZY")) job->lazy_second = atoi(env) != 0;
+    if (const char *env = getenv("MASHGPU_PROBE_PREFETCH")) job->probe_prefetch = atoi(env) != 0;
     if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
     *job_out = job;
     return MASHGPU_OK;
@@ -679,6 +697,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
     a.triangle = job->triangle ? 1 : 0;
+    a.probe_prefetch = job->probe_prefetch ? 1 : 0;
     {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
         const uint64_t pairs = q_count * job->n_ref;
         const uint64_t cap = std::min<uint64_t>(pairs, std::max<uint64_t>(1ull << 20, pairs / 16));
@@ -729,7 +748,8 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         p_slices = (uint32_t)((q_count + p_per_cta - 1) / p_per_cta);
         a.q_per_cta = p_per_cta;
         time_begin(ctx, ctx->dist_events, st);
-        dist_probe_kernel<<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
+        if (job->lazy_second) dist_probe_kernel<true><<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
+        else dist_probe_kernel<false><<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
         time_end(ctx, ctx->dist_events, st);
         MG_CUDA(ctx, cudaGetLastError());
         // merge the listed combinations: a few CTAs per tile walk its list (CTAs of tiles with short lists exit at once)

@@ -21,7 +21,7 @@ o_n = torch.empty(np_, dtype=torch.int32, device=dev); o_d = torch.empty(np_, dt
 o_D = torch.empty(np_, dtype=torch.float64, device=dev); o_p = torch.empty(np_, dtype=torch.float64, device=dev)
 o_x = torch.empty(np_, dtype=torch.uint8, device=dev)
 results = {}
-for order in ("family_contiguous", "shuffled"):
+for order in os.environ.get("ORDERS", "family_contiguous,shuffled").split(","):
     Hs, Ls = (H, L) if order == "family_contiguous" else (H[perm].contiguous(), L[perm].contiguous())
     ref = mash_b200._capi._Set(Hs.data_ptr(), N.data_ptr(), Ls.data_ptr(), on_device=True, n=n, stride=S)
     job = mash_b200._capi.DistJob(eng, ref, None, None, None, None, None, S, K, ks, 1.0, 1.0)
@@ -50,4 +50,4 @@ for order in ("family_contiguous", "shuffled"):
     del keep
     job.close()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(results, open("gpurun_out/dist_prefilter_probe.json", "w"), indent=1)
+json.dump(results, open(os.environ.get("PROBE_OUT", "gpurun_out/dist_prefilter_probe.json"), "w"), indent=1)
