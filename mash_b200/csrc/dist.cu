@@ -481,7 +481,9 @@ struct mashgpu_dist_job {
     int prefilter_mode = -1;
     bool triangle = false;
     bool probe_prefetch = true;         // MASHGPU_PROBE_PREFETCH=0 to compare
-    bool lazy_second = true;            // probe kernel: load the second bucket only where the first one is full (MASHGPU_CF_LAZY=0 to compare)
+    bool lazy_second = false;           // probe kernel: load the second bucket only where the first one is full (MASHGPU_CF_LAZY=1).
+                                        // Measured on configs[2], first query tile (B200): off/prefetch 20.9 ms, on/prefetch 21.8, off/no
+                                        // prefetch 22.4, on/no prefetch 23.2 -- the predicate logic costs more than the LDS wavefronts saved
     bool auto_off = false;
     DevBuf<uint32_t> qlist, qcount;
     DevBuf<FixEntry> fix_list;
