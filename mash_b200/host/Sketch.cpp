@@ -13,6 +13,7 @@
 #include <fstream>
 #include <iostream>
 #include <list>
+#include <thread>
 
 #include "capnp_lite.hpp"
 #include "fastx.hpp"
@@ -296,7 +297,38 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
                 if (test == NULL) { cerr << "ERROR: could not open " << files[i] << " for reading." << endl; exit(1); }
                 fclose(test);
             }
-            if (parameters.concatenated) {
+            if (parameters.concatenated && parameters.parallelism > 1 && files[i] != "-") {
+                // -p N: the reference parses N files at a time, one ThreadPool job each (Sketch.cpp:202-212), and takes the
+                // outputs in submission order.  Same here for the host-side parse of a run of sequence files: N threads
+                // parse one file each into private buffers, appended to the batch in input order.
+                size_t run = 1;
+                while (i + run < files.size() && run < (size_t)parameters.parallelism && !hasSuffix(files[i + run], suffixSketch) && files[i + run] != "-") run++;
+                struct Parsed { Reference ref; vector<string> seqs; vector<uint32_t> unitOfRecord; uint64_t bytes = 0; };
+                vector<Parsed> parsed(run);
+                vector<std::thread> workers;
+                for (size_t t = 0; t < run; t++) {
+                    if (t > 0) {
+                        if (verbosity > 0) cerr << "Sketching " << files[i + t] << "..." << endl;
+                        FILE *test = fopen(files[i + t].c_str(), "r");
+                        if (test == NULL) { cerr << "ERROR: could not open " << files[i + t] << " for reading." << endl; exit(1); }
+                        fclose(test);
+                    }
+                    workers.emplace_back([&, t]() {
+                        vector<string> file(1, files[i + t]);
+                        parseUnit(file, parameters, parsed[t].ref, parsed[t].seqs, parsed[t].unitOfRecord, 0, parsed[t].bytes);
+                    });
+                }
+                for (auto &w : workers) w.join();
+                for (size_t t = 0; t < run; t++) {
+                    const uint32_t unit = (uint32_t)batch.refs.size();
+                    batch.refs.push_back(std::move(parsed[t].ref));
+                    for (auto &q : parsed[t].seqs) batch.seqs.push_back(std::move(q));
+                    batch.unitOfRecord.insert(batch.unitOfRecord.end(), parsed[t].seqs.size(), unit);
+                    batch.bytes += parsed[t].bytes;
+                    if (batch.bytes > batchBytesMax) flushBatch(batch);
+                }
+                i += run - 1;
+            } else if (parameters.concatenated) {
                 vector<string> file(1, files[i]);
                 batch.refs.emplace_back();
                 parseUnit(file, parameters, batch.refs.back(), batch.seqs, batch.unitOfRecord, (uint32_t)batch.refs.size() - 1, batch.bytes);

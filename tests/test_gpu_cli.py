@@ -115,3 +115,15 @@ def test_filtered_dist_uses_pass_list(work):
     full = out(work, "dist", "genomes.msh", "genomes.msh").splitlines()
     want = [l for l in full if float(l.split("\t")[2]) <= 0.01]
     assert got == want and 0 < len(got) < len(full)
+
+
+def test_parallel_parse_keeps_input_order(work):
+    # -p N parses N files at a time (reference Sketch.cpp:202-212: outputs are taken in submission order): same .msh bytes
+    for p in ("2", "3", "8"):
+        subprocess.run([MASH, "sketch", "-p", p, "-o", f"genomes_p{p}.msh", "genome1.fna", "genome2.fna", "genome3.fna", "genome2.fna", "genome1.fna"],
+                       cwd=work, check=True, capture_output=True)
+    subprocess.run([MASH, "sketch", "-o", "genomes_p1.msh", "genome1.fna", "genome2.fna", "genome3.fna", "genome2.fna", "genome1.fna"],
+                   cwd=work, check=True, capture_output=True)
+    want = open(work / "genomes_p1.msh", "rb").read()
+    for p in ("2", "3", "8"):
+        assert open(work / f"genomes_p{p}.msh", "rb").read() == want
