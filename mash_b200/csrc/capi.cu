@@ -55,6 +55,7 @@ extern "C" void mashgpu_destroy(mashgpu_ctx *ctx)
         for (auto &ev : *list) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (int b = 0; b < 2; b++) {
         if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
+        if (ctx->pinned_sep[b]) cudaFreeHost(ctx->pinned_sep[b]);
         if (ctx->wave_copied[b]) cudaEventDestroy(ctx->wave_copied[b]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -60,6 +60,8 @@ struct mashgpu_ctx {
     mashgpu::Scratch sc_start, sc_t, sc_off, sc_log2, sc_flags, sc_maxhash, sc_keys, sc_cnt, sc_tmax, sc_first, sc_last, sc_qtarget, sc_qtstar;
     // mashgpu_sketch_batch: wave stream buffers and outputs
     mashgpu::Scratch sc_wave[2], sc_inval[2], sc_runs[2], sc_out_hashes, sc_out_n, sc_out_counts;
+    mashgpu::Scratch sc_sep[2];
+    void *pinned_sep[2] = {nullptr, nullptr};
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
     cudaEvent_t wave_copied[2] = {nullptr, nullptr};

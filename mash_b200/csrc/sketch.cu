@@ -209,6 +209,13 @@ __global__ void compact_table_kernel(const uint64_t *keys, uint64_t cap, uint64_
 
 // Packed source: expand the host's list of invalid runs into the 1-bit-per-position mask.  One warp per run; runs
 // are disjoint, so interior words are plain stores and only the two edge words need atomics.
+// record separators of the directly copied records of a wave (one launch instead of one 1-byte memset per record)
+__global__ void write_separators_kernel(uint8_t *stream, const uint64_t *offsets, uint32_t n)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) stream[offsets[t]] = 0;
+}
+
 __global__ void apply_runs_kernel(const PackRun *runs, uint64_t n_runs, uint32_t *mask)
 {
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -595,6 +602,7 @@ namespace {
 struct Wave { uint64_t unit_begin, unit_end, rec_begin, rec_end, bytes; };
 
 constexpr uint64_t WAVE_BYTES = 1ull << 31;        // stream bytes per wave
+constexpr uint32_t SEP_LIST_MAX = 1u << 15;        // directly copied records per wave whose separators go through the list
 constexpr uint64_t DIRECT_COPY_MIN = 1ull << 18;   // records at least this long are copied straight from the caller's buffer
 
 }  // namespace
@@ -801,6 +809,14 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         }
         std::vector<uint64_t> &us = wave_unit_start[wi];
         us.assign(w.unit_end - w.unit_begin + 1, 0);
+        // separator offsets of the directly copied records (pinned list -> device -> one kernel); list full: 1-byte memsets
+        if (!ctx->pinned_sep[b]) {
+            if (cudaMallocHost(&ctx->pinned_sep[b], SEP_LIST_MAX * 8) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (separator list)");
+        }
+        uint64_t *h_sep = (uint64_t *)ctx->pinned_sep[b];
+        uint64_t *d_sep = ctx->sc_sep[b].get<uint64_t>(SEP_LIST_MAX);
+        if (!d_sep) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (separator list)");
+        uint32_t n_sep = 0;
         uint64_t off = 0, st_off = 0;
         uint64_t run_dst = 0, run_src = 0, run_len = 0;   // pending staged run
         auto flush_run = [&]() -> cudaError_t {
@@ -816,7 +832,8 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
                 if (len[r] >= DIRECT_COPY_MIN) {
                     MG_CUDA(ctx, flush_run());
                     MG_CUDA(ctx, cudaMemcpyAsync(dst + off, seq[r], len[r], cudaMemcpyHostToDevice, ctx->copy_stream));
-                    MG_CUDA(ctx, cudaMemsetAsync(dst + off + len[r], 0, 1, ctx->copy_stream));
+                    if (n_sep < SEP_LIST_MAX) h_sep[n_sep++] = off + len[r];
+                    else MG_CUDA(ctx, cudaMemsetAsync(dst + off + len[r], 0, 1, ctx->copy_stream));
                 } else {
                     if (!run_len) { run_dst = off; run_src = st_off; }
                     memcpy(staging[b].p + st_off, seq[r], len[r]);
@@ -828,6 +845,12 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
             }
         }
         MG_CUDA(ctx, flush_run());
+        if (n_sep) {
+            MG_CUDA(ctx, cudaMemcpyAsync(d_sep, h_sep, n_sep * 8ull, cudaMemcpyHostToDevice, ctx->copy_stream));
+            write_separators_kernel<<<(n_sep + 255) / 256, 256, 0, ctx->copy_stream>>>(dst, d_sep, n_sep);
+            MG_CUDA(ctx, cudaGetLastError());
+            ctx->kernel_launches++;
+        }
         us[w.unit_end - w.unit_begin] = off;
         MG_CUDA(ctx, cudaEventRecord(copied[b], ctx->copy_stream));
         return MASHGPU_OK;
