@@ -391,6 +391,10 @@ def main():
     dist_obj = None
     screen_obj = None
     if not args.skip_dist:
+        # configs[3] samples its reads from 50 of the configs[1] genomes: keep those genomes and their sketches for the screen step
+        n_src = min(50, n_units)
+        screen_src = stream[: n_src * (glen + 1)].clone()
+        screen_src_hashes = d_hashes[:n_src].clone()
         del stream
         torch.cuda.empty_cache()
         n_sk = args.sketches
@@ -523,12 +527,18 @@ def main():
             torch.cuda.empty_cache()
             n_reads, read_len = args.reads, 150
             span_r = read_len + 1
-            # reads: '*' + 150 bases; half of them drawn as substrings of a synthetic "genome" pool so that the side bottom-s
-            # has real duplicates, all on the device
+            # reads: '*' + 150 bases drawn as substrings of the genome pool (0.5 % substitutions, 0.1 % N), all on the device
             g = torch.Generator(device=dev); g.manual_seed(4242 + rank)
             lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
             chunk_reads = min(n_reads, 2_000_000)
-            pool = lut[torch.randint(0, 4, (50_000_000,), generator=g, device=dev, dtype=torch.uint8).long()]
+            # reads are sampled from rank 0's first 50 genomes (configs[3]); the sketches of those genomes replace the first 50
+            # rows of the reference table, so that the table probe and the hit counters see real hits
+            pool = screen_src
+            if dist_on:
+                td.broadcast(pool, src=0); td.broadcast(screen_src_hashes, src=0)
+            QH = QH.clone(); QL = QL.clone()
+            QH[:n_src] = screen_src_hashes
+            QL[:n_src] = glen
             idx = torch.arange(read_len, device=dev)[None, :]
             # the reference table is replicated: every rank screens its reads against ALL sketches (QH = the gathered set)
             sset = mash_b200._capi._Set(QH.data_ptr(), QN.data_ptr(), QL.data_ptr(), on_device=True, n=QH.shape[0], stride=S)
@@ -569,7 +579,9 @@ def main():
                                       f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads per rank (one chunk re-fed; inputs in HBM); "
                                       f"{'counters all-reduced over NCCL + mixtures merged, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"], "gpu_launches": int(sstats["kernel_launches"]),
-                          "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum())}
+                          "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()),
+                          "source_genomes": n_src, "median_multiplicity_of_hit_references": float(np.median(res["median"][res["shared"] > 0])) if (res["shared"] > 0).any() else 0.0,
+                          "mean_identity_of_source_genomes": float(np.mean(res["identity"][:n_src]))}
         else:
             screen_obj = None
 
