@@ -555,6 +555,7 @@ def main():
                 v[:, 1:] = body
 
             make_chunk()
+            torch.cuda.synchronize()          # the chunk is written on torch's stream, the engine reads it on its own
             n_chunks = max(1, n_reads // chunk_reads)
             sjob = mash_b200._capi.ScreenJob(eng, sset, None, p)
             for _ in range(2):
@@ -562,13 +563,18 @@ def main():
             eng.set_timing(True); eng.stats(reset=True)
             barrier()
             t0 = time.perf_counter()
+            feed_ms = []
             for _ in range(n_chunks):
+                tf = time.perf_counter()
                 sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)     # the same device chunk again: the table and mixture logic still run
+                feed_ms.append((time.perf_counter() - tf) * 1e3)          # feed_dev returns after its own stream sync
+            t_fin = time.perf_counter()
             if dist_on:
                 from mash_b200.shard import screen_allreduce
                 screen_allreduce(sjob)                                    # reads sharded over ranks: sum the counters, merge the mixtures
             res = sjob.finish()
             torch.cuda.synchronize()
+            fin_ms = (time.perf_counter() - t_fin) * 1e3
             dt = max_over_ranks(time.perf_counter() - t0)
             sstats = eng.stats(reset=True)
             eng.set_timing(False)
@@ -578,8 +584,9 @@ def main():
                           "workload": f"configs[3]: {QH.shape[0]}-sketch reference table ({int(QN.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
                                       f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads per rank (one chunk re-fed; inputs in HBM); "
                                       f"{'counters all-reduced over NCCL + mixtures merged, ' if dist_on else ''}finish() included",
-                          "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"], "gpu_launches": int(sstats["kernel_launches"]),
-                          "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()),
+                          "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"],
+                          "host_ms": {"feed_first": feed_ms[0], "feed_median": float(np.median(feed_ms)), "feed_max": max(feed_ms), "allreduce_and_finish": fin_ms}, "gpu_launches": int(sstats["kernel_launches"]),
+                          "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()), "exact_reruns": int(sstats["exact_reruns"]),
                           "source_genomes": n_src, "median_multiplicity_of_hit_references": float(np.median(res["median"][res["shared"] > 0])) if (res["shared"] > 0).any() else 0.0,
                           "mean_identity_of_source_genomes": float(np.mean(res["identity"][:n_src]))}
         else:
