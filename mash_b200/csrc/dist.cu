@@ -11,6 +11,13 @@
 //      a <= b -> advance ref;  b <= a -> advance query;   common = i + j - steps.
 // Steps that consume sentinels on both sides are the "list ran out" case of CommandDistance.cpp:367-385 and are
 // subtracted afterwards.
+//
+// A run is three kernels:
+//   dist_probe_kernel  tile prefilter: a cuckoo filter over each 32-reference tile decides which (query, tile) combinations
+//                      share a hash at all; the others get the closed form of an empty intersection for all 32 pairs
+//   dist_kernel        the merge, on the tiles' work lists (or on every pair when the prefilter is off)
+//   dist_fix_kernel    p-value / pass flag / pass-list entry of the pairs with shared hashes, evaluated densely
+// Results are identical with and without the prefilter (tests/test_gpu_dist_prefilter.py).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
