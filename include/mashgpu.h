@@ -203,6 +203,11 @@ int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64
  * mixture_hashes (nullable, sketch_size slots) / mixture_n receive that bottom-s list.  Host buffers. */
 int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, uint64_t *median, double *identity,
                           double *pvalue, uint64_t *set_size, uint64_t *mixture_hashes, uint32_t *mixture_n);
+/* `mash screen -w` ("winner take all", CommandScreen.cpp:357-407): on != 0 makes mashgpu_screen_finish re-assign every
+ * reference hash seen in the mixture to the one sketch, among those containing it, with the highest identity estimate
+ * (ties: the longer genome, refs->length at mashgpu_screen_open; a tie in both goes to the lowest index -- the reference
+ * leaves it to the iteration order of a hash set) before shared / median / identity / p-value are computed. */
+int mashgpu_screen_set_winner(mashgpu_screen_job *job, int on);
 /* Multi-GPU screening (reads sharded over ranks, table replicated): the hit counters live in device memory as one
  * uint32 per distinct reference hash, in ascending hash order, so counter i means the same hash on every rank that
  * opened the job with the same sketches.  *d_counters / *n_counters expose that array for an all-reduce(sum) (NCCL via torch.distributed); the

@@ -101,6 +101,7 @@ def load_library():
     L.mashgpu_screen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), u64p]
     L.mashgpu_screen_merge_mixture.argtypes = [C.c_void_p, u64p, C.c_uint32]
     L.mashgpu_screen_close.argtypes = [C.c_void_p]
+    L.mashgpu_screen_set_winner.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
     _lib = L
@@ -221,8 +222,8 @@ class Engine:
         return DistJob(self, ref, ref_n, ref_len, qry, qry_n, qry_len, sketch_size, k, kmer_space, max_distance, max_pvalue)
 
     # ---- hot path 3 ----------------------------------------------------------------------------------------
-    def screen_open(self, ref, ref_n, p):
-        return ScreenJob(self, ref, ref_n, p)
+    def screen_open(self, ref, ref_n, p, ref_len=None):
+        return ScreenJob(self, ref, ref_n, p, ref_len)
 
     # ---- instrumentation -----------------------------------------------------------------------------------
     def set_timing(self, on=True):
@@ -292,9 +293,9 @@ class DistJob:
 
 
 class ScreenJob:
-    def __init__(self, eng, ref, ref_n, p):
+    def __init__(self, eng, ref, ref_n, p, ref_len=None):
         self.eng = eng
-        self._ref = ref if isinstance(ref, _Set) else _Set(ref, ref_n)
+        self._ref = ref if isinstance(ref, _Set) else _Set(ref, ref_n, ref_len)
         self.n_ref = int(self._ref.c.n)
         self.p = p
         h = C.c_void_p()
@@ -307,6 +308,10 @@ class ScreenJob:
 
     def feed_dev(self, d_ptr, length):
         self.eng._check(self.eng.lib.mashgpu_screen_feed_dev(self.h, d_ptr, length))
+
+    def set_winner(self, on=True):
+        """`mash screen -w`: reallocate every seen reference hash to the best sketch containing it before the reduce."""
+        self.eng._check(self.eng.lib.mashgpu_screen_set_winner(self.h, int(on)))
 
     def counters(self):
         """(device pointer, slot count) of the uint32 hit counters, for an all-reduce across ranks."""

@@ -13,6 +13,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <vector>
+#include <algorithm>
 #include "common.cuh"
 #include "scan.cuh"
 #include "sketch_core.cuh"
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(SCR_THREADS) merge_bottom_s_kernel(uint64_t *m
 __global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
     const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, const uint64_t *keys, const uint32_t *slot_idx, const uint32_t *cnt, uint32_t log2cap,
     uint64_t set_size, int kmer_size, double kmer_space,
-    uint64_t *shared_out, uint64_t *median_out, double *identity_out, double *pvalue_out)
+    uint64_t *shared_out, uint64_t *median_out, double *identity_out, double *pvalue_out,
+    const uint32_t *best, const uint32_t *prio)     // -w: count a hash only for the sketch that won it (best[key] == prio[r])
 {
     extern __shared__ uint32_t depths[];
     __shared__ uint32_t n_s;
@@ -99,7 +102,12 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
         uint32_t slot = slot_hash(key, log2cap), c = 0;
         for (;;) {
             uint64_t k = keys[slot];
-            if (k == key) { c = cnt[slot_idx[slot]]; break; }
+            if (k == key) {
+                const uint32_t d = slot_idx[slot];
+                c = cnt[d];
+                if (best && best[d] != prio[r]) c = 0;        // reallocated to another sketch (CommandScreen.cpp:366-404)
+                break;
+            }
             if (k == EMPTY_KEY) break;
             slot = (slot + 1) & mask;
         }
@@ -134,6 +142,33 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_reduce_kernel(
     }
 }
 
+// `-w`, CommandScreen.cpp:375-404: every reference hash seen in the mixture goes to the containing sketch with the best
+// (identity estimate, genome length) -- prio[r] is the rank of sketch r in that order (0 = best), so the winner of a
+// hash is the minimum prio over the sketches that hold it.
+__global__ void __launch_bounds__(SCR_THREADS) screen_winner_kernel(
+    const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, const uint64_t *keys, const uint32_t *slot_idx, const uint32_t *cnt,
+    uint32_t log2cap, const uint32_t *prio, uint32_t *best)
+{
+    const uint64_t r = blockIdx.x;
+    const uint32_t n = n_hashes[r];
+    const uint32_t mask = (1u << log2cap) - 1;
+    const uint32_t pr = prio[r];
+    for (uint32_t i = threadIdx.x; i < n; i += SCR_THREADS) {
+        const uint64_t key = hashes[r * stride + i];
+        uint32_t slot = slot_hash(key, log2cap);
+        for (;;) {
+            uint64_t k = keys[slot];
+            if (k == key) {
+                const uint32_t d = slot_idx[slot];
+                if (cnt[d] >= 1) atomicMin(&best[d], pr);
+                break;
+            }
+            if (k == EMPTY_KEY) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
 }  // namespace mashgpu
 
 using namespace mashgpu;
@@ -151,6 +186,9 @@ struct mashgpu_screen_job {
     DevBuf<uint64_t> mix, chunk_hashes; DevBuf<uint32_t> mix_n, chunk_n;
     uint32_t h_mix_n = 0; uint64_t h_mix_top = 0;
     DevBuf<uint8_t> stage;   // device staging for host chunks
+    bool winner = false;     // -w
+    std::vector<uint64_t> h_len;      // Reference::length per sketch (tie break of -w), zeros when the caller gave none
+    std::vector<uint32_t> h_n;        // hashes per sketch
 };
 
 extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params *params, const mashgpu_sketch_set *refs,
@@ -223,6 +261,16 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
         if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "screen table build failed: %s", cudaGetErrorString(e)));
     }
     job->hmax = hmax;
+    job->h_n.assign(refs->n, 0); job->h_len.assign(refs->n, 0);
+    if (refs->n) {
+        if (refs->on_device) {
+            MG_CUDA(ctx, cudaMemcpy(job->h_n.data(), refs->n_hashes, refs->n * 4, cudaMemcpyDeviceToHost));
+            if (refs->length) MG_CUDA(ctx, cudaMemcpy(job->h_len.data(), refs->length, refs->n * 8, cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(job->h_n.data(), refs->n_hashes, refs->n * 4);
+            if (refs->length) memcpy(job->h_len.data(), refs->length, refs->n * 8);
+        }
+    }
     if (!ctx->attr_merge) {   // per context: function attributes are per device
         cudaFuncSetAttribute(merge_bottom_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         ctx->attr_merge = true;
@@ -303,9 +351,40 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
         if ((size_t)N * 4 > 48 * 1024)
             MG_CUDA(ctx, cudaFuncSetAttribute(screen_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)N * 4)));
         screen_reduce_kernel<<<(unsigned)n, SCR_THREADS, (size_t)N * 4, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap,
-                                                                            set_size, k, kmer_space, d_shared.p, d_median.p, d_ident.p, d_p.p);
+                                                                            set_size, k, kmer_space, d_shared.p, d_median.p, d_ident.p, d_p.p, nullptr, nullptr);
         ctx->kernel_launches++;
         MG_CUDA(ctx, cudaGetLastError());
+        if (job->winner) {
+            // scores[] = estimateIdentity of the plain shared counts (CommandScreen.cpp:361-364), evaluated with the host libm as
+            // the reference does; order the sketches by (score desc, length desc, index asc) and let every seen hash go to the
+            // best sketch that holds it; then rebuild shared / depths from the assignments (:366-404) with the same reduce kernel
+            std::vector<uint64_t> h_shared(n);
+            MG_CUDA(ctx, cudaMemcpyAsync(h_shared.data(), d_shared.p, n * 8, cudaMemcpyDeviceToHost, st));
+            MG_CUDA(ctx, cudaStreamSynchronize(st));
+            std::vector<double> score(n);
+            for (uint64_t i = 0; i < n; i++) {
+                const uint64_t common = h_shared[i], denom = job->h_n[i];
+                score[i] = common == denom ? 1. : (common == 0 ? 0. : std::pow((double)common / (double)denom, 1. / k));
+            }
+            std::vector<uint32_t> order(n), prio(n);
+            for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                if (score[a] != score[b]) return score[a] > score[b];
+                if (job->h_len[a] != job->h_len[b]) return job->h_len[a] > job->h_len[b];
+                return a < b;
+            });
+            for (uint64_t i = 0; i < n; i++) prio[order[i]] = (uint32_t)i;
+            DevBuf<uint32_t> d_prio, d_best;
+            if (d_prio.alloc(n) != cudaSuccess || d_best.alloc(job->n_distinct) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (winner table)");
+            MG_CUDA(ctx, cudaMemcpyAsync(d_prio.p, prio.data(), n * 4, cudaMemcpyHostToDevice, st));
+            MG_CUDA(ctx, cudaMemsetAsync(d_best.p, 0xFF, std::max<uint64_t>(1, job->n_distinct) * 4, st));
+            screen_winner_kernel<<<(unsigned)n, SCR_THREADS, 0, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, d_prio.p, d_best.p);
+            screen_reduce_kernel<<<(unsigned)n, SCR_THREADS, (size_t)N * 4, st>>>(job->ref_hashes, job->stride, job->ref_n, job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap,
+                                                                                set_size, k, kmer_space, d_shared.p, d_median.p, d_ident.p, d_p.p, d_best.p, d_prio.p);
+            ctx->kernel_launches += 2;
+            MG_CUDA(ctx, cudaGetLastError());
+            MG_CUDA(ctx, cudaStreamSynchronize(st));      // d_prio / d_best go out of scope below
+        }
         if (shared) MG_CUDA(ctx, cudaMemcpyAsync(shared, d_shared.p, n * 8, cudaMemcpyDeviceToHost, st));
         if (median) MG_CUDA(ctx, cudaMemcpyAsync(median, d_median.p, n * 8, cudaMemcpyDeviceToHost, st));
         if (identity) MG_CUDA(ctx, cudaMemcpyAsync(identity, d_ident.p, n * 8, cudaMemcpyDeviceToHost, st));
@@ -314,6 +393,13 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
     } else {
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_set_winner(mashgpu_screen_job *job, int on)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    job->winner = on != 0;
     return MASHGPU_OK;
 }
 

@@ -470,7 +470,6 @@ int runScreen(int argc, const char **argv)
         cerr << "ERROR: " << c.arguments[0] << " does not look like a sketch (.msh)" << endl;
         exit(1);
     }
-    if (c.opt("winning!").active) { cerr << "ERROR: -w (winner-takes-all) is not available in the GPU engine." << endl; return 1; }
     double pValueMax = c.opt("pvalue").number, identityMin = c.opt("identity").number;
     Sketch sketch;
     Sketch::Parameters parameters;
@@ -488,6 +487,7 @@ int runScreen(int argc, const char **argv)
     sketch.toSketchSet(set, h, nn, l);
     mashgpu_screen_job *job = 0;
     if (mashgpu_screen_open(gpuContext(), &p, &set, &job) != MASHGPU_OK) gpuFail();
+    if (c.opt("winning!").active && mashgpu_screen_set_winner(job, 1) != MASHGPU_OK) gpuFail();     // -w, CommandScreen.cpp:357-407
     int queryCount = (int)c.arguments.size() - 1;
     cerr << "Streaming from ";
     if (queryCount == 1) cerr << c.arguments[1]; else cerr << queryCount << " inputs";

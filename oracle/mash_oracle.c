@@ -630,3 +630,49 @@ MO_API void mo_screen_finish(const uint64_t *ref, const uint32_t *ref_n, uint64_
     }
     free(depths);
 }
+
+/* Screen reduce with `-w` ("winner take all", CommandScreen.cpp:357-407): after the plain shared counts, every reference
+ * hash seen in the mixture is re-assigned to ONE of the sketches that contain it -- the one with the highest identity
+ * estimate (scores[] = estimateIdentity of the plain shared count, :361-364), ties going to the longer genome (:392-396) --
+ * and shared / depths are rebuilt from those assignments (:366-404); median, identity and p-value then follow from the
+ * new counts as in mo_screen_finish (:409-436).  The reference walks each hash's sketches in the iteration order of a
+ * robin_hood::unordered_set, so a tie in BOTH score and length is broken by an order this restatement does not
+ * reproduce: here the lowest sketch index wins (parity unpinned for exact ties; the tests avoid equal lengths). */
+MO_API void mo_screen_finish_winner(const uint64_t *ref, const uint32_t *ref_n, const uint64_t *ref_len, uint64_t n_ref, uint64_t stride,
+                                    const uint64_t *keys, const uint32_t *counts, uint64_t n_keys,
+                                    uint64_t set_size, int kmer_size, double kmer_space,
+                                    uint64_t *shared, uint64_t *median, double *identity, double *pvalue)
+{
+    double *scores = (double *)malloc(sizeof(double) * (n_ref ? n_ref : 1));
+    int64_t *winner = (int64_t *)malloc(sizeof(int64_t) * (n_keys ? n_keys : 1));
+    for (uint64_t k = 0; k < n_keys; k++) winner[k] = -1;
+    for (uint64_t r = 0; r < n_ref; r++) {             /* plain shared counts -> scores */
+        uint64_t s = 0;
+        for (uint32_t i = 0; i < ref_n[r]; i++) {
+            int64_t at = find_sorted(keys, n_keys, ref[r * stride + i]);
+            if (at >= 0 && counts[at] >= 1) s++;
+        }
+        scores[r] = mo_estimate_identity(s, ref_n[r], kmer_size);
+    }
+    for (uint64_t r = 0; r < n_ref; r++)               /* ascending index: a full tie keeps the earlier sketch */
+        for (uint32_t i = 0; i < ref_n[r]; i++) {
+            int64_t at = find_sorted(keys, n_keys, ref[r * stride + i]);
+            if (at < 0 || counts[at] < 1) continue;
+            int64_t w = winner[at];
+            if (w < 0 || scores[r] > scores[w] || (scores[r] == scores[w] && ref_len[r] > ref_len[w])) winner[at] = (int64_t)r;
+        }
+    uint32_t *depths = (uint32_t *)malloc(sizeof(uint32_t) * (stride + 1));
+    for (uint64_t r = 0; r < n_ref; r++) {
+        uint64_t s = 0;
+        for (uint32_t i = 0; i < ref_n[r]; i++) {
+            int64_t at = find_sorted(keys, n_keys, ref[r * stride + i]);
+            if (at >= 0 && counts[at] >= 1 && winner[at] == (int64_t)r) depths[s++] = counts[at];
+        }
+        qsort(depths, s, sizeof(uint32_t), cmp_u32);
+        shared[r] = s;
+        median[r] = s > 0 ? depths[s / 2] : 0;
+        identity[r] = mo_estimate_identity(s, ref_n[r], kmer_size);
+        pvalue[r] = mo_pvalue_within(s, set_size, kmer_space, ref_n[r]);
+    }
+    free(depths); free(winner); free(scores);
+}

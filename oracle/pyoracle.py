@@ -103,6 +103,9 @@ class Oracle:
         L.mo_hash_sequence.argtypes = [C.c_void_p, u64p, u32p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(Params)]
         L.mo_screen_build_table.restype = C.c_uint64
         L.mo_screen_build_table.argtypes = [u64p, u32p, C.c_uint64, C.c_uint64, u64p]
+        L.mo_screen_finish_winner.restype = None
+        L.mo_screen_finish_winner.argtypes = [u64p, u32p, u64p, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
+                                              C.c_uint64, C.c_int, C.c_double, u64p, u64p, f64p, f64p]
         L.mo_screen_finish.restype = None
         L.mo_screen_finish.argtypes = [u64p, u32p, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
                                        C.c_uint64, C.c_int, C.c_double, u64p, u64p, f64p, f64p]
@@ -175,8 +178,9 @@ class Oracle:
         return a.reshape(nq, nr).copy()
 
     # ---- screen ------------------------------------------------------------------------------
-    def screen(self, ref, ref_n, chunks, p, s=1000):
+    def screen(self, ref, ref_n, chunks, p, s=1000, winner=False, ref_len=None):
         """ref: (n x stride) u64; chunks: list of '*'-joined byte strings (CommandScreen.cpp:224-262).
+        winner: `-w` reallocation (CommandScreen.cpp:357-407), needs ref_len.
         Returns dict(shared, median, identity, pvalue, set_size, counts, keys, mixture)."""
         ref = np.ascontiguousarray(ref, np.uint64); ref_n = np.ascontiguousarray(ref_n, np.uint32)
         nr, stride = ref.shape
@@ -194,9 +198,15 @@ class Oracle:
         self.lib.mo_heap_free(heap)
         shared = np.zeros(nr, np.uint64); median = np.zeros(nr, np.uint64)
         ident = np.zeros(nr, np.float64); pv = np.zeros(nr, np.float64)
-        self.lib.mo_screen_finish(_ptr(ref, u64p), _ptr(ref_n, u32p), nr, stride, _ptr(keys, u64p), _ptr(counts, u32p), nk,
-                                  set_size, p.kmer_size, self.kmer_space(p), _ptr(shared, u64p), _ptr(median, u64p),
-                                  _ptr(ident, f64p), _ptr(pv, f64p))
+        if winner:
+            ref_len = np.ascontiguousarray(ref_len, np.uint64)
+            self.lib.mo_screen_finish_winner(_ptr(ref, u64p), _ptr(ref_n, u32p), _ptr(ref_len, u64p), nr, stride, _ptr(keys, u64p), _ptr(counts, u32p), nk,
+                                             set_size, p.kmer_size, self.kmer_space(p), _ptr(shared, u64p), _ptr(median, u64p),
+                                             _ptr(ident, f64p), _ptr(pv, f64p))
+        else:
+            self.lib.mo_screen_finish(_ptr(ref, u64p), _ptr(ref_n, u32p), nr, stride, _ptr(keys, u64p), _ptr(counts, u32p), nk,
+                                      set_size, p.kmer_size, self.kmer_space(p), _ptr(shared, u64p), _ptr(median, u64p),
+                                      _ptr(ident, f64p), _ptr(pv, f64p))
         return dict(shared=shared, median=median, identity=ident, pvalue=pv, set_size=set_size,
                     counts=counts[:nk], keys=keys, mixture=mix[:nm].copy())
 

@@ -127,3 +127,20 @@ def test_parallel_parse_keeps_input_order(work):
     want = open(work / "genomes_p1.msh", "rb").read()
     for p in ("2", "3", "8"):
         assert open(work / f"genomes_p{p}.msh", "rb").read() == want
+
+
+def test_screen_winner_take_all_cli(work, oracle, golden):
+    # mash screen -w genomes.msh reads1.fastq reads2.fastq  (CommandScreen.cpp:357-407) against the oracle's restatement;
+    # genome2 and genome3 of the reference's test set are related strains, so the reallocation changes their rows
+    got = [l.split("\t") for l in out(work, "screen", "-w", "genomes.msh", "reads1.fastq", "reads2.fastq").splitlines()]
+    po = oracle.params(k=21)
+    ref = np.stack([golden.golden_sketch(i)[0] for i in range(3)])
+    lengths = np.array([golden.golden_sketch(i)[1] for i in range(3)], np.uint64)
+    reads = [r for r in golden.reads_round_robin() if len(r) >= 21]
+    chunk = b"".join(b"*" + r for r in reads)
+    want = oracle.screen(ref, np.full(3, 1000, np.uint32), [chunk], po, s=1000, winner=True, ref_len=lengths)
+    rows = [i for i in range(3) if want["shared"][i] != 0]                  # identityMin = 0: rows with shared == 0 are not printed (:420)
+    assert len(got) == len(rows)
+    for line, i in zip(got, rows):
+        assert line[:4] == [fmt_g(want["identity"][i]), f"{want['shared'][i]}/1000", str(want["median"][i]), fmt_g(want["pvalue"][i])]
+        assert line[4] == golden.golden_sketch(i)[2]

@@ -78,3 +78,23 @@ def test_empty_stream(gpu, oracle):
     ref = np.arange(1, 101, dtype=np.uint64)[None, :] * np.uint64(1 << 40)
     res = run_screen(gpu, ref, np.array([100], np.uint32), p, [b"*NNNNNNNNNNNNNNNNNNNNNNNNNNNNNN"])
     assert res["set_size"] == 0 and res["shared"][0] == 0 and res["pvalue"][0] == 1.0 and res["identity"][0] == 0.0
+
+
+def test_winner_take_all_matches_oracle(gpu, oracle):
+    # `mash screen -w` (CommandScreen.cpp:357-407): hashes shared by several sketches are counted for the best one only
+    from test_oracle_screen_winner import build
+    po, ref, ref_n, lengths, chunks = build(oracle)
+    p = gpu.params(k=21, s=400)
+    want_plain = oracle.screen(ref, ref_n, chunks, po, s=400)
+    want = oracle.screen(ref, ref_n, chunks, po, s=400, winner=True, ref_len=lengths)
+    job = gpu.screen_open(ref, ref_n, p, ref_len=lengths)
+    try:
+        for c in chunks:
+            job.feed(c)
+        check(job.finish(), want_plain)            # finish is repeatable: plain first, then with the reallocation
+        job.set_winner(True)
+        res = job.finish()
+    finally:
+        job.close()
+    check(res, want)
+    assert not np.array_equal(want["shared"], want_plain["shared"])
