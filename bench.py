@@ -10,7 +10,12 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
            sketches are inside the timed region.
   dist     (extra object) sketch-pairs/s of hot path 2 on configs[2]: all-vs-all of 100 000 synthetic s=1000 sketches
            (10^10 ordered pairs, dense numer/denom/distance/p-value/pass materialised in HBM tile by tile); at N>1 the
-           reference axis is sharded per rank and the query sketches are NCCL-broadcast from their owners.
+           reference axis is sharded per rank and the query sketches are NCCL-broadcast from their owners.  The timed run
+           uses the engine's default (tile prefilter + merge + dense p-value pass, results identical to merging every
+           pair); `prefilter` reports how many (query, tile) combinations reached the merge, `side_measurements` the
+           rate with the prefilter off and with the sketches in random order, `triangle` the `mash triangle` enumeration.
+  screen   (extra object) Gbp/s of hot path 3 on configs[3]: 100 000-sketch reference table, 50 M 150 bp reads sampled
+           from 50 of the configs[1] genomes (their sketches are in the table), chunks resident in HBM.
   roofline the scan kernel against the measured HBM peak (algorithmic bytes = 1 B/base of ASCII input), plus the
            integer-issue fraction that actually bounds it.
   cpu_baseline / --impl reference: the reference's own hash+heap object code (oracle/_ref) on all host cores.
