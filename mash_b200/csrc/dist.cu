@@ -63,7 +63,6 @@ struct DistArgs {
     uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
     int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
     int probe_prefetch;         // dist_probe_kernel: request the query lines two groups ahead into L1
-    int probe_unroll2;          // dist_probe_kernel: two groups (256 ranks) per loop iteration
     int triangle;               // self comparison, lower triangle only: pairs with r >= q are neither computed nor written
     // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
     struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
@@ -364,26 +363,9 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
         // name the four 128-byte lines): 8 warps per sub-partition do not cover the L2 latency on their own (ncu r01:
         // long_scoreboard 5.8 per issue, issue active 67 %).  ptxas sinks register prefetches to the end of the body.
         uint32_t cur[PROBE_DEPTH];
-        if (a.probe_unroll2) {
-            // two groups per iteration: 8 independent lookups in flight per lane and one vote per 256 ranks
-            while (base + 2 * GROUP <= nB && !confirmed) {
-                if (a.probe_prefetch && base + 2 * GROUP + 32 * (lane & 7) < nB)
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + base + 2 * GROUP + 32 * (lane & 7)));
-                uint32_t cur2[PROBE_DEPTH];
-#pragma unroll
-                for (int c = 0; c < PROBE_DEPTH; c++) { cur[c] = __ldg(pB + 32 * c); cur2[c] = __ldg(pB + GROUP + 32 * c); }
-                CfProbe p0[PROBE_DEPTH], p1[PROBE_DEPTH];
-#pragma unroll
-                for (int c = 0; c < PROBE_DEPTH; c++) { p0[c] = cf_fetch_s<false>(tab_s, cur[c]); p1[c] = cf_fetch_s<false>(tab_s, cur2[c]); }
-                const uint32_t h = cf_group_hit(p0[0], p0[1], p0[2], p0[3]) | cf_group_hit(p1[0], p1[1], p1[2], p1[3]);
-                if (__any_sync(0xFFFFFFFFu, h != 0)) {
-                    confirmed = probe_confirm<true>(s_tab, cur[0], cur[1], cur[2], cur[3], base, nB, lane, rowA, nA_lim);
-                    if (!confirmed) confirmed = probe_confirm<true>(s_tab, cur2[0], cur2[1], cur2[2], cur2[3], base + GROUP, nB, lane, rowA, nA_lim);
-                }
-                base += 2 * GROUP; pB += 2 * GROUP;
-            }
-        }
-        if (a.probe_prefetch && !a.probe_unroll2 && 2 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + GROUP + 32 * (lane & 3)));
+        // (two groups per iteration -- 8 lookups in flight per lane, one vote per 256 ranks -- measured slower, 22.6 vs 20.8 ms
+        // on the first query tile of configs[2]: the loop is bound by ALU-pipe and shared-memory throughput, not by latency)
+        if (a.probe_prefetch && 2 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + GROUP + 32 * (lane & 3)));
         while (base + GROUP <= nB && !confirmed) {
             if (a.probe_prefetch && base + 3 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + base + 2 * GROUP + 32 * (lane & 3)));
 #pragma unroll
@@ -516,7 +498,6 @@ struct mashgpu_dist_job {
     int prefilter_mode = -1;
     bool triangle = false;
     bool probe_prefetch = true;         // MASHGPU_PROBE_PREFETCH=0 to compare
-    bool probe_unroll2 = false;         // MASHGPU_PROBE_UNROLL2=1 to compare
     bool lazy_second = false;           // probe kernel: load the second bucket only where the first one is full (MASHGPU_CF_LAZY=1).
                                         // Measured on configs[2], first query tile (B200): off/prefetch 20.9 ms, on/prefetch 21.8, off/no
                                         // prefetch 22.4, on/no prefetch 23.2 -- the predicate logic costs more than the LDS wavefronts saved
@@ -661,7 +642,6 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     }
     if (const char *env = getenv("MASHGPU_CF_LAZY")) job->lazy_second = atoi(env) != 0;
     if (const char *env = getenv("MASHGPU_PROBE_PREFETCH")) job->probe_prefetch = atoi(env) != 0;
-    if (const char *env = getenv("MASHGPU_PROBE_UNROLL2")) job->probe_unroll2 = atoi(env) != 0;
     if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
     *job_out = job;
     return MASHGPU_OK;
@@ -737,7 +717,6 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
     a.triangle = job->triangle ? 1 : 0;
     a.probe_prefetch = job->probe_prefetch ? 1 : 0;
-    a.probe_unroll2 = job->probe_unroll2 ? 1 : 0;
     {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
         const uint64_t pairs = q_count * job->n_ref;
         const uint64_t cap = std::min<uint64_t>(pairs, std::max<uint64_t>(1ull << 20, pairs / 16));

@@ -176,30 +176,6 @@ __device__ __forceinline__ CfProbe cf_fetch_s(uint32_t tab_s, uint32_t code)
     return r;
 }
 
-// Lane-level form of cf_group_any (no vote): does THIS lane have a fingerprint match in any of its four probes?
-__device__ __forceinline__ uint32_t cf_group_hit(const CfProbe &a, const CfProbe &b, const CfProbe &c, const CfProbe &d)
-{
-    uint32_t any;
-    asm volatile("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7, q;\n\t"
-                 "setp.eq.f16x2 p0|p1, %1, %3;\n\t"
-                 "setp.eq.f16x2 p2|p3, %2, %3;\n\t"
-                 "setp.eq.f16x2 p4|p5, %4, %6;\n\t"
-                 "setp.eq.f16x2 p6|p7, %5, %6;\n\t"
-                 "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p4, p4, p5;\n\tor.pred p6, p6, p7;\n\t"
-                 "or.pred p0, p0, p2;\n\tor.pred p4, p4, p6;\n\tor.pred q, p0, p4;\n\t"
-                 "setp.eq.f16x2 p0|p1, %7, %9;\n\t"
-                 "setp.eq.f16x2 p2|p3, %8, %9;\n\t"
-                 "setp.eq.f16x2 p4|p5, %10, %12;\n\t"
-                 "setp.eq.f16x2 p6|p7, %11, %12;\n\t"
-                 "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p4, p4, p5;\n\tor.pred p6, p6, p7;\n\t"
-                 "or.pred p0, p0, p2;\n\tor.pred p4, p4, p6;\n\tor.pred p0, p0, p4;\n\tor.pred q, q, p0;\n\t"
-                 "selp.u32 %0, 1, 0, q;\n\t}"
-                 : "=r"(any)
-                 : "r"(a.w1), "r"(a.w2), "r"(a.f2), "r"(b.w1), "r"(b.w2), "r"(b.f2),
-                   "r"(c.w1), "r"(c.w2), "r"(c.f2), "r"(d.w1), "r"(d.w2), "r"(d.f2));
-    return any;
-}
-
 // Does any lane of the warp have a fingerprint match in any of its four probes?  8 half2 compares (a fingerprint is a
 // finite non-zero half, the free slot is +0.0), predicate ors and one vote.  An f2 of 0x7E007E00 (NaN) never matches.
 __device__ __forceinline__ bool cf_group_any(const CfProbe &a, const CfProbe &b, const CfProbe &c, const CfProbe &d)
