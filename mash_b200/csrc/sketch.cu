@@ -674,7 +674,16 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
             for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
             const uint64_t max_tiles = (max_bytes + SCAN_TILE - 1) / SCAN_TILE;
             const uint64_t groups_alloc = max_tiles * (SCAN_TILE / 32) + 64;       // tile-padded + halo
+            // as many packer threads as the process may actually run: a container's CPU quota (cgroup v2 cpu.max) can be far
+            // below the visible core count, and threads beyond it are throttled together -- measured on this pool's B200 box
+            // (128 vCPUs visible, quota 16): 61 GB/s with 16 threads, 13 GB/s with 128 (tools/pack_bench.py)
             int threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 96u);
+            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                long long quota = 0, period = 0;
+                if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+                    threads = std::min(threads, (int)std::max(1ll, (quota + period - 1) / period));
+                fclose(f);
+            }
             if (const char *t = getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, atoi(t));
             const int nbuf = waves.size() > 1 ? 2 : 1;
             uint64_t *d_codes[2] = {nullptr, nullptr}; uint32_t *d_inval[2] = {nullptr, nullptr};
