@@ -186,6 +186,34 @@ def host_genomes(n_units, genome_len, seed):
     return [acgt[rng.integers(0, 4, genome_len, dtype=np.uint8)] for _ in range(n_units)]
 
 
+def usable_cpus():
+    """CPUs this process may really use: visible count, affinity mask and the container's CPU quota (cgroup v2 cpu.max)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def best_cpu_sketch_rate(n_units, genome_len, seed=123):
+    """The CPU arm at its best on this host: once with one thread per usable CPU (the quota), once with one per visible CPU --
+    oversubscribing a quota can go either way -- and the faster of the two counts.  Returns (Gbp/s, kind, seconds, threads, tried)."""
+    tried = {}
+    for th in sorted({usable_cpus(), os.cpu_count() or 1}):
+        r, kind, dt = cpu_sketch_rate(n_units, genome_len, th, seed)
+        tried[th] = (r, kind, dt)
+    th = max(tried, key=lambda t: tried[t][0])
+    r, kind, dt = tried[th]
+    return r, kind, dt, th, {str(t): round(v[0], 4) for t, v in tried.items()}
+
+
 def cpu_sketch_rate(n_units, genome_len, threads, seed=123):
     """Times the reference's hash + MinHashHeap object code (oracle/_ref, restated scan loop) on `threads` host threads.
     Falls back to the plain-C oracle port when oracle/_ref is absent. Returns (Gbp/s, kind, seconds)."""
@@ -213,11 +241,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    n_units = max(8, 2 * cores)
+    n_units = max(128, 2 * (os.cpu_count() or 1))
     rates = []
+    cores, tried, kind = 1, {}, "port"
     for i in range(args.warmup + args.steps):
-        r, kind, dt = cpu_sketch_rate(n_units, args.genome_len, cores, seed=1000 + i)
+        r, kind, dt, cores, tried = best_cpu_sketch_rate(n_units, args.genome_len, seed=1000 + i)
         if i >= args.warmup:
             rates.append((r, dt))
     value = float(np.mean([r for r, _ in rates]))
@@ -228,7 +256,9 @@ def run_reference_arm(args):
         "config": {"workload": "configs[1]: synthetic 5 Mbp genomes, k=21 s=1000 (bounded sample of the 10 000-genome batch)",
                    "k": K, "s": S, "genome_len": args.genome_len},
         "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind,
-                         "sample": f"{n_units} genomes x {args.genome_len} bp per step, one job per genome on {cores} threads; "
+                         "visible_cpus": os.cpu_count(), "usable_cpus": usable_cpus(), "gbp_per_s_by_threads": tried,
+                         "sample": f"{n_units} genomes x {args.genome_len} bp per step, one job per genome on {cores} threads (the faster of one "
+                                   "thread per usable CPU and one per visible CPU); "
                                    "reference MurmurHash3/hash/MinHashHeap object code, restated addMinHashes loop, in-memory input (no FASTA parse)"},
         "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -600,11 +630,12 @@ def main():
     # ---------------- CPU baseline on rank 0 --------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cores = os.cpu_count() or 1
-        n_cpu = max(8, 2 * cores)
-        rate, kind, dt = cpu_sketch_rate(n_cpu, glen, cores)
+        n_cpu = max(128, 2 * (os.cpu_count() or 1))
+        rate, kind, dt, cores, tried = best_cpu_sketch_rate(n_cpu, glen)
         cpu = {"value": rate, "unit": "Gbp/s", "cores": cores, "kind": kind,
-               "sample": f"{n_cpu} genomes x {glen} bp, one job per genome on {cores} threads, {dt:.1f} s wall; reference MurmurHash3/hash/MinHashHeap "
+               "visible_cpus": os.cpu_count(), "usable_cpus": usable_cpus(), "gbp_per_s_by_threads": tried,
+               "sample": f"{n_cpu} genomes x {glen} bp, one job per genome on {cores} threads (the faster of one thread per usable CPU -- the "
+                         f"container's quota -- and one per visible CPU), {dt:.1f} s wall; reference MurmurHash3/hash/MinHashHeap "
                          "object code (oracle/_ref), restated addMinHashes loop, in-memory input"}
 
     if rank == 0:
