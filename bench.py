@@ -18,7 +18,9 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
            from 50 of the configs[1] genomes (their sketches are in the table), chunks resident in HBM.
   roofline the scan kernel against the measured HBM peak (algorithmic bytes = 1 B/base of ASCII input), plus the
            integer-issue fraction that actually bounds it.
-  cpu_baseline / --impl reference: the reference's own hash+heap object code (oracle/_ref) on all host cores.
+  cpu_baseline / --impl reference: the reference's own hash+heap object code (oracle/_ref) on the host cores the process
+           may use (the faster of one thread per usable CPU -- cgroup quota -- and one per visible CPU; both reported), input
+           in memory; `with_fasta_parse` = the same with the reference's kseq.h parser reading FASTA files from tmpfs.
 """
 import argparse
 import json
@@ -235,6 +237,34 @@ def cpu_sketch_rate(n_units, genome_len, threads, seed=123):
         dt = time.perf_counter() - t0
         kind = "port"
     return n_units * genome_len / dt / 1e9, kind, dt
+
+
+def cpu_sketch_rate_from_files(n_units, genome_len, threads, seed=321):
+    """The CPU arm with the parse included, as `mash sketch -p threads *.fna` runs it: uncompressed 70-column FASTA files on
+    tmpfs, the reference's own kseq.h parser + hash + heap object code (oracle/_ref).  Returns (Gbp/s, seconds) or None."""
+    from oracle.pyoracle import Oracle, RefLib
+    if not RefLib.available():
+        return None
+    ref = RefLib()
+    if not hasattr(ref.lib, "ref_sketch_files"):
+        return None
+    p = Oracle().params(k=K, seed=SEED)
+    seqs = host_genomes(n_units, genome_len, seed)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        paths = []
+        for i, q in enumerate(seqs):
+            a = np.frombuffer(q, np.uint8)
+            full = (a.size // 70) * 70
+            lines = np.concatenate([a[:full].reshape(-1, 70), np.full((full // 70, 1), 10, np.uint8)], axis=1).tobytes()
+            path = os.path.join(d, f"g{i}.fna")
+            with open(path, "wb") as f:
+                f.write(b">g%d synthetic\n" % i + lines + a[full:].tobytes() + b"\n")
+            paths.append(path)
+        t0 = time.perf_counter()
+        ref.sketch_files(paths, p, s=S, threads=threads)
+        dt = time.perf_counter() - t0
+    return n_units * genome_len / dt / 1e9, dt
 
 
 def run_reference_arm(args):
@@ -632,8 +662,12 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         n_cpu = max(128, 2 * (os.cpu_count() or 1))
         rate, kind, dt, cores, tried = best_cpu_sketch_rate(n_cpu, glen)
+        parsed = cpu_sketch_rate_from_files(max(32, 2 * usable_cpus()), glen, cores)
         cpu = {"value": rate, "unit": "Gbp/s", "cores": cores, "kind": kind,
                "visible_cpus": os.cpu_count(), "usable_cpus": usable_cpus(), "gbp_per_s_by_threads": tried,
+               "with_fasta_parse": None if parsed is None else
+               {"value": parsed[0], "unit": "Gbp/s", "threads": cores,
+                "note": f"same threads, one job per file: uncompressed 70-column FASTA on tmpfs through the reference's kseq.h parser (oracle/_ref), {parsed[1]:.1f} s wall"},
                "sample": f"{n_cpu} genomes x {glen} bp, one job per genome on {cores} threads (the faster of one thread per usable CPU -- the "
                          f"container's quota -- and one per visible CPU), {dt:.1f} s wall; reference MurmurHash3/hash/MinHashHeap "
                          "object code (oracle/_ref), restated addMinHashes loop, in-memory input"}

@@ -253,6 +253,18 @@ class RefLib:
                                  _ptr(out, u64p), _ptr(out_n, u32p))
         return out, out_n
 
+    def sketch_files(self, paths, p, s=1000, threads=1):
+        """One sketch per FASTA/FASTQ(.gz) file through the reference's own parser (kseq.h) + hash + heap: `mash sketch -p`
+        as the CPU runs it.  Returns (hashes (n x s), n_hashes, lengths)."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(q) for q in paths])
+        out = np.zeros((len(paths), s), dtype=np.uint64); out_n = np.zeros(len(paths), dtype=np.uint32)
+        lens = np.zeros(len(paths), dtype=np.uint64)
+        self.lib.ref_sketch_files.restype = C.c_int
+        rc = self.lib.ref_sketch_files(C.byref(p), C.c_uint64(s), C.c_uint64(len(paths)), arr, C.c_int(threads), _ptr(out, u64p), _ptr(out_n, u32p), _ptr(lens, u64p))
+        if rc:
+            raise RuntimeError("ref_sketch_files: a file could not be read")
+        return out, out_n, lens
+
     def hash_sequence(self, keys, counts, chunk, p, s=1000):
         b = np.frombuffer(chunk, dtype=np.uint8) if isinstance(chunk, (bytes, bytearray)) else np.ascontiguousarray(chunk, np.uint8)
         out = np.empty(s, np.uint64); n = C.c_uint32(0)

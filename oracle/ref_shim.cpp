@@ -16,9 +16,13 @@
 #include <vector>
 #include <atomic>
 
+#include <zlib.h>
+
 #include "hash.h"
 #include "HashList.h"
 #include "MinHashHeap.h"
+#include "kseq.h"
+KSEQ_INIT(gzFile, gzread)            // as the reference instantiates its parser (Sketch.cpp:21)
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
@@ -123,6 +127,49 @@ REF_API void ref_sketch_many(const ref_params *p, uint64_t sketch_size, uint64_t
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++) pool.emplace_back(work);
     for (auto &t : pool) t.join();
+}
+
+// sketchFile's own loop for ONE file per sketch (Sketch.cpp:1186-1282, default non-reads mode): the reference's parser
+// (kseq_read) feeds addMinHashes record by record; records shorter than k are skipped and not counted in the length.
+// Returns the number of hashes; *out_length = Reference::length.  -1 when the file cannot be opened / is truncated.
+static int64_t sketch_one_file(const ref_params *p, uint64_t sketch_size, const char *path, uint64_t *out_hashes, uint64_t *out_length)
+{
+    gzFile fp = gzopen(path, "r");
+    if (!fp) return -1;
+    kseq_t *ks = kseq_init(fp);
+    MinHashHeap heap(p->use64 != 0, sketch_size, 1, 0);
+    uint64_t length = 0;
+    int l;
+    while ((l = kseq_read(ks)) >= 0) {
+        if (l < p->kmer_size) continue;
+        length += (uint64_t)l;
+        add_min_hashes(heap, ks->seq.s, (uint64_t)l, *p);
+    }
+    kseq_destroy(ks);
+    gzclose(fp);
+    if (l != -1) return -1;
+    if (out_length) *out_length = length;
+    return (int64_t)emit(heap, p->use64 != 0, out_hashes, nullptr);
+}
+
+// The CPU arm as `mash sketch -p threads file1 file2 ...` runs it: one job per file, parse included.
+REF_API int ref_sketch_files(const ref_params *p, uint64_t sketch_size, uint64_t n_files, const char *const *paths, int threads,
+                             uint64_t *out_hashes, uint32_t *out_n, uint64_t *out_length)
+{
+    std::atomic<uint64_t> next(0);
+    std::atomic<int> failed(0);
+    auto work = [&]() {
+        for (;;) {
+            uint64_t u = next.fetch_add(1);
+            if (u >= n_files) return;
+            int64_t n = sketch_one_file(p, sketch_size, paths[u], out_hashes + u * sketch_size, out_length ? out_length + u : nullptr);
+            if (n < 0) { failed = 1; out_n[u] = 0; } else out_n[u] = (uint32_t)n;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+    return failed.load();
 }
 
 // hashSequence (CommandScreen.cpp:484-599) nucleotide path around reference getHash/MinHashHeap;

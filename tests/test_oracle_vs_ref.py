@@ -47,3 +47,33 @@ def test_hash_sequence_matches_reference(oracle, reflib):
     mix = reflib.hash_sequence(res["keys"], counts, chunk, p, s=500)
     assert np.array_equal(counts, res["counts"])
     assert np.array_equal(mix, res["mixture"])
+
+
+def test_reference_cpu_path_from_files_reproduces_the_goldens(reflib, golden, tmp_path):
+    # the whole CPU arm as `mash sketch` runs it -- the reference's own parser (kseq.h), the restated addMinHashes loop and the
+    # reference's hash + heap object code -- on the reference's test genomes (gzipped, as gzread takes them) must give
+    # test/ref/genomes.json: this is the code bench.py times as cpu_baseline / --impl reference
+    import os
+    from fixtures import GOLDEN
+    from oracle.pyoracle import Oracle
+    p = Oracle().params(k=21, seed=42)
+    paths = [os.path.join(GOLDEN, f"genome{i}.fna.gz") for i in (1, 2, 3)]
+    h, n, lens = reflib.sketch_files(paths, p, s=1000, threads=3)
+    for i in range(3):
+        want, length, _, _ = golden.golden_sketch(i)
+        assert n[i] == 1000 and np.array_equal(h[i], want) and int(lens[i]) == length
+
+
+def test_file_path_equals_in_memory_path(reflib, tmp_path):
+    from oracle.pyoracle import Oracle
+    p = Oracle().params(k=21, seed=42)
+    g = synth_genome(77, 300_000, n_runs=4, lower_frac=0.05)
+    path = tmp_path / "g.fa"
+    with open(path, "wb") as f:
+        f.write(b">g some comment\n")
+        for a in range(0, g.size, 70):
+            f.write(bytes(g[a:a + 70]) + b"\n")
+        f.write(b">tiny\nACGT\n")                      # shorter than k: skipped, not counted in the length
+    h, n, lens = reflib.sketch_files([str(path)], p, s=500, threads=1)
+    hm, _, lm = reflib.sketch_unit([bytes(g), b"ACGT"], p, s=500)
+    assert int(lens[0]) == lm == g.size and np.array_equal(h[0, :n[0]], hm)
