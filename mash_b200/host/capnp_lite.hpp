@@ -119,7 +119,7 @@ private:
     // BuilderArena::allocate: only the newest segment is tried before a new one is made
     Ptr arenaAllocate(uint32_t amount)
     {
-        uint32_t off;
+        uint32_t off = 0;
         if (segs_.empty()) addSegment(amount);
         else if (!tryAlloc((uint32_t)segs_.size() - 1, amount, off)) { addSegment(amount); }
         else return Ptr{(uint32_t)segs_.size() - 1, off};
