@@ -7,6 +7,9 @@
 // Implementation differs (block-wise scanning with a byte-class table instead of one ks_getc call per byte).
 #pragma once
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cctype>
 #include <cstdio>
 #include <cstring>
@@ -50,6 +53,8 @@ public:
             const unsigned char *run = p;
             int stop = 0;
             while (p < e) {
+                p = skipGraph(p, e);         // next byte that is not a plain sequence byte (class != 0), 32 bytes at a time
+                if (p >= e) break;
                 int k = cls_[*p];
                 if (k == 0) { p++; continue; }
                 if (p > run) seq.append(reinterpret_cast<const char *>(run), p - run);
@@ -63,10 +68,25 @@ public:
         }
         if (c == '>' || c == '@') lastChar_ = c;
         if (c != '+') return (int)seq.size();   // FASTA
-        while ((c = getc()) != -1 && c != '\n') {}
+        // rest of the '+' line (block-wise memchr instead of one getc per byte)
+        for (c = -1;;) {
+            if (begin_ >= end_ && !fill()) break;
+            const unsigned char *nlp = static_cast<const unsigned char *>(memchr(buf_.data() + begin_, '\n', end_ - begin_));
+            if (nlp) { begin_ = (size_t)(nlp - buf_.data()) + 1; c = '\n'; break; }
+            begin_ = end_;
+        }
         if (c == -1) return -2;
-        while ((c = getc()) != -1 && qual < seq.size())
-            if (c >= 33 && c <= 127) qual++;
+        // quality: kseq reads one byte past the last quality character it needs (`while ((c = ks_getc(ks)) != -1 && qual.l < seq.l)`
+        // consumes a byte, then tests the length), so one further byte is taken after the count is complete
+        for (;;) {
+            if (begin_ >= end_ && !fill()) break;
+            if (qual >= seq.size()) { begin_++; break; }                 // the byte kseq consumes before it notices it is done
+            const unsigned char *q = buf_.data() + begin_, *qe = buf_.data() + end_;
+            size_t need = seq.size() - qual;
+            while (q < qe && need) { need -= (size_t)(*q >= 33 && *q <= 127); q++; }
+            qual = seq.size() - need;
+            begin_ = (size_t)(q - buf_.data());
+        }
         lastChar_ = 0;
         if (seq.size() != qual) return -2;
         return (int)seq.size();
@@ -79,6 +99,34 @@ private:
     bool eof_ = false;
     int lastChar_ = 0;
     unsigned char cls_[256];
+
+    // First position in [p, e) whose byte is not a plain sequence byte: outside isgraph() (33..126) or one of '>' '+' '@'.
+#if defined(__x86_64__)
+    __attribute__((target("avx2"))) static const unsigned char *skipGraphAvx2(const unsigned char *p, const unsigned char *e)
+    {
+        const __m256i lo = _mm256_set1_epi8(33), flip = _mm256_set1_epi8((char)0x80), lim = _mm256_set1_epi8((char)(93 ^ 0x80));
+        const __m256i gt = _mm256_set1_epi8('>'), pl = _mm256_set1_epi8('+'), at = _mm256_set1_epi8('@');
+        while (p + 32 <= e) {
+            const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+            const __m256i a = _mm256_xor_si256(_mm256_sub_epi8(x, lo), flip);          // (x - 33) as a biased signed value
+            const __m256i nongraph = _mm256_cmpgt_epi8(a, lim);                          // (x - 33) > 93 unsigned
+            const __m256i term = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, gt), _mm256_cmpeq_epi8(x, pl)), _mm256_cmpeq_epi8(x, at));
+            const unsigned m = (unsigned)_mm256_movemask_epi8(_mm256_or_si256(nongraph, term));
+            if (m) return p + __builtin_ctz(m);
+            p += 32;
+        }
+        return p;
+    }
+#endif
+    const unsigned char *skipGraph(const unsigned char *p, const unsigned char *e) const
+    {
+#if defined(__x86_64__)
+        static const bool avx2 = __builtin_cpu_supports("avx2");
+        if (avx2) p = skipGraphAvx2(p, e);
+#endif
+        while (p < e && cls_[*p] == 0) p++;
+        return p;
+    }
 
     bool fill()
     {
