@@ -18,9 +18,16 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
            from 50 of the configs[1] genomes (their sketches are in the table), chunks resident in HBM.
   roofline the scan kernel against the measured HBM peak (algorithmic bytes = 1 B/base of ASCII input), plus the
            integer-issue fraction that actually bounds it.
+  dist5    (extra object) BASELINE.json configs[4]: all-vs-all of 1 000 000 s=1000 sketches (10^12 ordered pairs), reference axis
+           sharded over the ranks, dictionary built by the sharded sample sort (mash_b200/shard.py), `-d 0.05` pass list returned
+           to the host tile by tile.  ONE pass, timed from the raw hashes to the last list on the host: dictionary build, exchange
+           and every kernel are inside the figure.
   cpu_baseline / --impl reference: the reference's own hash+heap object code (oracle/_ref) on the host cores the process
            may use (the faster of one thread per usable CPU -- cgroup quota -- and one per visible CPU; both reported), input
-           in memory; `with_fasta_parse` = the same with the reference's kseq.h parser reading FASTA files from tmpfs.
+           in memory; `with_fasta_parse` = the same with the reference's kseq.h parser reading FASTA files from tmpfs;
+           `.dist` = compare / compareSketches (CommandDistance.cpp:195-232, 306-448 restated in oracle/) over 4096-pair jobs of
+           a 4000 x 4000 subset; `.screen` = hashSequence (CommandScreen.cpp:484-599) on 10^6 reads with the reference's own
+           hash, heap and robin_hood table code.
 """
 import argparse
 import json
@@ -53,6 +60,8 @@ def parse_args():
     ap.add_argument("--sketches", type=int, default=N_SKETCHES, help="sketches in the dist workload (default: the BASELINE config)")
     ap.add_argument("--e2e-units", type=int, default=0, help="genomes per e2e step (0 = as many of --units as pinned host memory allows)")
     ap.add_argument("--reads", type=int, default=50_000_000, help="150 bp reads in the screen workload (default: the BASELINE config)")
+    ap.add_argument("--sketches5", type=int, default=1_000_000, help="sketches in the configs[4] dist workload (dist5)")
+    ap.add_argument("--skip-dist5", action="store_true")
     ap.add_argument("--skip-dist", action="store_true")
     ap.add_argument("--skip-screen", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -183,9 +192,119 @@ def make_sketches_device(torch, dev, n, s, seed, n_families=100, length=5_000_00
 # CPU baseline (reference object code on host cores)
 # ------------------------------------------------------------------------------------------------------------------
 def host_genomes(n_units, genome_len, seed):
+    """configs[1] genomes in host memory: iid uniform ACGT; every 10th with 20 N-runs (U[1,1000]) and 5 % lower case."""
     rng = np.random.Generator(np.random.PCG64(seed))
     acgt = np.frombuffer(b"ACGT", np.uint8)
-    return [acgt[rng.integers(0, 4, genome_len, dtype=np.uint8)] for _ in range(n_units)]
+    out = []
+    for u in range(n_units):
+        g = acgt[rng.integers(0, 4, genome_len, dtype=np.uint8)]
+        if u % 10 == 0:
+            for a, l in zip(rng.integers(0, genome_len, 20), rng.integers(1, 1001, 20)):
+                g[int(a):min(genome_len, int(a) + int(l))] = ord("N")
+            g[rng.random(genome_len) < 0.05] |= 0x20
+        out.append(g)
+    return out
+
+
+def host_sketches(n, s, seed, n_families, length=5_000_000):
+    """The configs[2] generator (make_sketches_device) in numpy, for the CPU arms."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    hi = int(2 ** 64 * s / length)
+    per = (n + n_families - 1) // n_families
+    H = np.empty((n, s), np.uint64)
+    jac = np.array([1.0, 0.98, 0.95, 0.9, 0.8, 0.5, 0.1, 0.0])
+    for f in range(n_families):
+        r0, r1 = f * per, min(n, (f + 1) * per)
+        if r0 >= r1:
+            break
+        m = r1 - r0
+        base = rng.integers(0, hi, 2 * s, dtype=np.uint64)
+        fresh = rng.integers(0, hi, (m, 2 * s), dtype=np.uint64)
+        keep = rng.random((m, 2 * s)) < jac[rng.integers(0, jac.size, m)][:, None]
+        v = np.sort(np.where(keep, base[None, :], fresh), axis=1)
+        dup = np.zeros(v.shape, bool)
+        dup[:, 1:] = v[:, 1:] <= v[:, :-1]
+        v = v + np.cumsum(dup, axis=1, dtype=np.uint64)
+        H[r0:r1] = v[:, :s]
+    N = np.full(n, s, np.uint32)
+    L = rng.integers(4_000_000, 6_000_000, n).astype(np.uint64)
+    return H, N, L
+
+
+def cpu_dist_rate(threads, n_sub=4000, seed=55):
+    """compare (CommandDistance.cpp:306-334) over the reference's <= 4096-pair jobs (:195-232), one job per pool thread at a
+    time, on an n_sub x n_sub subset of the configs[2] generator.  compareSketches / pValue are the oracle's restatement
+    (CommandDistance.cpp does not compile here: GSL/Boost and the capnp header are absent).  Returns (pairs/s, seconds)."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.pyoracle import Oracle, PairOutput, u64p, u32p
+    orc = Oracle()
+    H, N, L = host_sketches(n_sub, S, seed, n_families=max(1, n_sub // 100))
+    out = (PairOutput * (n_sub * n_sub))()
+    rows_per_job = max(1, 4096 // n_sub)
+    ks = 4.0 ** K
+
+    def job(q0):
+        orc.lib.mo_compare_all(out, H.ctypes.data_as(u64p), N.ctypes.data_as(u32p), L.ctypes.data_as(u64p), n_sub, S,
+                               H.ctypes.data_as(u64p), N.ctypes.data_as(u32p), L.ctypes.data_as(u64p), n_sub, S,
+                               S, K, ks, 1.0, 1.0, q0, min(n_sub, q0 + rows_per_job))
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(job, range(0, n_sub, rows_per_job)))
+    dt = time.perf_counter() - t0
+    return n_sub * n_sub / dt, dt
+
+
+def cpu_screen_rate(threads, n_reads=1_000_000, n_table=10_000, seed=66):
+    """hashSequence (CommandScreen.cpp:484-599) on n_reads 150 bp reads in 1 MiB '*'-joined chunks (:224-262), the reference's
+    own getHash / MinHashHeap object code and its robin_hood table type (oracle/_ref), `threads` workers.  The table holds
+    n_table synthetic sketches plus the sketches of the 4 genomes the reads are sampled from.  Returns (Gbp/s, seconds, kind)."""
+    from oracle.pyoracle import Oracle, RefLib
+    if not RefLib.available():
+        return None
+    ref = RefLib()
+    p = Oracle().params(k=K, seed=SEED)
+    H, N, L = host_sketches(n_table, S, seed, n_families=max(1, n_table // 1000))
+    src = host_genomes(4, 2_000_000, seed + 1)
+    sk, sk_n = ref.sketch_many(src, p, s=S, threads=min(4, threads))
+    keys = np.unique(np.concatenate([H.reshape(-1), sk.reshape(-1)]))
+    rng = np.random.Generator(np.random.PCG64(seed + 2))
+    pool = np.concatenate(src)
+    starts = rng.integers(0, pool.size - 150, n_reads)
+    reads = pool[starts[:, None] + np.arange(150)[None, :]]
+    err = rng.random(reads.shape) < 0.005
+    reads[err] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(err.sum()))]
+    reads[rng.random(reads.shape) < 0.001] = ord("N")
+    joined = np.concatenate([np.full((n_reads, 1), ord("*"), np.uint8), reads], axis=1).reshape(-1)
+    per_chunk = (1 << 20) // 151 * 151
+    chunks = [joined[o:o + per_chunk] for o in range(0, joined.size, per_chunk)]
+    t = ref.screen_table(keys)
+    try:
+        t0 = time.perf_counter()
+        ref.screen_many(t, chunks, p, s=S, threads=threads)
+        dt = time.perf_counter() - t0
+    finally:
+        ref.screen_table_free(t)
+    return n_reads * 150 / dt / 1e9, dt, "reference"
+
+
+WORKLOAD_SKETCH = ("configs[1]: {units} synthetic genomes x {glen} bp per GPU, k=%d s=%d seed=%d, canonical, ASCII input "
+                   "(every 10th genome with 20 N-runs and 5%% lower case)" % (K, S, SEED))
+
+
+def cpu_arms(threads):
+    """dist and screen CPU arms (bounded samples), as sub-objects of cpu_baseline."""
+    d_rate, d_dt = cpu_dist_rate(threads)
+    out = {"dist": {"value": d_rate, "unit": "pairs/s", "cores": threads, "kind": "port",
+                    "sample": f"4000 x 4000 sketches of the configs[2] generator (s={S}), compare over <= 4096-pair jobs on {threads} threads, {d_dt:.1f} s wall; "
+                              "compareSketches/pValue restated in oracle/mash_oracle.c (CommandDistance.cpp needs GSL/Boost, absent here)"}}
+    sc = cpu_screen_rate(threads)
+    if sc is not None:
+        out["screen"] = {"value": sc[0], "unit": "Gbp/s", "cores": threads, "kind": sc[2],
+                         "sample": f"10^6 synthetic 150 bp reads in 1 MiB chunks against a 10 004-sketch table on {threads} threads, {sc[1]:.1f} s wall; "
+                                   "reference getHash/MinHashHeap object code and robin_hood table (oracle/_ref), restated hashSequence loop"}
+    return out
 
 
 def usable_cpus():
@@ -279,19 +398,25 @@ def run_reference_arm(args):
         if i >= args.warmup:
             rates.append((r, dt))
     value = float(np.mean([r for r, _ in rates]))
+    arms = cpu_arms(cores)
     line = {
         "impl": "reference", "metric": "Gbp_per_s_sketched", "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([dt for _, dt in rates]) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic 5 Mbp genomes, k=21 s=1000 (bounded sample of the 10 000-genome batch)",
-                   "k": K, "s": S, "genome_len": args.genome_len},
+        "config": {"workload": WORKLOAD_SKETCH.format(units=args.units, glen=args.genome_len),
+                   "k": K, "s": S, "units_per_gpu": args.units, "genome_len": args.genome_len,
+                   "sample": f"{n_units} genomes of the batch per step (CPU arm: bounded sample of the same workload)"},
         "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind,
                          "visible_cpus": os.cpu_count(), "usable_cpus": usable_cpus(), "gbp_per_s_by_threads": tried,
                          "sample": f"{n_units} genomes x {args.genome_len} bp per step, one job per genome on {cores} threads (the faster of one "
                                    "thread per usable CPU and one per visible CPU); "
                                    "reference MurmurHash3/hash/MinHashHeap object code, restated addMinHashes loop, in-memory input (no FASTA parse)"},
         "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dist": dict(arms["dist"], metric="sketch_pairs_per_s"),
+        "screen": dict(arms["screen"], metric="Gbp_per_s_screened") if "screen" in arms else None,
     }
+    line["cpu_baseline"]["dist"] = arms["dist"]
+    line["cpu_baseline"]["screen"] = arms.get("screen")
     emit_json_line(line)
 
 
@@ -454,6 +579,7 @@ def main():
 
     # ---------------- hot path 2: dist ---------------------------------------------------------------------------
     dist_obj = None
+    dist5_obj = None
     screen_obj = None
     if not args.skip_dist:
         # configs[3] samples its reads from 50 of the configs[1] genomes: keep those genomes and their sketches for the screen step
@@ -463,34 +589,30 @@ def main():
         del stream
         torch.cuda.empty_cache()
         n_sk = args.sketches
-        # every rank owns n_sk/world sketches: its reference shard, and the queries it broadcasts
+        # every rank owns n_sk/world sketches: its reference shard (resident), and its share of the queries
         shard = (n_sk + world - 1) // world
-        H, N, L = make_sketches_device(torch, dev, shard, S, seed=1000 + rank)
+        H, N, L = make_sketches_device(torch, dev, shard, S, seed=1000 + rank, n_families=max(1, 100 // world))
         if dist_on:
-            # exchange step: each owner broadcasts its query tile over NCCL/NVLink (here one tile per owner)
-            allH = [torch.empty_like(H) for _ in range(world)]
-            allL = [torch.empty_like(L) for _ in range(world)]
-            t0e = torch.cuda.Event(enable_timing=True); t1e = torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            for r in range(world):
-                bufH = H if r == rank else allH[r]
-                bufL = L if r == rank else allL[r]
-                td.broadcast(bufH, src=r); td.broadcast(bufL, src=r)
-                allH[r], allL[r] = bufH, bufL
-            t1e.record(); torch.cuda.synchronize()
-            bcast_ms = t0e.elapsed_time(t1e)
-            QH = torch.cat(allH); QL = torch.cat(allL)
-            QN = torch.full((QH.shape[0],), S, dtype=torch.int32, device=dev)
-            del allH, allL
-        else:
-            QH, QN, QL = H, N, L
-            bcast_ms = 0.0
-        ref_set = mash_b200._capi._Set(H.data_ptr(), N.data_ptr(), L.data_ptr(), on_device=True, n=H.shape[0], stride=S)
-        qry_set = None if not dist_on else mash_b200._capi._Set(QH.data_ptr(), QN.data_ptr(), QL.data_ptr(), on_device=True, n=QH.shape[0], stride=S)
-        t_open = time.perf_counter()
-        job = mash_b200._capi.DistJob(eng, ref_set, None, None, qry_set, None, None, S, K, p.kmer_space, 1.0, 1.0)
+            from mash_b200.shard import sharded_dictionary, DictOps, warm_collectives
+            warm_collectives(dev)                 # communicator channel set-up is a process start-up cost, not part of a pass
         torch.cuda.synchronize()
-        open_ms = (time.perf_counter() - t_open) * 1e3
+        barrier()
+        # ---- one-off work of a job, timed: dictionary build (+ the exchange step at N > 1) ----
+        t_open = time.perf_counter()
+        enc = None
+        if dist_on:
+            # exchange step: sample sort of the hashes by hash range (all-to-all) + all-gather of the encoded rows (4 B per hash)
+            rows, n_eff, lens_all, counts, dstat = sharded_dictionary(DictOps(eng, st_ptr), H, N, L, S)
+            b0 = sum(counts[:rank])
+            enc = (rows, n_eff, lens_all)
+            job = eng.dist_open_encoded(rows.data_ptr(), n_eff.data_ptr(), lens_all.data_ptr(), rows.shape[0], b0, counts[rank],
+                                        sketch_size=S, k=K, kmer_space=p.kmer_space, keepalive=enc)
+        else:
+            dstat = None
+            ref_set = mash_b200._capi._Set(H.data_ptr(), N.data_ptr(), L.data_ptr(), on_device=True, n=H.shape[0], stride=S)
+            job = mash_b200._capi.DistJob(eng, ref_set, None, None, None, None, None, S, K, p.kmer_space, 1.0, 1.0)
+        torch.cuda.synchronize()
+        open_ms = max_over_ranks((time.perf_counter() - t_open) * 1e3)
         n_ref, n_qry = job.n_ref, job.n_qry
         q_tile = max(1, min(n_qry, (1 << 29) // max(1, n_ref)))   # 2^29 pairs = 13.4 GB of dense outputs per launch
         o_numer = torch.empty(q_tile * n_ref, dtype=torch.int32, device=dev)
@@ -505,7 +627,13 @@ def main():
                 job.run_dev(q0, qc, o_numer.data_ptr(), o_denom.data_ptr(), o_dist.data_ptr(), o_p.data_ptr(), o_pass.data_ptr(), stream=st_ptr)
 
         dW = min(W, 1) if n_ref * n_qry >= 10 ** 9 else W
-        for _ in range(dW):
+        barrier()
+        e0.record(st)
+        dist_step()                               # the first pass of the job (also the first warm-up step)
+        e1.record(st)
+        barrier()
+        first_pass_ms = max_over_ranks(e0.elapsed_time(e1))
+        for _ in range(max(0, dW - 1)):
             dist_step()
         eng.set_timing(True); eng.stats(reset=True)
         barrier()
@@ -555,13 +683,18 @@ def main():
         dist_obj = {"metric": "sketch_pairs_per_s", "value": total_pairs / (dms * 1e-3), "unit": "pairs/s", "ms_per_step": dms,
                     "steps": dK, "warmup": dW, "pairs_per_step": total_pairs, "enumeration": "all ordered pairs (full Q x R grid)",
                     "workload": f"configs[2]: {n_sk} synthetic s={S} sketches all-vs-all, 100 families stored family by family (SURVEY.md 8d generator); "
-                                f"reference axis sharded over {world} rank(s)",
+                                f"reference axis sharded over {world} rank(s), every rank compares all {n_sk} queries with its shard",
                     "outputs": "dense numer,denom (u32), distance,pvalue (f64), pass (u8) = 25 B/pair written to an HBM tile buffer that is reused per query tile",
                     "algorithm": "tile prefilter (cuckoo filter per 32-reference tile; closed form for pairs without shared hashes) + sorted merge of the "
                                  "rest + dense p-value pass; results identical to merging every pair (tests/test_gpu_dist_prefilter.py)",
                     "prefilter": {"query_tile_combinations_probed": pf["combos_probed"], "sent_to_merge": pf["combos_flagged"],
                                   "fraction_merged": (pf["combos_flagged"] / pf["combos_probed"]) if pf["combos_probed"] else None},
-                    "dict_build_ms": open_ms, "query_broadcast_ms": bcast_ms,
+                    "one_off_ms": open_ms, "first_pass_ms": first_pass_ms,
+                    "value_first_pass_incl_one_off": total_pairs / ((open_ms + first_pass_ms) * 1e-3),
+                    "one_off": ("dictionary build inside mashgpu_dist_open (radix sort of all hashes)" if not dist_on else
+                                "sharded dictionary build: local sort, all-to-all by hash range, ranking, all-to-all back, all-gather of the encoded rows "
+                                "(mash_b200/shard.py sharded_dictionary), then mashgpu_dist_open_encoded; wall clock, max over ranks"),
+                    "sharded_dictionary": dstat,
                     "kernel_ms_per_step": dstats["dist_kernel_ms"] / dK, "gpu_launches": int(dstats["kernel_launches"]),
                     "pairs_with_shared_hashes_in_last_tile": last_shared_nonzero,
                     "roofline": {"bound": "hbm", "achieved": (total_pairs / world * 25 + (n_ref + n_qry) * S * 4) / (dstats["dist_kernel_ms"] / dK * 1e-3) / 1e9,
@@ -586,10 +719,94 @@ def main():
         dist_obj["side_measurements"] = side
         dist_obj["triangle"] = tri
 
+        # ---------------- configs[4]: 1 M sketches all-vs-all, one pass from raw hashes to pass lists on the host ----------
+        if not args.skip_dist5:
+            del o_numer, o_denom, o_dist, o_p, o_pass, enc
+            torch.cuda.empty_cache()
+            import ctypes as C
+            n5 = args.sketches5
+            shard5 = (n5 + world - 1) // world
+            H5, N5, L5 = make_sketches_device(torch, dev, shard5, S, seed=5000 + rank, n_families=max(1, shard5 // 1000))
+            cap5 = 1 << 22
+            l_idx = torch.empty(cap5, dtype=torch.int64, pin_memory=True); l_num = torch.empty(cap5, dtype=torch.int32, pin_memory=True)
+            l_den = torch.empty(cap5, dtype=torch.int32, pin_memory=True); l_dist = torch.empty(cap5, dtype=torch.float64, pin_memory=True)
+            l_pv = torch.empty(cap5, dtype=torch.float64, pin_memory=True)
+            max_d5 = 0.05
+            eng.set_timing(True); eng.stats(reset=True)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            if dist_on:
+                rows5, neff5, lens5, counts5, dstat5 = sharded_dictionary(DictOps(eng, st_ptr), H5, N5, L5, S)
+                job5 = eng.dist_open_encoded(rows5.data_ptr(), neff5.data_ptr(), lens5.data_ptr(), rows5.shape[0], sum(counts5[:rank]), counts5[rank],
+                                             sketch_size=S, k=K, kmer_space=p.kmer_space, max_distance=max_d5, max_pvalue=1.0, keepalive=(rows5, neff5, lens5))
+            else:
+                dstat5 = None
+                set5 = mash_b200._capi._Set(H5.data_ptr(), N5.data_ptr(), L5.data_ptr(), on_device=True, n=H5.shape[0], stride=S)
+                job5 = mash_b200._capi.DistJob(eng, set5, None, None, None, None, None, S, K, p.kmer_space, max_d5, 1.0)
+            torch.cuda.synchronize()
+            t_dict = time.perf_counter() - t0
+            n_ref5, n_qry5 = job5.n_ref, job5.n_qry
+            q_tile5 = max(1, min(n_qry5, (1 << 29) // max(1, n_ref5)))
+            n_pass_total, n_tiles5, max_tile_pass = 0, 0, 0
+            npass = C.c_uint64(0)
+            u64p, u32p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+            for q0 in range(0, n_qry5, q_tile5):
+                qc = min(q_tile5, n_qry5 - q0)
+                eng._check(eng.lib.mashgpu_dist_run_list(job5.h, q0, qc, cap5, C.cast(l_idx.data_ptr(), u64p), C.cast(l_num.data_ptr(), u32p),
+                                                         C.cast(l_den.data_ptr(), u32p), C.cast(l_dist.data_ptr(), f64p), C.cast(l_pv.data_ptr(), f64p), C.byref(npass)))
+                if npass.value > cap5:
+                    raise SystemExit(f"dist5: pass list of a tile ({npass.value}) exceeds the capacity {cap5}")
+                n_pass_total += npass.value; n_tiles5 += 1; max_tile_pass = max(max_tile_pass, npass.value)
+            torch.cuda.synchronize()
+            t_rank = time.perf_counter() - t0
+            barrier()
+            dt5 = max_over_ranks(t_rank)
+            t_dict = max_over_ranks(t_dict)
+            st5 = eng.stats(reset=True)
+            eng.set_timing(False)
+            pf5 = job5.prefilter_stats()
+            pass_all = n_pass_total
+            if dist_on:
+                tt = torch.tensor([n_pass_total], dtype=torch.int64, device=dev)
+                td.all_reduce(tt)
+                pass_all = int(tt.item())
+            last_ok = bool(npass.value == 0 or (l_dist[:npass.value] <= max_d5).all().item())
+            pairs5 = n_ref5 * n_qry5 * world
+            dist5_obj = {"metric": "sketch_pairs_per_s", "value": pairs5 / dt5, "unit": "pairs/s", "seconds": dt5,
+                         "workload": f"configs[4]: {shard5 * world} synthetic s={S} sketches all-vs-all ({shard5 * world // 1000} families of 1000, configs[2] generator), "
+                                     f"reference axis sharded over {world} rank(s), every rank compares all queries with its {shard5} references",
+                         "pairs": pairs5, "enumeration": "all ordered pairs (full Q x R grid)",
+                         "timed_region": "ONE pass from the raw uint64 hashes in HBM to the last pass list in pinned host memory: dictionary build "
+                                         f"({'sharded sample sort + all-gather of encoded rows' if dist_on else 'mashgpu_dist_open'}), probe + merge + p-value kernels for every "
+                                         "query tile, list sort by pair index, D2H of the lists; wall clock, max over ranks",
+                         "outputs": f"compacted pass list of `-d {max_d5}` (pair index, numer, denom, distance, p-value = 32 B per passing pair) in the reference's "
+                                    "output order per query tile (CommandDistance.cpp:247-304 prints only passing pairs); dense outputs would be 25 TB",
+                         "dictionary_and_exchange_seconds": t_dict, "kernel_seconds_this_rank": st5["dist_kernel_ms"] / 1e3,
+                         "query_tiles": n_tiles5, "queries_per_tile": q_tile5, "passing_pairs": pass_all, "largest_tile_list": max_tile_pass,
+                         "last_list_within_max_distance": last_ok, "gpu_launches": int(st5["kernel_launches"]),
+                         "prefilter": {"query_tile_combinations_probed": pf5["combos_probed"], "sent_to_merge": pf5["combos_flagged"],
+                                       "fraction_merged": (pf5["combos_flagged"] / pf5["combos_probed"]) if pf5["combos_probed"] else None},
+                         "sharded_dictionary": dstat5,
+                         "hbm_roofline_note": "algorithmic HBM bytes = rank rows read once per reference tile pass (L2-resident re-reads) + 32 B per passing pair: "
+                                              "far below the HBM roofline; the probe kernel's shared-memory lookups bound this workload (DESIGN.md 3.3)"}
+            job5.close()
+            del H5, N5, L5, l_idx, l_num, l_den, l_dist, l_pv
+            if dist_on:
+                del rows5, neff5, lens5
+            torch.cuda.empty_cache()
+
         # ---------------- hot path 3: screen (configs[3], rank 0's sketches as the reference .msh) -----------------
         if not args.skip_screen:
-            del o_numer, o_denom, o_dist, o_p, o_pass
+            if args.skip_dist5:
+                del o_numer, o_denom, o_dist, o_p, o_pass
             torch.cuda.empty_cache()
+            if dist_on:
+                from mash_b200.shard import _all_gather
+                QH = _all_gather(H, world).view(-1, S); QL = _all_gather(L, world).view(-1)
+                QN = torch.full((QH.shape[0],), S, dtype=torch.int32, device=dev)
+            else:
+                QH, QN, QL = H, N, L
             n_reads, read_len = args.reads, 150
             span_r = read_len + 1
             # reads: '*' + 150 bases drawn as substrings of the genome pool (0.5 % substitutions, 0.1 % N), all on the device
@@ -671,18 +888,18 @@ def main():
                "sample": f"{n_cpu} genomes x {glen} bp, one job per genome on {cores} threads (the faster of one thread per usable CPU -- the "
                          f"container's quota -- and one per visible CPU), {dt:.1f} s wall; reference MurmurHash3/hash/MinHashHeap "
                          "object code (oracle/_ref), restated addMinHashes loop, in-memory input"}
+        cpu.update(cpu_arms(cores))
 
     if rank == 0:
         line = {"metric": "Gbp_per_s_sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic",
-                "config": {"workload": f"configs[1]: {n_units} synthetic genomes x {glen} bp per GPU, k={K} s={S} seed={SEED}, canonical, ASCII input "
-                                       "(every 10th genome with 20 N-runs and 5% lower case)",
+                "config": {"workload": WORKLOAD_SKETCH.format(units=n_units, glen=glen),
                            "k": K, "s": S, "units_per_gpu": n_units, "genome_len": glen,
                            "l2": "inputs larger than L2 (one step streams %.1f GB)" % (bases_per_step / 1e9),
                            "parallelism": f"records sharded over {world} rank(s), no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]),
-                "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "screen": screen_obj, "sanity": sanity,
+                "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "dist5": dist5_obj, "screen": screen_obj, "sanity": sanity,
                 "exact_reruns": int(stats["exact_reruns"])}
         emit_json_line(line)
     if dist_on:

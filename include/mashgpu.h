@@ -149,7 +149,9 @@ int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mas
  * Any output pointer may be NULL.  Host buffers. */
 int mashgpu_dist_run(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
                      uint32_t *numer, uint32_t *denom, double *distance, double *pvalue, uint8_t *pass);
-/* Same with device output buffers, enqueued on `stream` (cudaStream_t, NULL = context stream). */
+/* Same with device output buffers, enqueued on `stream` (cudaStream_t, NULL = context stream).  A job holds one set of
+ * scratch buffers (work lists, deferred p-value queue, pass list): at most ONE run of a job may be in flight -- enqueue the
+ * runs of a job on a single stream, or synchronise between runs on different streams. */
 int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
                          uint32_t *d_numer, uint32_t *d_denom, double *d_distance, double *d_pvalue, uint8_t *d_pass,
                          void *stream);
@@ -178,6 +180,41 @@ int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode);
 /* Counters of the prefilter since the job was opened: (query, tile) combinations probed, those that went on to the merge,
  * and whether the next run would probe.  Synchronises the device.  Any pointer may be NULL. */
 int mashgpu_dist_prefilter_stats(mashgpu_dist_job *job, uint64_t *combos_probed, uint64_t *combos_flagged, int *active);
+
+/* ---- Sharded dictionary build (multi-GPU all-vs-all).  With the reference axis sharded over G ranks the
+ * dictionary of mashgpu_dist_open would be rebuilt in full on every rank.  These entry points split it by HASH RANGE
+ * instead (a sample sort): a rank sorts only its own rows' hashes, the sorted keys are cut at G-1 splitters, every rank
+ * receives one hash range from all ranks (the caller's all-to-all, NCCL), ranks the distinct values of its range, and the
+ * 32-bit codes travel back; the owners scatter them into rows of sketch_size+1 codes which are then all-gathered (4 B per
+ * hash instead of 8) and opened with mashgpu_dist_open_encoded.  Codes of range d are offset by the number of distinct
+ * values in the ranges below it, so the encoding is order- and equality-preserving over the whole collection, which is
+ * all the merge of compareSketches (CommandDistance.cpp:347-365) depends on.  All pointers named d_* are device memory;
+ * `stream` is a cudaStream_t (NULL = the context's stream); the calls that return a host value synchronise it. */
+/* Hashes i < min(n_hashes, sketch_size+1, stride) of every row, ascending, with their slot row * (sketch_size+1) + i.
+ * d_keys / d_slots must hold set->n * min(stride, sketch_size+1) entries; *n_valid = number of entries written. */
+int mashgpu_dict_local_sort(mashgpu_ctx *ctx, const mashgpu_sketch_set *set, uint64_t sketch_size,
+                            uint64_t *d_keys, uint32_t *d_slots, uint64_t *n_valid, void *stream);
+/* counts[p] = number of keys of the ascending list d_keys[0..n) in part p of n_parts: part p holds
+ * splitters[p-1] <= key < splitters[p] (splitters: host array of n_parts-1 ascending values). */
+int mashgpu_dict_split(mashgpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, const uint64_t *splitters, uint32_t n_parts,
+                       uint64_t *counts, void *stream);
+/* d_codes[t] = number of distinct keys smaller than d_keys[t] (any order of d_keys; equal keys get equal codes);
+ * *n_distinct = number of distinct keys. */
+int mashgpu_dict_rank(mashgpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, uint32_t *d_codes, uint64_t *n_distinct, void *stream);
+/* Rows of sketch_size+1 codes from the codes of this rank's sorted keys: entry t (in the order of mashgpu_dict_local_sort)
+ * belongs to segment g = the part it was sent to (seg_counts[g] consecutive entries, host arrays of n_segs) and becomes
+ * d_rows[d_slots[t]] = d_codes[t] + seg_base[g]; every other position of the n_rows rows is the padding code 0xFFFFFFFF.
+ * d_n_eff[row] = min(n_hashes, sketch_size+1, stride).  Fails when a code would reach the padding value. */
+int mashgpu_dict_scatter(mashgpu_ctx *ctx, const uint32_t *d_codes, const uint32_t *d_slots, const uint64_t *seg_counts,
+                         const uint64_t *seg_base, uint32_t n_segs, const mashgpu_sketch_set *set, uint64_t sketch_size,
+                         uint32_t *d_rows, uint32_t *d_n_eff, void *stream);
+/* A job over rows that are already dictionary-encoded (device memory, owned by the caller, must outlive the job):
+ * n_rows rows of sketch_size+1 codes, d_n_eff / d_length per row.  The queries are all n_rows rows, the references rows
+ * [ref_begin, ref_begin + ref_count): pair (q, r) of a run is query row q against row ref_begin + r, written at
+ * (q - q_begin) * ref_count + r.  mashgpu_dist_set_triangle compares q with rows below it only (ref_begin + r < q). */
+int mashgpu_dist_open_encoded(mashgpu_ctx *ctx, const uint32_t *d_rows, const uint32_t *d_n_eff, const uint64_t *d_length,
+                              uint64_t n_rows, uint64_t ref_begin, uint64_t ref_count, const mashgpu_dist_params *params,
+                              mashgpu_dist_job **job);
 
 /* One-shot convenience: open + run over all queries + close (the whole `compare` grid). */
 int mashgpu_dist(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mashgpu_sketch_set *qry,
@@ -216,6 +253,12 @@ int mashgpu_screen_set_winner(mashgpu_screen_job *job, int on);
  * per-thread heaps the same way, CommandScreen.cpp:288-302).  Then mashgpu_screen_finish as usual. */
 int mashgpu_screen_counters(mashgpu_screen_job *job, uint32_t **d_counters, uint64_t *n_counters);
 int mashgpu_screen_merge_mixture(mashgpu_screen_job *job, const uint64_t *hashes, uint32_t n);
+/* The same without a host round trip per rank: *d_mix / *d_mix_n expose the running bottom-s list (sketch_size uint64 slots,
+ * ascending, *d_mix_n of them valid) for an all-gather; mashgpu_screen_merge_mixtures_dev folds n_lists lists lying in
+ * device memory (list i = d_hashes[i * stride ...], d_n[i] ascending distinct hashes; the job's own list may be among
+ * them) into the job's list with one kernel and one read-back of the new top. */
+int mashgpu_screen_mixture_dev(mashgpu_screen_job *job, uint64_t **d_mix, uint32_t **d_mix_n);
+int mashgpu_screen_merge_mixtures_dev(mashgpu_screen_job *job, const uint64_t *d_hashes, const uint32_t *d_n, uint32_t n_lists, uint64_t stride);
 int mashgpu_screen_close(mashgpu_screen_job *job);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -101,6 +101,15 @@ def load_library():
     L.mashgpu_screen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), u64p]
     L.mashgpu_screen_merge_mixture.argtypes = [C.c_void_p, u64p, C.c_uint32]
     L.mashgpu_screen_close.argtypes = [C.c_void_p]
+    L.mashgpu_screen_mixture_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.mashgpu_screen_merge_mixtures_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+    L.mashgpu_dict_local_sort.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.c_uint64, C.c_void_p, C.c_void_p, u64p, C.c_void_p]
+    L.mashgpu_dict_split.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, C.c_uint32, u64p, C.c_void_p]
+    L.mashgpu_dict_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p, C.c_void_p]
+    L.mashgpu_dict_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, C.c_uint32, C.POINTER(SketchSet), C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_dist_open_encoded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                            C.POINTER(DistParams), C.POINTER(C.c_void_p)]
     L.mashgpu_screen_set_winner.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
@@ -221,6 +230,36 @@ class Engine:
                   max_distance=1.0, max_pvalue=1.0):
         return DistJob(self, ref, ref_n, ref_len, qry, qry_n, qry_len, sketch_size, k, kmer_space, max_distance, max_pvalue)
 
+    def dist_open_encoded(self, d_rows, d_n_eff, d_length, n_rows, ref_begin, ref_count, *, sketch_size, k, kmer_space,
+                          max_distance=1.0, max_pvalue=1.0, keepalive=None):
+        """Job over dictionary-encoded rows in device memory (pointers); references = rows [ref_begin, ref_begin + ref_count)."""
+        return DistJob.encoded(self, d_rows, d_n_eff, d_length, n_rows, ref_begin, ref_count, sketch_size, k, kmer_space,
+                               max_distance, max_pvalue, keepalive)
+
+    # ---- sharded dictionary build (device pointers; see mash_b200/shard.py) ----------------------------------
+    def dict_local_sort(self, d_hashes, d_n_hashes, n, stride, sketch_size, d_keys, d_slots, stream=None):
+        st = SketchSet(n, stride, d_hashes, d_n_hashes, None, 1)
+        nv = C.c_uint64(0)
+        self._check(self.lib.mashgpu_dict_local_sort(self.h, C.byref(st), sketch_size, d_keys, d_slots, C.byref(nv), stream))
+        return nv.value
+
+    def dict_split(self, d_keys, n, splitters, stream=None):
+        spl = np.ascontiguousarray(splitters, np.uint64)
+        counts = np.zeros(spl.size + 1, np.uint64)
+        self._check(self.lib.mashgpu_dict_split(self.h, d_keys, n, _p(spl, u64p), spl.size + 1, _p(counts, u64p), stream))
+        return [int(c) for c in counts]
+
+    def dict_rank(self, d_keys, n, d_codes, stream=None):
+        nd = C.c_uint64(0)
+        self._check(self.lib.mashgpu_dict_rank(self.h, d_keys, n, d_codes, C.byref(nd), stream))
+        return nd.value
+
+    def dict_scatter(self, d_codes, d_slots, seg_counts, seg_base, d_n_hashes, n, stride, sketch_size, d_rows, d_n_eff, stream=None):
+        sc = np.ascontiguousarray(seg_counts, np.uint64); sb = np.ascontiguousarray(seg_base, np.uint64)
+        st = SketchSet(n, stride, 1, d_n_hashes, None, 1)          # the hashes themselves are not read again
+        self._check(self.lib.mashgpu_dict_scatter(self.h, d_codes, d_slots, _p(sc, u64p), _p(sb, u64p), sc.size, C.byref(st), sketch_size,
+                                                  d_rows, d_n_eff, stream))
+
     # ---- hot path 3 ----------------------------------------------------------------------------------------
     def screen_open(self, ref, ref_n, p, ref_len=None):
         return ScreenJob(self, ref, ref_n, p, ref_len)
@@ -251,6 +290,20 @@ class DistJob:
         eng._check(eng.lib.mashgpu_dist_open(eng.h, C.byref(self._ref.c), C.byref(self._qry.c) if self._qry is not None else None,
                                              C.byref(self.params), C.byref(h)))
         self.h = h
+
+    @classmethod
+    def encoded(cls, eng, d_rows, d_n_eff, d_length, n_rows, ref_begin, ref_count, sketch_size, k, kmer_space, max_distance, max_pvalue,
+                keepalive=None):
+        self = cls.__new__(cls)
+        self.eng = eng
+        self._ref = keepalive        # the caller's device arrays must outlive the job
+        self._qry = None
+        self.n_ref, self.n_qry = int(ref_count), int(n_rows)
+        self.params = DistParams(sketch_size, k, kmer_space, max_distance, max_pvalue)
+        h = C.c_void_p()
+        eng._check(eng.lib.mashgpu_dist_open_encoded(eng.h, d_rows, d_n_eff, d_length, n_rows, ref_begin, ref_count, C.byref(self.params), C.byref(h)))
+        self.h = h
+        return self
 
     def run(self, q_begin, q_count):
         n = q_count * self.n_ref
@@ -322,6 +375,15 @@ class ScreenJob:
     def merge_mixture(self, hashes):
         h = np.ascontiguousarray(hashes, np.uint64)
         self.eng._check(self.eng.lib.mashgpu_screen_merge_mixture(self.h, _p(h, u64p), h.size))
+
+    def mixture_dev(self):
+        """(device pointer of the running bottom-s list, device pointer of its length) for an all-gather across ranks."""
+        a = C.c_void_p(); b = C.c_void_p()
+        self.eng._check(self.eng.lib.mashgpu_screen_mixture_dev(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def merge_mixtures_dev(self, d_hashes, d_n, n_lists, stride):
+        self.eng._check(self.eng.lib.mashgpu_screen_merge_mixtures_dev(self.h, d_hashes, d_n, n_lists, stride))
 
     def mixture(self):
         """The running bottom-s list of the mixture (ascending u64)."""

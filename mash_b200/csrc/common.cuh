@@ -107,10 +107,13 @@ struct DevBuf {
     cudaError_t alloc(size_t count)
     {
         release();
+        const cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); return e; }    // n stays 0: a later `n < need` test re-allocates
         n = count;
-        if (count == 0) count = 1;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        return e;
     }
+    // grow-only: keeps the buffer when it already holds `count` entries
+    cudaError_t reserve(size_t count) { return (p && n >= count) ? cudaSuccess : alloc(count + count / 4); }
 };
 
 template <typename T>
@@ -125,9 +128,10 @@ struct PinnedBuf {
     cudaError_t alloc(size_t count)
     {
         release();
+        const cudaError_t e = cudaMallocHost((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); return e; }
         n = count;
-        if (count == 0) count = 1;
-        return cudaMallocHost((void **)&p, count * sizeof(T));
+        return e;
     }
 };
 

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <memory>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -63,7 +64,8 @@ struct DistArgs {
     uint32_t *qlist; uint32_t *qcount; uint64_t qlist_stride; unsigned long long *flag_total;
     int use_qlist;              // dist_kernel: take the queries of a tile from qlist instead of the dense range
     int probe_prefetch;         // dist_probe_kernel: request the query lines two groups ahead into L1
-    int triangle;               // self comparison, lower triangle only: pairs with r >= q are neither computed nor written
+    int triangle;               // lower triangle only: pairs with tri_r0 + r >= q are neither computed nor written
+    uint32_t tri_r0;            // row of reference 0 in the query numbering (0 for a self comparison; the shard offset of an encoded job)
     // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
     struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
 };
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
         for (int c = 0; c < DIST_ILP; c++) {
             const uint32_t item = ib + c;
             qs[c] = item < it_hi ? (my_list ? my_list[item] : a.q_begin + item) : 0xFFFFFFFFu;
-            if (a.triangle && qs[c] <= r0) qs[c] = 0xFFFFFFFFu;        // the whole tile lies on or above the diagonal
+            if (a.triangle && qs[c] <= a.tri_r0 + r0) qs[c] = 0xFFFFFFFFu;        // the whole tile lies on or above the diagonal
             all_skipped &= qs[c] == 0xFFFFFFFFu;
         }
         if (all_skipped) continue;                      // warp-uniform
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
             const uint32_t q = qs[c];
-            if (q == 0xFFFFFFFFu || !r_ok || (a.triangle && r >= q)) continue;
+            if (q == 0xFFFFFFFFu || !r_ok || (a.triangle && a.tri_r0 + r >= q)) continue;
             const uint32_t i_end = (pa[c] - sref_base) / (DIST_TILE_R * 4);
             const uint32_t j_end = (pb[c] - pb0[c]) / 4;
             const uint32_t bogus = i_end > nA ? i_end - nA : 0;   // steps that consumed padding on both sides
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     const uint8_t pass_const = (far || (a.max_pvalue >= 0 && 1.0 > a.max_pvalue)) ? 0 : 1;
 
     for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
-        if (a.triangle && q <= r0) continue;            // the whole tile lies on or above the diagonal
+        if (a.triangle && q <= a.tri_r0 + r0) continue;            // the whole tile lies on or above the diagonal
         const uint32_t nB_all = a.qry_n[q];
         const uint32_t nB = min(nB_all, a.S);
         const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
@@ -384,10 +386,12 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
                 a.qlist[(uint64_t)blockIdx.x * a.qlist_stride + at] = q;
                 atomicAdd(a.flag_total, 1ull);
             }
-        } else if (r_ok && !(a.triangle && r >= q)) {
+        } else if (r_ok && !(a.triangle && a.tri_r0 + r >= q)) {
             // empty intersection: the merge would take min(s', |A| + |B|) union steps and count nothing
             const uint32_t denom = min(a.S, nA + nB_all);
-            if (denom == a.S && !a.list_idx) {
+            if (denom == a.S && a.list_idx && pass_const == 0) {
+                // filtered run (-d / -v) and distance 1 / p-value 1 does not pass: nothing to write for this pair
+            } else if (denom == a.S && !a.list_idx) {
                 const uint64_t o = (uint64_t)(q - a.q_begin) * a.n_ref + r;
                 if (a.numer) a.numer[o] = 0;
                 if (a.denom) a.denom[o] = denom;
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
     const uint64_t total = (uint64_t)a.q_count * a.n_ref;
     if (t >= total) return;
     const uint32_t q = a.q_begin + (uint32_t)(t / a.n_ref), r = (uint32_t)(t % a.n_ref);
-    if (a.triangle && r >= q) return;
+    if (a.triangle && a.tri_r0 + r >= q) return;
     const uint32_t *A = a.ranks + (a.ref_row0 + r) * (uint64_t)a.P;
     const uint32_t *B = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
     uint32_t i = 0, j = 0;
@@ -429,19 +433,26 @@ __global__ void __launch_bounds__(256) dist_kernel_general(const DistArgs a)
 // ---------------------------------------------------------------------------------------------------------
 // dictionary encoding
 // ---------------------------------------------------------------------------------------------------------
-// keys[row*P + i] = hash i of the row (or all-ones padding); idx = slot id
-__global__ void dict_gather_kernel(const uint64_t *hashes, uint64_t stride, const uint32_t *n_hashes, uint64_t n_rows,
-                                   uint32_t P, uint64_t row0, uint64_t *keys, uint32_t *idx, uint32_t *n_eff)
+// n_eff[row0 + row] = number of hashes of the row that take part: min(n_hashes, P, stride)
+__global__ void dict_neff_kernel(const uint32_t *n_hashes, uint64_t n_rows, uint32_t P, uint64_t stride, uint64_t row0, uint32_t *n_eff)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    n_eff[row0 + t] = (uint32_t)min((uint64_t)min(n_hashes[t], P), stride);
+}
+
+// valid hashes only, compacted: entry off[row] + i = hash i of the row, with its slot (row0 + row) * P + i
+__global__ void dict_gather_kernel(const uint64_t *hashes, uint64_t stride, uint64_t n_rows, uint32_t P, uint64_t row0,
+                                   const uint32_t *n_eff, const uint32_t *off, uint64_t out0, uint64_t *keys, uint32_t *slots)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= n_rows * P) return;
     const uint64_t row = t / P;
     const uint32_t i = (uint32_t)(t % P);
-    const uint32_t n = min(n_hashes[row], P);
-    const uint64_t slot = (row0 + row) * P + i;
-    keys[slot] = (i < n && i < stride) ? hashes[row * stride + i] : 0xFFFFFFFFFFFFFFFFULL;
-    idx[slot] = (uint32_t)slot;
-    if (i == 0) n_eff[row0 + row] = min(n, (uint32_t)min((uint64_t)P, stride));
+    if (i >= n_eff[row0 + row]) return;
+    const uint64_t o = out0 + off[row] + i;
+    keys[o] = hashes[row * stride + i];
+    slots[o] = (uint32_t)((row0 + row) * P + i);
 }
 
 __global__ void dict_flag_kernel(const uint64_t *sorted_keys, uint64_t n, uint32_t *flags)
@@ -451,14 +462,39 @@ __global__ void dict_flag_kernel(const uint64_t *sorted_keys, uint64_t n, uint32
     flags[t] = (t == 0 || sorted_keys[t] != sorted_keys[t - 1]) ? 1u : 0u;
 }
 
-__global__ void dict_scatter_kernel(const uint32_t *sorted_idx, const uint32_t *scan, uint64_t n, uint32_t P,
-                                    const uint32_t *n_eff, uint32_t *ranks)
+// out[value of sorted entry t] = rank of its key among the distinct keys
+__global__ void dict_scatter_kernel(const uint32_t *sorted_vals, const uint32_t *scan, uint64_t n, uint32_t *out)
 {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const uint32_t slot = sorted_idx[t];
-    const uint32_t row = slot / P, i = slot % P;
-    ranks[slot] = (i < n_eff[row]) ? (scan[t] - 1u) : RANK_PAD;
+    out[sorted_vals[t]] = scan[t] - 1u;
+}
+
+// sharded build: rows[slots[t]] = codes[t] + base of the segment (hash range) entry t was sent to
+__global__ void dict_scatter_seg_kernel(const uint32_t *codes, const uint32_t *slots, uint64_t n, const uint64_t *seg_end, const uint64_t *seg_base,
+                                        uint32_t n_segs, uint32_t *rows, uint32_t *err)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint32_t g = 0;
+    while (g + 1 < n_segs && t >= seg_end[g]) g++;
+    const uint64_t c = (uint64_t)codes[t] + seg_base[g];
+    if (c >= 0xFFFFFFFFull) { atomicOr(err, 1u); return; }
+    rows[slots[t]] = (uint32_t)c;
+}
+
+// lower bounds of the splitters in an ascending key list
+__global__ void dict_split_kernel(const uint64_t *keys, uint64_t n, const uint64_t *splitters, uint32_t n_split, uint64_t *pos)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_split) return;
+    const uint64_t v = splitters[t];
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    pos[t] = lo;
 }
 
 __global__ void list_gather_kernel(const uint32_t *order, uint64_t n, const uint32_t *numer, const uint32_t *denom, const double *distance,
@@ -486,6 +522,10 @@ struct mashgpu_dist_job {
     uint64_t n_ref = 0, n_qry = 0;
     bool self = false;
     uint32_t P = 0;
+    // rank rows: views used by the kernels (into the buffers below, or the caller's arrays for mashgpu_dist_open_encoded)
+    const uint32_t *d_ranks = nullptr, *d_n_eff = nullptr;
+    const uint64_t *d_lens = nullptr;
+    uint64_t ref_row0 = 0, qry_row0 = 0;     // first row of each set
     DevBuf<uint32_t> ranks, n_eff;
     DevBuf<uint64_t> lens;          // ref lengths then query lengths
     DevBuf<double> lut, binom_m;
@@ -494,6 +534,9 @@ struct mashgpu_dist_job {
     // pass-list target of the next run (set by mashgpu_dist_run_list only)
     uint64_t *list_idx = nullptr; uint32_t *list_numer = nullptr, *list_denom = nullptr; double *list_distance = nullptr, *list_pvalue = nullptr;
     unsigned long long *list_count = nullptr; uint64_t list_capacity = 0;
+    // grow-only buffers of mashgpu_dist_run_list (no cudaMalloc per call after the first)
+    DevBuf<uint64_t> l_idx, s_idx; DevBuf<uint32_t> l_n, l_d, l_order, s_order, o_n, o_d; DevBuf<double> l_D, l_P, o_D, o_P;
+    DevBuf<unsigned long long> l_cnt; DevBuf<uint8_t> l_tmp;
     // prefilter (dist_probe_kernel): -1 = auto (on; switched off when most combinations turn out to share hashes), 0 = off, 1 = on
     int prefilter_mode = -1;
     bool triangle = false;
@@ -522,22 +565,138 @@ struct SetOnDevice {
     DevBuf<uint64_t> h, l; DevBuf<uint32_t> n;
 };
 
-int stage_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, SetOnDevice &d, cudaStream_t st)
+int stage_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, SetOnDevice &d, cudaStream_t st, bool want_length = true)
 {
     if (s->on_device) { d.hashes = s->hashes; d.n_hashes = s->n_hashes; d.length = s->length; return MASHGPU_OK; }
-    if (d.h.alloc(s->n * s->stride) != cudaSuccess || d.n.alloc(s->n) != cudaSuccess || d.l.alloc(s->n) != cudaSuccess)
+    if (d.h.alloc(s->n * s->stride) != cudaSuccess || d.n.alloc(s->n) != cudaSuccess || (want_length && d.l.alloc(s->n) != cudaSuccess))
         return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sketch set of %llu x %llu)", (unsigned long long)s->n, (unsigned long long)s->stride);
     MG_CUDA(ctx, cudaMemcpyAsync(d.h.p, s->hashes, s->n * s->stride * 8, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaMemcpyAsync(d.n.p, s->n_hashes, s->n * 4, cudaMemcpyHostToDevice, st));
-    MG_CUDA(ctx, cudaMemcpyAsync(d.l.p, s->length, s->n * 8, cudaMemcpyHostToDevice, st));
+    if (want_length) MG_CUDA(ctx, cudaMemcpyAsync(d.l.p, s->length, s->n * 8, cudaMemcpyHostToDevice, st));
     d.hashes = d.h.p; d.n_hashes = d.n.p; d.length = d.l.p;
     return MASHGPU_OK;
 }
 
-int check_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, const char *what)
+int check_set(mashgpu_ctx *ctx, const mashgpu_sketch_set *s, const char *what, bool want_length = true)
 {
     if (!s) return fail(ctx, MASHGPU_ERR_INVALID, "%s set is NULL", what);
-    if (s->n && (!s->hashes || !s->n_hashes || !s->length)) return fail(ctx, MASHGPU_ERR_INVALID, "%s set has NULL arrays", what);
+    if (s->n && (!s->hashes || !s->n_hashes || (want_length && !s->length))) return fail(ctx, MASHGPU_ERR_INVALID, "%s set has NULL arrays", what);
+    return MASHGPU_OK;
+}
+
+inline unsigned blocks_for(uint64_t n, unsigned tb = 256) { return (unsigned)std::max<uint64_t>(1, (n + tb - 1) / tb); }
+
+// Valid hashes of a device-resident set -> keys[out0 ...] / slots[out0 ...] (compacted, row order); n_eff[row0 + row] filled.
+// Returns the number of entries through *n_out (synchronises the stream once to read it).
+int dict_gather(mashgpu_ctx *ctx, const SetOnDevice &d, uint64_t n_rows, uint64_t stride, uint32_t P, uint64_t row0, uint32_t *n_eff,
+                uint64_t out0, uint64_t *keys, uint32_t *slots, uint64_t *n_out, cudaStream_t st)
+{
+    *n_out = 0;
+    if (n_rows == 0) return MASHGPU_OK;
+    if (n_rows * P >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)n_rows, P);
+    DevBuf<uint32_t> off; DevBuf<uint8_t> tmp;
+    if (off.alloc(n_rows + 1) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (row offsets)");
+    dict_neff_kernel<<<blocks_for(n_rows), 256, 0, st>>>(d.n_hashes, n_rows, P, stride, row0, n_eff);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, n_eff + row0, off.p, (int)n_rows, st);
+    if (tmp.alloc(tb) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (scan scratch)");
+    MG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, n_eff + row0, off.p, (int)n_rows, st));
+    uint32_t last_off = 0, last_n = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&last_off, off.p + (n_rows - 1), 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(&last_n, n_eff + row0 + (n_rows - 1), 4, cudaMemcpyDeviceToHost, st));
+    dict_gather_kernel<<<blocks_for(n_rows * P), 256, 0, st>>>(d.hashes, stride, n_rows, P, row0, n_eff, off.p, out0, keys, slots);
+    MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, cudaStreamSynchronize(st));      // off / tmp go out of scope
+    ctx->kernel_launches += 4;
+    *n_out = (uint64_t)last_off + last_n;
+    return MASHGPU_OK;
+}
+
+// out[vals[t]] = rank of keys[t] among the distinct keys (keys in any order; `keys` and `vals` are clobbered).
+// *n_distinct is read back (synchronises the stream).
+int dict_rank(mashgpu_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, uint32_t *out, uint64_t *n_distinct, cudaStream_t st)
+{
+    *n_distinct = 0;
+    if (n == 0) return MASHGPU_OK;
+    if (n >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 hashes in one dictionary sort");
+    DevBuf<uint64_t> keys2; DevBuf<uint32_t> vals2; DevBuf<uint8_t> tmp;
+    if (keys2.alloc(n) != cudaSuccess || vals2.alloc(n) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)n);
+    size_t tmp_sort = 0, tmp_scan = 0;
+    uint32_t *flags = reinterpret_cast<uint32_t *>(keys), *scan = flags + n;        // the unsorted keys are dead after the sort
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys2.p, vals, vals2.p, (int)n, 0, 64, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, flags, scan, (int)n, st);
+    if (tmp.alloc(std::max(tmp_sort, tmp_scan)) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_sort, keys, keys2.p, vals, vals2.p, (int)n, 0, 64, st);
+    if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
+    dict_flag_kernel<<<blocks_for(n), 256, 0, st>>>(keys2.p, n, flags);
+    e = cub::DeviceScan::InclusiveSum(tmp.p, tmp_scan, flags, scan, (int)n, st);
+    if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e));
+    dict_scatter_kernel<<<blocks_for(n), 256, 0, st>>>(vals2.p, scan, n, out);
+    MG_CUDA(ctx, cudaGetLastError());
+    uint32_t nd = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&nd, scan + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(e));
+    ctx->kernel_launches += 12;
+    *n_distinct = nd;
+    return MASHGPU_OK;
+}
+
+// distance LUT, binomial table, kernel attributes and the environment switches: everything of a job but the rank rows
+int dist_job_tables(mashgpu_ctx *ctx, mashgpu_dist_job *job, cudaStream_t st)
+{
+    const mashgpu_dist_params *params = &job->params;
+    const uint64_t S = params->sketch_size;
+    if (job->lut.alloc(S + 1) != cudaSuccess || job->binom_m.alloc(S + 1) != cudaSuccess || job->binom_e.alloc(S + 1) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (distance / binomial tables)");
+    // distance LUT for denom == sketch_size, computed with the host libm exactly as the reference does
+    std::vector<double> lut(S + 1);
+    for (uint64_t c = 0; c <= S; c++) {
+        double d;
+        double j = (double)c / (double)S;
+        if (c == S) d = 0; else if (c == 0) d = 1.; else { d = -log(2 * j / (1. + j)) / params->kmer_size; if (d > 1) d = 1; }
+        lut[c] = d;
+    }
+    MG_CUDA(ctx, cudaMemcpyAsync(job->lut.p, lut.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+    // C(S, x) as mant * 2^expo for the device binomial tail (binom.cuh), running product in long double
+    std::vector<double> bm(S + 1);
+    std::vector<int> be(S + 1);
+    {
+        long double m = 1.0L;
+        int e = 0;
+        bm[0] = 1.0; be[0] = 0;
+        for (uint64_t x = 1; x <= S; x++) {
+            m *= (long double)(S - x + 1) / (long double)x;
+            int k;
+            m = frexpl(m, &k);
+            e += k;
+            bm[x] = (double)m; be[x] = e;
+        }
+    }
+    MG_CUDA(ctx, cudaMemcpyAsync(job->binom_m.p, bm.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(job->binom_e.p, be.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));      // the host vectors go out of scope
+    if (!ctx->attr_dist) {   // per context: function attributes are per device
+        cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(dist_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        ctx->attr_dist = true;
+    }
+    if (const char *env = getenv("MASHGPU_CF_LAZY")) job->lazy_second = atoi(env) != 0;
+    if (const char *env = getenv("MASHGPU_PROBE_PREFETCH")) job->probe_prefetch = atoi(env) != 0;
+    if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
+    // shared memory needed by the merge kernel; larger sketches run dist_kernel_general
+    job->tiled = ((size_t)job->P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * job->P) * 4 <= 227 * 1024;
+    return MASHGPU_OK;
+}
+
+int check_dist_params(mashgpu_ctx *ctx, const mashgpu_dist_params *params)
+{
+    if (params->sketch_size < 1 || params->sketch_size > 0x7FFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size out of range");
+    if (params->kmer_size < 1) return fail(ctx, MASHGPU_ERR_INVALID, "kmer_size out of range");
     return MASHGPU_OK;
 }
 
@@ -551,99 +710,183 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     MG_TRY(check_set(ctx, ref, "reference"));
     const bool self = (qry == nullptr || qry == ref);
     if (!self) MG_TRY(check_set(ctx, qry, "query"));
-    if (params->sketch_size < 1 || params->sketch_size > 0x7FFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size out of range");
-    if (params->kmer_size < 1) return fail(ctx, MASHGPU_ERR_INVALID, "kmer_size out of range");
+    MG_TRY(check_dist_params(ctx, params));
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
-    mashgpu_dist_job *job = new mashgpu_dist_job();
+    std::unique_ptr<mashgpu_dist_job> job(new mashgpu_dist_job());      // every early return below frees the job and its buffers
     job->ctx = ctx; job->params = *params; job->self = self;
     job->n_ref = ref->n; job->n_qry = self ? ref->n : qry->n;
     const uint32_t P = (uint32_t)params->sketch_size + 1;
     job->P = P;
     const uint64_t rows = job->n_ref + (self ? 0 : job->n_qry);
     const uint64_t total = rows * P;
-    auto bail = [&](int rc) { delete job; return rc; };
-    if (total >= 0x7FFFFFFFull) return bail(fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)rows, P));
-    // shared memory needed by the merge kernel
-    job->tiled = ((size_t)P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * P) * 4 <= 227 * 1024;   // else: dist_kernel_general
+    if (total >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)rows, P);
 
     SetOnDevice dr, dq;
-    int rc = stage_set(ctx, ref, dr, st);
-    if (rc) return bail(rc);
-    if (!self && (rc = stage_set(ctx, qry, dq, st))) return bail(rc);
+    MG_TRY(stage_set(ctx, ref, dr, st));
+    if (!self) MG_TRY(stage_set(ctx, qry, dq, st));
 
-    if (job->ranks.alloc(total) != cudaSuccess || job->n_eff.alloc(rows) != cudaSuccess || job->lens.alloc(rows) != cudaSuccess ||
-        job->lut.alloc(params->sketch_size + 1) != cudaSuccess)
-        return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (rank rows)"));
-    if (rows == 0) { *job_out = job; return MASHGPU_OK; }
-    {
-        DevBuf<uint64_t> keys, keys2; DevBuf<uint32_t> idx, idx2, flags, scan; DevBuf<uint8_t> tmp;
-        if (keys.alloc(total) != cudaSuccess || keys2.alloc(total) != cudaSuccess || idx.alloc(total) != cudaSuccess ||
-            idx2.alloc(total) != cudaSuccess || flags.alloc(total) != cudaSuccess || scan.alloc(total) != cudaSuccess)
-            return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)total));
-        const unsigned tb = 256;
-        dict_gather_kernel<<<(unsigned)((job->n_ref * P + tb - 1) / tb), tb, 0, st>>>(dr.hashes, ref->stride, dr.n_hashes, job->n_ref, P, 0, keys.p, idx.p, job->n_eff.p);
-        if (!self && job->n_qry)
-            dict_gather_kernel<<<(unsigned)((job->n_qry * P + tb - 1) / tb), tb, 0, st>>>(dq.hashes, qry->stride, dq.n_hashes, job->n_qry, P, job->n_ref, keys.p, idx.p, job->n_eff.p);
-        size_t tmp_sort = 0, tmp_scan = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys.p, keys2.p, idx.p, idx2.p, (int)total, 0, 64, st);
-        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, flags.p, scan.p, (int)total, st);
-        if (tmp.alloc(std::max(tmp_sort, tmp_scan)) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)"));
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_sort, keys.p, keys2.p, idx.p, idx2.p, (int)total, 0, 64, st);
-        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e)));
-        dict_flag_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(keys2.p, total, flags.p);
-        e = cub::DeviceScan::InclusiveSum(tmp.p, tmp_scan, flags.p, scan.p, (int)total, st);
-        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e)));
-        dict_scatter_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(idx2.p, scan.p, total, P, job->n_eff.p, job->ranks.p);
-        ctx->kernel_launches += 14;
+    if (job->ranks.alloc(total) != cudaSuccess || job->n_eff.alloc(rows) != cudaSuccess || job->lens.alloc(rows) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (rank rows)");
+    job->d_ranks = job->ranks.p; job->d_n_eff = job->n_eff.p; job->d_lens = job->lens.p;
+    job->ref_row0 = 0; job->qry_row0 = self ? 0 : job->n_ref;
+    if (rows) {
+        DevBuf<uint64_t> keys; DevBuf<uint32_t> slots;
+        if (keys.alloc(total) != cudaSuccess || slots.alloc(total) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)total);
+        uint64_t n_r = 0, n_q = 0, n_distinct = 0;
+        MG_TRY(dict_gather(ctx, dr, job->n_ref, ref->stride, P, 0, job->n_eff.p, 0, keys.p, slots.p, &n_r, st));
+        if (!self) MG_TRY(dict_gather(ctx, dq, job->n_qry, qry->stride, P, job->n_ref, job->n_eff.p, n_r, keys.p, slots.p, &n_q, st));
+        MG_CUDA(ctx, cudaMemsetAsync(job->ranks.p, 0xFF, total * 4, st));                  // padding code everywhere, then the real ranks
+        MG_TRY(dict_rank(ctx, keys.p, slots.p, n_r + n_q, job->ranks.p, &n_distinct, st));
+        if (n_distinct >= 0xFFFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^32 - 1 distinct hashes");
         MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p, dr.length, job->n_ref * 8, cudaMemcpyDeviceToDevice, st));
         if (!self && job->n_qry)
             MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p + job->n_ref, dq.length, job->n_qry * 8, cudaMemcpyDeviceToDevice, st));
-        // distance LUT for denom == sketch_size, computed with the host libm exactly as the reference does
-        std::vector<double> lut(params->sketch_size + 1);
-        const uint64_t S = params->sketch_size;
-        for (uint64_t c = 0; c <= S; c++) {
-            double d;
-            double j = (double)c / (double)S;
-            if (c == S) d = 0; else if (c == 0) d = 1.; else { d = -log(2 * j / (1. + j)) / params->kmer_size; if (d > 1) d = 1; }
-            lut[c] = d;
-        }
-        MG_CUDA(ctx, cudaMemcpyAsync(job->lut.p, lut.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
-        // C(S, x) as mant * 2^expo for the device binomial tail (binom.cuh), running product in long double
-        std::vector<double> bm(S + 1);
-        std::vector<int> be(S + 1);
-        {
-            long double m = 1.0L;
-            int e = 0;
-            bm[0] = 1.0; be[0] = 0;
-            for (uint64_t x = 1; x <= S; x++) {
-                m *= (long double)(S - x + 1) / (long double)x;
-                int k;
-                m = frexpl(m, &k);
-                e += k;
-                bm[x] = (double)m; be[x] = e;
-            }
-        }
-        if (job->binom_m.alloc(S + 1) != cudaSuccess || job->binom_e.alloc(S + 1) != cudaSuccess)
-            return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (binomial table)"));
-        MG_CUDA(ctx, cudaMemcpyAsync(job->binom_m.p, bm.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
-        MG_CUDA(ctx, cudaMemcpyAsync(job->binom_e.p, be.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
-        cudaError_t es = cudaStreamSynchronize(st);
-        if (es != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(es)));
     }
-    if (!ctx->attr_dist) {   // per context: function attributes are per device
-        cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
-        e = cudaFuncSetAttribute(dist_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
-        if (e != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
-        ctx->attr_dist = true;
+    MG_TRY(dist_job_tables(ctx, job.get(), st));
+    *job_out = job.release();
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dist_open_encoded(mashgpu_ctx *ctx, const uint32_t *d_rows, const uint32_t *d_n_eff, const uint64_t *d_length,
+                                         uint64_t n_rows, uint64_t ref_begin, uint64_t ref_count, const mashgpu_dist_params *params,
+                                         mashgpu_dist_job **job_out)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    if (!params || !job_out) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (n_rows && (!d_rows || !d_n_eff || !d_length)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL row arrays");
+    if (ref_begin + ref_count > n_rows) return fail(ctx, MASHGPU_ERR_INVALID, "reference rows [%llu, %llu) exceed %llu rows", (unsigned long long)ref_begin,
+                                                    (unsigned long long)(ref_begin + ref_count), (unsigned long long)n_rows);
+    if (n_rows >= 0xFFFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^32 - 1 rows");
+    MG_TRY(check_dist_params(ctx, params));
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<mashgpu_dist_job> job(new mashgpu_dist_job());
+    job->ctx = ctx; job->params = *params; job->self = false;
+    job->n_ref = ref_count; job->n_qry = n_rows;
+    job->P = (uint32_t)params->sketch_size + 1;
+    job->d_ranks = d_rows; job->d_n_eff = d_n_eff; job->d_lens = d_length;
+    job->ref_row0 = ref_begin; job->qry_row0 = 0;
+    MG_TRY(dist_job_tables(ctx, job.get(), ctx->stream));
+    *job_out = job.release();
+    return MASHGPU_OK;
+}
+
+// ---- sharded dictionary build (see include/mashgpu.h) ----------------------------------------------------------------
+extern "C" int mashgpu_dict_local_sort(mashgpu_ctx *ctx, const mashgpu_sketch_set *set, uint64_t sketch_size,
+                                       uint64_t *d_keys, uint32_t *d_slots, uint64_t *n_valid, void *stream)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    if (!n_valid) return fail(ctx, MASHGPU_ERR_INVALID, "n_valid is NULL");
+    *n_valid = 0;
+    MG_TRY(check_set(ctx, set, "sketch", false));
+    if (sketch_size < 1 || sketch_size > 0x7FFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size out of range");
+    if (set->n == 0) return MASHGPU_OK;
+    if (!d_keys || !d_slots) return fail(ctx, MASHGPU_ERR_INVALID, "NULL output");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t P = (uint32_t)sketch_size + 1;
+    SetOnDevice d;
+    MG_TRY(stage_set(ctx, set, d, st, false));
+    DevBuf<uint32_t> n_eff, slots0; DevBuf<uint64_t> keys0; DevBuf<uint8_t> tmp;
+    const uint64_t cap = set->n * std::min<uint64_t>(set->stride, P);
+    if (n_eff.alloc(set->n) != cudaSuccess || keys0.alloc(cap) != cudaSuccess || slots0.alloc(cap) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)cap);
+    uint64_t n = 0;
+    MG_TRY(dict_gather(ctx, d, set->n, set->stride, P, 0, n_eff.p, 0, keys0.p, slots0.p, &n, st));
+    if (n) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, keys0.p, d_keys, slots0.p, d_slots, (int)n, 0, 64, st);
+        if (tmp.alloc(tb) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+        MG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys0.p, d_keys, slots0.p, d_slots, (int)n, 0, 64, st));
+        ctx->kernel_launches += 8;
     }
-    if (const char *env = getenv("MASHGPU_CF_LAZY")) job->lazy_second = atoi(env) != 0;
-    if (const char *env = getenv("MASHGPU_PROBE_PREFETCH")) job->probe_prefetch = atoi(env) != 0;
-    if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
-    *job_out = job;
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_valid = n;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dict_split(mashgpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, const uint64_t *splitters, uint32_t n_parts,
+                                  uint64_t *counts, void *stream)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    if (n_parts == 0 || !counts || (n_parts > 1 && !splitters) || (n && !d_keys)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (n_parts == 1) { counts[0] = n; return MASHGPU_OK; }
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t ns = n_parts - 1;
+    for (uint32_t i = 1; i < ns; i++)
+        if (splitters[i] < splitters[i - 1]) return fail(ctx, MASHGPU_ERR_INVALID, "splitters must be ascending");
+    DevBuf<uint64_t> d_spl, d_pos;
+    if (d_spl.alloc(ns) != cudaSuccess || d_pos.alloc(ns) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory");
+    std::vector<uint64_t> pos(ns);
+    MG_CUDA(ctx, cudaMemcpyAsync(d_spl.p, splitters, ns * 8ull, cudaMemcpyHostToDevice, st));
+    dict_split_kernel<<<blocks_for(ns, 64), 64, 0, st>>>(d_keys, n, d_spl.p, ns, d_pos.p);
+    MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, cudaMemcpyAsync(pos.data(), d_pos.p, ns * 8ull, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->kernel_launches++;
+    uint64_t prev = 0;
+    for (uint32_t p = 0; p < ns; p++) { counts[p] = pos[p] - prev; prev = pos[p]; }
+    counts[ns] = n - prev;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_dict_rank(mashgpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, uint32_t *d_codes, uint64_t *n_distinct, void *stream)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    if (!n_distinct) return fail(ctx, MASHGPU_ERR_INVALID, "n_distinct is NULL");
+    *n_distinct = 0;
+    if (n == 0) return MASHGPU_OK;
+    if (!d_keys || !d_codes) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (n >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 hashes in one dictionary sort");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    DevBuf<uint64_t> keys; DevBuf<uint32_t> pos;
+    if (keys.alloc(n) != cudaSuccess || pos.alloc(n) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)n);
+    MG_CUDA(ctx, cudaMemcpyAsync(keys.p, d_keys, n * 8, cudaMemcpyDeviceToDevice, st));
+    iota_kernel<<<blocks_for(n), 256, 0, st>>>(pos.p, n);
+    ctx->kernel_launches++;
+    return dict_rank(ctx, keys.p, pos.p, n, d_codes, n_distinct, st);
+}
+
+extern "C" int mashgpu_dict_scatter(mashgpu_ctx *ctx, const uint32_t *d_codes, const uint32_t *d_slots, const uint64_t *seg_counts,
+                                    const uint64_t *seg_base, uint32_t n_segs, const mashgpu_sketch_set *set, uint64_t sketch_size,
+                                    uint32_t *d_rows, uint32_t *d_n_eff, void *stream)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(check_set(ctx, set, "sketch", false));
+    if (sketch_size < 1 || sketch_size > 0x7FFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "sketch_size out of range");
+    if (set->n == 0) return MASHGPU_OK;
+    if (!d_rows || !d_n_eff || !seg_counts || !seg_base || n_segs == 0) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t P = (uint32_t)sketch_size + 1;
+    uint64_t n = 0;
+    std::vector<uint64_t> seg_end(n_segs);
+    for (uint32_t g = 0; g < n_segs; g++) { n += seg_counts[g]; seg_end[g] = n; }
+    if (n && (!d_codes || !d_slots)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL codes");
+    DevBuf<uint64_t> d_seg; DevBuf<uint32_t> d_err, d_nh;
+    if (d_seg.alloc(2ull * n_segs) != cudaSuccess || d_err.alloc(1) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory");
+    MG_CUDA(ctx, cudaMemcpyAsync(d_seg.p, seg_end.data(), n_segs * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_seg.p + n_segs, seg_base, n_segs * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, 4, st));
+    MG_CUDA(ctx, cudaMemsetAsync(d_rows, 0xFF, set->n * (uint64_t)P * 4, st));
+    const uint32_t *n_hashes = set->n_hashes;
+    if (!set->on_device) {
+        if (d_nh.alloc(set->n) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory");
+        MG_CUDA(ctx, cudaMemcpyAsync(d_nh.p, set->n_hashes, set->n * 4, cudaMemcpyHostToDevice, st));
+        n_hashes = d_nh.p;
+    }
+    dict_neff_kernel<<<blocks_for(set->n), 256, 0, st>>>(n_hashes, set->n, P, set->stride, 0, d_n_eff);
+    if (n) dict_scatter_seg_kernel<<<blocks_for(n), 256, 0, st>>>(d_codes, d_slots, n, d_seg.p, d_seg.p + n_segs, n_segs, d_rows, d_err.p);
+    MG_CUDA(ctx, cudaGetLastError());
+    uint32_t err = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->kernel_launches += 2;
+    if (err) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^32 - 1 distinct hashes in the collection");
     return MASHGPU_OK;
 }
 
@@ -658,7 +901,8 @@ extern "C" int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode)
 extern "C" int mashgpu_dist_set_triangle(mashgpu_dist_job *job, int on)
 {
     if (!job) return MASHGPU_ERR_INVALID;
-    if (on && !job->self) return fail(job->ctx, MASHGPU_ERR_INVALID, "triangle enumeration needs a self comparison (qry == NULL)");
+    if (on && !job->self && job->d_ranks == job->ranks.p)
+        return fail(job->ctx, MASHGPU_ERR_INVALID, "triangle enumeration needs a self comparison (qry == NULL) or an encoded job");
     job->triangle = on != 0;
     return MASHGPU_OK;
 }
@@ -702,10 +946,9 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     DistArgs a;
-    a.ranks = job->ranks.p; a.P = job->P; a.S = (uint32_t)job->params.sketch_size;
-    a.ref_n = job->n_eff.p; a.ref_len = job->lens.p; a.ref_row0 = 0;
-    const uint64_t qrow0 = job->self ? 0 : job->n_ref;
-    a.qry_n = job->n_eff.p + qrow0; a.qry_len = job->lens.p + qrow0; a.qry_row0 = qrow0;
+    a.ranks = job->d_ranks; a.P = job->P; a.S = (uint32_t)job->params.sketch_size;
+    a.ref_n = job->d_n_eff + job->ref_row0; a.ref_len = job->d_lens + job->ref_row0; a.ref_row0 = job->ref_row0;
+    a.qry_n = job->d_n_eff + job->qry_row0; a.qry_len = job->d_lens + job->qry_row0; a.qry_row0 = job->qry_row0;
     a.n_ref = (uint32_t)job->n_ref; a.q_begin = (uint32_t)q_begin; a.q_count = (uint32_t)q_count;
     a.kmer_size = job->params.kmer_size; a.kmer_space = job->params.kmer_space;
     a.max_distance = job->params.max_distance; a.max_pvalue = job->params.max_pvalue;
@@ -716,6 +959,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.list_pvalue = job->list_pvalue; a.list_count = job->list_count; a.list_capacity = job->list_capacity;
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
     a.triangle = job->triangle ? 1 : 0;
+    a.tri_r0 = job->self ? 0u : (uint32_t)job->ref_row0;
     a.probe_prefetch = job->probe_prefetch ? 1 : 0;
     {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
         const uint64_t pairs = q_count * job->n_ref;
@@ -864,36 +1108,40 @@ extern "C" int mashgpu_dist_run_list(mashgpu_dist_job *job, uint64_t q_begin, ui
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t cap = std::max<uint64_t>(capacity, 1);
-    DevBuf<uint64_t> l_idx, s_idx; DevBuf<uint32_t> l_n, l_d, order, s_order, o_n, o_d; DevBuf<double> l_D, l_P, o_D, o_P; DevBuf<unsigned long long> cnt; DevBuf<uint8_t> tmp;
-    if (l_idx.alloc(cap) != cudaSuccess || s_idx.alloc(cap) != cudaSuccess || l_n.alloc(cap) != cudaSuccess || l_d.alloc(cap) != cudaSuccess ||
-        l_D.alloc(cap) != cudaSuccess || l_P.alloc(cap) != cudaSuccess || order.alloc(cap) != cudaSuccess || s_order.alloc(cap) != cudaSuccess ||
-        o_n.alloc(cap) != cudaSuccess || o_d.alloc(cap) != cudaSuccess || o_D.alloc(cap) != cudaSuccess || o_P.alloc(cap) != cudaSuccess || cnt.alloc(1) != cudaSuccess)
+    mashgpu_dist_job &J = *job;       // grow-only list buffers: no cudaMalloc per call once they are large enough
+    if (J.l_idx.reserve(cap) != cudaSuccess || J.s_idx.reserve(cap) != cudaSuccess || J.l_n.reserve(cap) != cudaSuccess || J.l_d.reserve(cap) != cudaSuccess ||
+        J.l_D.reserve(cap) != cudaSuccess || J.l_P.reserve(cap) != cudaSuccess || J.l_order.reserve(cap) != cudaSuccess || J.s_order.reserve(cap) != cudaSuccess ||
+        J.o_n.reserve(cap) != cudaSuccess || J.o_d.reserve(cap) != cudaSuccess || J.o_D.reserve(cap) != cudaSuccess || J.o_P.reserve(cap) != cudaSuccess ||
+        J.l_cnt.reserve(1) != cudaSuccess)
         return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (pass list of %llu entries)", (unsigned long long)cap);
-    MG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, 8, st));
-    job->list_idx = l_idx.p; job->list_numer = l_n.p; job->list_denom = l_d.p; job->list_distance = l_D.p; job->list_pvalue = l_P.p;
-    job->list_count = cnt.p; job->list_capacity = capacity;
+    MG_CUDA(ctx, cudaMemsetAsync(J.l_cnt.p, 0, 8, st));
+    job->list_idx = J.l_idx.p; job->list_numer = J.l_n.p; job->list_denom = J.l_d.p; job->list_distance = J.l_D.p; job->list_pvalue = J.l_P.p;
+    job->list_count = J.l_cnt.p; job->list_capacity = capacity;
     int rc = mashgpu_dist_run_dev(job, q_begin, q_count, nullptr, nullptr, nullptr, nullptr, nullptr, st);
     job->list_idx = nullptr; job->list_numer = job->list_denom = nullptr; job->list_distance = job->list_pvalue = nullptr; job->list_count = nullptr; job->list_capacity = 0;
     MG_TRY(rc);
     unsigned long long n = 0;
-    MG_CUDA(ctx, cudaMemcpyAsync(&n, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(&n, J.l_cnt.p, 8, cudaMemcpyDeviceToHost, st));
     MG_CUDA(ctx, cudaStreamSynchronize(st));
     *n_pass = n;
     if (n == 0 || n > capacity) return MASHGPU_OK;      // overflow: the caller retries with a larger capacity (or the dense call)
     // restore the reference's output order (query-major pair index): sort the list by pair index on the device
     const unsigned tb = 256, nb = (unsigned)((n + tb - 1) / tb);
-    iota_kernel<<<nb, tb, 0, st>>>(order.p, n);
+    iota_kernel<<<nb, tb, 0, st>>>(J.l_order.p, n);
+    // the pair index is below q_count * n_ref: sort only the bits that can be set
+    int end_bit = 1;
+    while (end_bit < 64 && ((q_count * job->n_ref) >> end_bit)) end_bit++;
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, l_idx.p, s_idx.p, order.p, s_order.p, (int)n, 0, 64, st);
-    if (tmp.alloc(tmp_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
-    MG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, l_idx.p, s_idx.p, order.p, s_order.p, (int)n, 0, 64, st));
-    list_gather_kernel<<<nb, tb, 0, st>>>(s_order.p, n, l_n.p, l_d.p, l_D.p, l_P.p, o_n.p, o_d.p, o_D.p, o_P.p);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, J.l_idx.p, J.s_idx.p, J.l_order.p, J.s_order.p, (int)n, 0, end_bit, st);
+    if (J.l_tmp.reserve(tmp_bytes) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+    MG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(J.l_tmp.p, tmp_bytes, J.l_idx.p, J.s_idx.p, J.l_order.p, J.s_order.p, (int)n, 0, end_bit, st));
+    list_gather_kernel<<<nb, tb, 0, st>>>(J.s_order.p, n, J.l_n.p, J.l_d.p, J.l_D.p, J.l_P.p, J.o_n.p, J.o_d.p, J.o_D.p, J.o_P.p);
     ctx->kernel_launches += 10;
-    MG_CUDA(ctx, cudaMemcpyAsync(pair_index, s_idx.p, n * 8, cudaMemcpyDeviceToHost, st));
-    MG_CUDA(ctx, cudaMemcpyAsync(numer, o_n.p, n * 4, cudaMemcpyDeviceToHost, st));
-    MG_CUDA(ctx, cudaMemcpyAsync(denom, o_d.p, n * 4, cudaMemcpyDeviceToHost, st));
-    MG_CUDA(ctx, cudaMemcpyAsync(distance, o_D.p, n * 8, cudaMemcpyDeviceToHost, st));
-    MG_CUDA(ctx, cudaMemcpyAsync(pvalue, o_P.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(pair_index, J.s_idx.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(numer, J.o_n.p, n * 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(denom, J.o_d.p, n * 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(distance, J.o_D.p, n * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(pvalue, J.o_P.p, n * 8, cudaMemcpyDeviceToHost, st));
     MG_CUDA(ctx, cudaStreamSynchronize(st));
     return MASHGPU_OK;
 }

@@ -53,28 +53,45 @@ __global__ void screen_insert_kernel(const uint64_t *distinct, uint64_t n_distin
     }
 }
 
-// merge two ascending distinct lists (a: running mixture, b: chunk) -> ascending distinct, truncated to s.
-// Single CTA, bitonic sort of the concatenation in shared memory (2s <= 2^14 entries).
-__global__ void __launch_bounds__(SCR_THREADS) merge_bottom_s_kernel(uint64_t *mix, uint32_t *mix_n, const uint64_t *chunk, const uint32_t *chunk_n, uint32_t s)
+// merge ascending distinct lists -> ascending distinct, truncated to s, in `mix`: the running mixture (a) with n_lists more
+// lists (list i = lists[i * stride ...], list_n[i] entries; 1 list = a fed chunk, G lists = the ranks' mixtures).
+// Single CTA, bitonic sort of the concatenation in shared memory ((n_lists + 1) * s <= 2^14 entries).
+__global__ void __launch_bounds__(SCR_THREADS) merge_bottom_s_kernel(uint64_t *mix, uint32_t *mix_n, const uint64_t *lists, const uint32_t *list_n,
+                                                                     uint32_t n_lists, uint64_t stride, uint32_t s)
 {
     extern __shared__ uint64_t sk[];
-    const uint32_t na = *mix_n, nb = *chunk_n;
-    const uint32_t n = na + nb;
+    __shared__ uint32_t s_off[66];
+    if (threadIdx.x == 0) {
+        uint32_t o = min(*mix_n, s);
+        s_off[0] = o;
+        for (uint32_t i = 0; i < n_lists; i++) { o += min(list_n[i], s); s_off[i + 1] = o; }
+    }
+    __syncthreads();
+    const uint32_t na = s_off[0], n = s_off[n_lists];
     uint32_t N = 2;
     while (N < n) N <<= 1;
-    for (uint32_t i = threadIdx.x; i < N; i += SCR_THREADS) sk[i] = i < na ? mix[i] : (i < n ? chunk[i - na] : EMPTY_KEY);
+    for (uint32_t i = threadIdx.x; i < N; i += SCR_THREADS) {
+        uint64_t v = EMPTY_KEY;
+        if (i < na) v = mix[i];
+        else if (i < n) {
+            uint32_t l = 0;
+            while (i >= s_off[l + 1]) l++;
+            v = lists[(uint64_t)l * stride + (i - s_off[l])];
+        }
+        sk[i] = v;
+    }
     __syncthreads();
     for (uint32_t size = 2; size <= N; size <<= 1)
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t stride2 = size >> 1; stride2 > 0; stride2 >>= 1) {
             for (uint32_t t = threadIdx.x; t < N / 2; t += SCR_THREADS) {
-                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                uint32_t lo = 2 * t - (t & (stride2 - 1)), hi = lo + stride2;
                 bool up = (lo & size) == 0;
                 uint64_t a = sk[lo], b = sk[hi];
                 if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
             }
             __syncthreads();
         }
-    // unique + truncate: rank of each first occurrence = number of distinct predecessors (serial scan by one warp is fine: n <= 2s)
+    // unique + truncate: rank of each first occurrence = number of distinct predecessors (serial scan by one thread is fine: n <= 2^14)
     if (threadIdx.x == 0) {
         uint32_t m = 0;
         for (uint32_t i = 0; i < n && m < s; i++)
@@ -295,7 +312,7 @@ extern "C" int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_ch
     MG_TRY(sketch_stream_core(ctx, &job->params, S, job->chunk_hashes.p, nullptr, job->chunk_n.p, st, &probe));
     uint32_t N = 2;
     while (N < 2 * s) N <<= 1;
-    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, s);
+    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, 1, s, s);
     ctx->kernel_launches++;
     MG_CUDA(ctx, cudaGetLastError());
     MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
@@ -427,9 +444,48 @@ extern "C" int mashgpu_screen_merge_mixture(mashgpu_screen_job *job, const uint6
     MG_CUDA(ctx, cudaMemcpyAsync(job->chunk_n.p, &n, 4, cudaMemcpyHostToDevice, st));
     uint32_t N = 2;
     while (N < 2 * s) N <<= 1;
-    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, s);
+    merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, 1, s, s);
     ctx->kernel_launches++;
     MG_CUDA(ctx, cudaGetLastError());
+    MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (job->h_mix_n) {
+        MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_top, job->mix.p + (job->h_mix_n - 1), 8, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_mixture_dev(mashgpu_screen_job *job, uint64_t **d_mix, uint32_t **d_mix_n)
+{
+    if (!job || !d_mix || !d_mix_n) return MASHGPU_ERR_INVALID;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    *d_mix = job->mix.p;
+    *d_mix_n = job->mix_n.p;
+    return MASHGPU_OK;
+}
+
+extern "C" int mashgpu_screen_merge_mixtures_dev(mashgpu_screen_job *job, const uint64_t *d_hashes, const uint32_t *d_n, uint32_t n_lists, uint64_t stride)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    const uint32_t s = job->params.sketch_size;
+    if (n_lists == 0) return MASHGPU_OK;
+    if (!d_hashes || !d_n) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (stride < s) return fail(ctx, MASHGPU_ERR_INVALID, "stride must be at least sketch_size");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // as many lists per launch as the shared-memory sort holds (2^14 keys): all of them for 8 ranks x s = 1000
+    const uint32_t per_launch = std::max<uint32_t>(1, std::min<uint32_t>(64, (1u << 14) / s > 1 ? (1u << 14) / s - 1 : 1));
+    for (uint32_t l0 = 0; l0 < n_lists; l0 += per_launch) {
+        const uint32_t nl = std::min(per_launch, n_lists - l0);
+        uint32_t N = 2;
+        while (N < (nl + 1) * s) N <<= 1;
+        merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, d_hashes + (uint64_t)l0 * stride, d_n + l0, nl, stride, s);
+        ctx->kernel_launches++;
+        MG_CUDA(ctx, cudaGetLastError());
+    }
     MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
     MG_CUDA(ctx, cudaStreamSynchronize(st));
     if (job->h_mix_n) {

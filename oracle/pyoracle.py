@@ -271,3 +271,31 @@ class RefLib:
         self.lib.ref_hash_sequence(_ptr(keys, u64p), _ptr(counts, u32p), keys.size, b.ctypes.data, b.size, C.byref(p), s,
                                    _ptr(out, u64p), C.byref(n))
         return out[:n.value].copy()
+
+    # ---- screen with the reference's own table type (robin_hood map of atomics), multi-threaded ----------------------
+    def screen_table(self, keys):
+        L = self.lib
+        L.ref_screen_table_new.restype = C.c_void_p
+        L.ref_screen_table_new.argtypes = [u64p, C.c_uint64]
+        L.ref_screen_table_free.argtypes = [C.c_void_p]
+        L.ref_screen_table_counts.argtypes = [C.c_void_p, u64p, C.c_uint64, u32p]
+        L.ref_screen_many.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, u64p, C.POINTER(Params), C.c_uint64, C.c_int, u64p, u32p]
+        keys = np.ascontiguousarray(keys, np.uint64)
+        return L.ref_screen_table_new(_ptr(keys, u64p), keys.size)
+
+    def screen_table_free(self, t):
+        self.lib.ref_screen_table_free(C.c_void_p(t))
+
+    def screen_table_counts(self, t, keys):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        out = np.zeros(max(1, keys.size), np.uint32)
+        self.lib.ref_screen_table_counts(C.c_void_p(t), _ptr(keys, u64p), keys.size, _ptr(out, u32p))
+        return out[:keys.size]
+
+    def screen_many(self, t, chunks, p, s=1000, threads=1):
+        """hashSequence over '*'-joined chunks on `threads` workers (one chunk = one HashInput); returns the mixture bottom-s."""
+        bufs, ptrs, lens = _seq_arrays(chunks)
+        out = np.empty(s, np.uint64); n = C.c_uint32(0)
+        self.lib.ref_screen_many(C.c_void_p(t), len(bufs), C.cast(ptrs, C.c_void_p), _ptr(lens, u64p), C.byref(p), s, threads,
+                                 _ptr(out, u64p), C.byref(n))
+        return out[:n.value].copy()

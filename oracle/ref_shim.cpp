@@ -207,3 +207,86 @@ REF_API void ref_hash_sequence(const uint64_t *keys, uint32_t *counts, uint64_t 
     }
     if (out_hashes) *out_n = (uint32_t)emit(heap, p->use64 != 0, out_hashes, nullptr);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Screen with the reference's own table type: robin_hood::unordered_map<uint64_t, std::atomic<uint32_t>> hashCounts
+// (CommandScreen.cpp:94, 103-110), probed as hashSequence does (:571-575: count(key) == 1 -> hashCounts[key]++).
+// Multi-threaded CPU arm of bench.py: one HashInput per chunk (:224-262), one MinHashHeap per worker (:114-119, 239).
+// ---------------------------------------------------------------------------------------------------------
+#include "robin_hood.h"
+
+struct ref_screen_table {
+    robin_hood::unordered_map<uint64_t, std::atomic<uint32_t>> counts;
+};
+
+REF_API ref_screen_table *ref_screen_table_new(const uint64_t *keys, uint64_t n_keys)
+{
+    ref_screen_table *t = new ref_screen_table();
+    for (uint64_t i = 0; i < n_keys; i++) t->counts[keys[i]] = 0;
+    return t;
+}
+
+REF_API void ref_screen_table_free(ref_screen_table *t) { delete t; }
+
+REF_API void ref_screen_table_counts(ref_screen_table *t, const uint64_t *keys, uint64_t n_keys, uint32_t *out)
+{
+    for (uint64_t i = 0; i < n_keys; i++) {
+        auto it = t->counts.find(keys[i]);
+        out[i] = it == t->counts.end() ? 0u : it->second.load();
+    }
+}
+
+static void hash_sequence_map(ref_screen_table *t, MinHashHeap &heap, const char *seq_in, uint64_t length, const ref_params *p)
+{
+    const int k = p->kmer_size;
+    if (length < (uint64_t)k) return;
+    std::vector<char> seq(seq_in, seq_in + length), rev(length);
+    if (!p->preserve_case)
+        for (uint64_t i = 0; i < length; i++)
+            if (seq[i] > 96 && seq[i] < 123) seq[i] -= 32;
+    for (uint64_t i = 0; i < length; i++) rev[i] = complement_of((unsigned char)seq[length - 1 - i]);
+    int64_t lastGood = -1;
+    const int64_t len = (int64_t)length;
+    for (int64_t j = 0; j < len - k + 1; j++) {
+        while (lastGood < j + k - 1 && lastGood < len - 1) {
+            lastGood++;
+            if (!p->alphabet[(unsigned char)seq[lastGood]]) j = lastGood + 1;
+        }
+        if (j > len - k) break;
+        const char *fwd = seq.data() + j;
+        const char *rc = rev.data() + len - j - k;
+        const char *kmer = (p->noncanonical || memcmp(fwd, rc, k) <= 0) ? fwd : rc;
+        hash_u h = getHash(kmer, k, p->seed, p->use64 != 0);
+        heap.tryInsert(h);
+        uint64_t key = p->use64 ? h.hash64 : (uint64_t)h.hash32;
+        if (t->counts.count(key) == 1) t->counts[key]++;          // CommandScreen.cpp:571-575
+    }
+}
+
+// chunks: n_chunks '*'-joined read blocks; `threads` workers take chunks in order.  out_hashes/out_n (nullable): bottom-s of
+// the whole stream (heaps merged as CommandScreen.cpp:288-302).
+REF_API void ref_screen_many(ref_screen_table *t, uint64_t n_chunks, const char *const *chunks, const uint64_t *lens,
+                             const ref_params *p, uint64_t sketch_size, int threads, uint64_t *out_hashes, uint32_t *out_n)
+{
+    std::atomic<uint64_t> next(0);
+    std::vector<MinHashHeap *> heaps;
+    for (int i = 0; i < threads; i++) heaps.push_back(new MinHashHeap(p->use64 != 0, sketch_size));
+    auto work = [&](int w) {
+        for (;;) {
+            uint64_t c = next.fetch_add(1);
+            if (c >= n_chunks) return;
+            hash_sequence_map(t, *heaps[w], chunks[c], lens[c], p);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
+    for (auto &th : pool) th.join();
+    MinHashHeap merged(p->use64 != 0, sketch_size);
+    for (MinHashHeap *h : heaps) {
+        HashList list(p->use64 != 0);
+        h->toHashList(list);
+        for (int i = 0; i < list.size(); i++) merged.tryInsert(list.at(i));
+        delete h;
+    }
+    if (out_hashes && out_n) *out_n = (uint32_t)emit(merged, p->use64 != 0, out_hashes, nullptr);
+}

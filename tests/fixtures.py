@@ -146,3 +146,62 @@ def synth_sketches(n, s, seed, n_families=4, length=5_000_000, ragged=False):
         H[g, :v.size] = v
         N[g] = v.size
     return H, N, lens
+
+
+class NumpyDictOps:
+    """Test double for mash_b200.shard.DictOps (the four device steps of the sharded dictionary build) in numpy, so that the
+    exchange protocol of shard.sharded_dictionary can run under gloo without a GPU.  Same contracts as mashgpu_dict_*."""
+
+    @staticmethod
+    def _neff(n_hashes, stride, s):
+        return np.minimum(np.minimum(n_hashes.astype(np.int64), s + 1), stride)
+
+    def local_sort(self, hashes, n_hashes, sketch_size):
+        import torch
+        H = hashes.numpy().view(np.uint64)
+        ne = self._neff(n_hashes.numpy(), H.shape[1], sketch_size)
+        P = sketch_size + 1
+        keys, slots = [], []
+        for r in range(H.shape[0]):
+            keys.append(H[r, :ne[r]])
+            slots.append(r * P + np.arange(ne[r], dtype=np.int64))
+        keys = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+        slots = np.concatenate(slots) if slots else np.zeros(0, np.int64)
+        o = np.argsort(keys, kind="stable")
+        return torch.from_numpy(keys[o].view(np.int64).copy()), torch.from_numpy(slots[o].astype(np.int32))
+
+    def split(self, keys, splitters):
+        k = keys.numpy().view(np.uint64)
+        pos = [int(np.searchsorted(k, sp, side="left")) for sp in splitters]
+        edges = [0] + pos + [k.size]
+        return [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+
+    def rank(self, keys):
+        import torch
+        k = keys.numpy().view(np.uint64)
+        u, inv = np.unique(k, return_inverse=True)
+        return torch.from_numpy(inv.astype(np.int32)), int(u.size)
+
+    def scatter(self, codes, slots, seg_counts, seg_base, hashes, n_hashes, sketch_size):
+        import torch
+        m, stride = hashes.shape
+        P = sketch_size + 1
+        rows = np.full(m * P, 0xFFFFFFFF, np.uint32)
+        base = np.repeat(np.asarray(seg_base, np.int64), np.asarray(seg_counts, np.int64))
+        rows[slots.numpy().astype(np.int64)] = (codes.numpy().astype(np.int64) + base).astype(np.uint32)
+        ne = self._neff(n_hashes.numpy(), stride, sketch_size)
+        return torch.from_numpy(rows.view(np.int32).reshape(m, P).copy()), torch.from_numpy(ne.astype(np.int32))
+
+
+def dense_rank_rows(H, N, sketch_size):
+    """What every dictionary build must produce: rows of sketch_size+1 codes = rank of each hash among the distinct hashes of
+    the whole collection, padding 0xFFFFFFFF."""
+    P = sketch_size + 1
+    ne = np.minimum(np.minimum(N.astype(np.int64), P), H.shape[1])
+    valid = np.arange(H.shape[1])[None, :] < ne[:, None]
+    u = np.unique(H[valid])
+    rows = np.full((H.shape[0], P), 0xFFFFFFFF, np.uint32)
+    w = min(P, H.shape[1])
+    codes = np.searchsorted(u, H[:, :w]).astype(np.uint32)
+    rows[:, :w] = np.where(valid[:, :w], codes, np.uint32(0xFFFFFFFF))
+    return rows, ne.astype(np.uint32)

@@ -136,7 +136,7 @@ def test_pvalue_device_vs_mpmath(gpu, golden):
     assert worst < 1e-12
 
 
-def test_full_size_symmetry_property(gpu):
+def test_full_size_symmetry_property(gpu, oracle):
     # BASELINE configs[2] size (100 000 sketches, s=1000): size-independent property instead of an oracle run --
     # rows of a random subset Q against everything must equal the columns of everything against Q (merge symmetry),
     # self pairs have numer == denom == s, distance 0, and every distance/p-value is in [0, 1].
@@ -170,6 +170,27 @@ def test_full_size_symmetry_property(gpu):
     assert np.all(rows["numer"][np.arange(96), q] == s) and np.all(rows["distance"][np.arange(96), q] == 0)
     assert np.all((rows["distance"] >= 0) & (rows["distance"] <= 1)) and np.all((rows["pvalue"] >= 0) & (rows["pvalue"] <= 1))
     assert np.all(rows["denom"] == s)
+    # 10^4 sampled pairs of the full-size grid against the oracle: the 96 query rows x random columns, weighted towards the
+    # queries' own families (related pairs), plus the closed-form majority
+    cand = []
+    for i in range(96):
+        same = np.flatnonzero(fam == fam[q[i]])
+        cand.append(np.stack([np.full(60, i), rng.choice(same, 60)], axis=1))
+        cand.append(np.stack([np.full(45, i), rng.integers(0, n, 45)], axis=1))
+    cand = np.concatenate(cand)
+    assert cand.shape[0] >= 10_000
+    n_related = 0
+    for i in range(96):
+        cols_i = cand[cand[:, 0] == i, 1]
+        want = oracle.compare_all(H[cols_i], N[cols_i], L[cols_i], H[q[i]:q[i] + 1], N[q[i]:q[i] + 1], L[q[i]:q[i] + 1], s, 21, ks)[0]
+        got = {key: rows[key][i, cols_i] for key in ("numer", "denom", "distance", "pvalue", "pass")}
+        assert np.array_equal(got["numer"], want["numer"]) and np.array_equal(got["denom"], want["denom"])
+        assert np.all(np.abs(got["distance"] - want["distance"]) <= TOL)
+        big = want["pvalue"] > 1e-290
+        assert np.all(np.abs(got["pvalue"][big] - want["pvalue"][big]) <= TOL * want["pvalue"][big])
+        assert np.all(got["pvalue"][~big] <= 1e-289)
+        n_related += int((want["numer"] > 0).sum())
+    assert n_related > 1000      # the sample really contains pairs that went through the merge
 
 
 def test_pass_list_equals_dense_filter(gpu, oracle):

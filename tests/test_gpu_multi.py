@@ -1,7 +1,11 @@
-"""Multi-GPU paths with the real kernels (needs >= 2 GPUs; skipped otherwise): NCCL plumbing of mash_b200/shard.py.
-  * dist: reference axis sharded per rank, query tiles broadcast, grid assembled along the reference axis == oracle grid
-  * screen: reads sharded, counters all-reduced, mixture lists merged == oracle on the whole stream
-  * sketch: units sharded, no collective == oracle per unit"""
+"""Multi-GPU paths with the real kernels (needs >= 2 GPUs; skipped otherwise; runs on min(device_count, 8) ranks): NCCL plumbing
+of mash_b200/shard.py.
+  * dist: reference axis sharded per rank; (a) query tiles broadcast as hashes, every rank builds its own dictionary, and
+    (b) the sharded dictionary build (sample sort over hash ranges + all-gather of the encoded rows) with an encoded job;
+    both grids, assembled along the reference axis == oracle grid
+  * screen: reads sharded, counters all-reduced, mixture lists merged on the device == oracle on the whole stream
+  * sketch: units sharded, no collective == oracle per unit
+Run on the 2- and 8-GPU lease: `gpurun --gpus N -- python -m pytest tests/test_gpu_multi.py -m gpu -q` (logs: profiles/r02_multi_gpu_pytest_*.log)."""
 import os
 import socket
 import sys
@@ -33,7 +37,7 @@ def _worker(rank, world, port, tmp):
     td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import mash_b200
-        from mash_b200.shard import shard_bounds, exchange_query_tiles, screen_allreduce
+        from mash_b200.shard import shard_bounds, exchange_query_tiles, screen_allreduce, sharded_dictionary, DictOps, warm_collectives
         from fixtures import synth_sketches, synth_genome
         eng = mash_b200.Engine(rank)
         dev = torch.device("cuda", rank)
@@ -52,6 +56,19 @@ def _worker(rank, world, port, tmp):
         res = job.run(0, n)
         job.close()
         np.savez(os.path.join(tmp, f"dist{rank}.npz"), **res)
+        # ---- dist (b): sharded dictionary, encoded rows all-gathered, lower triangle as well
+        warm_collectives(dev)
+        rows, n_eff, lens, counts, stats = sharded_dictionary(DictOps(eng), hl, nl, ll, s, n_samples=128)
+        assert counts == [e - b for b, e in shard_bounds(n, world)] and stats["keys_sorted_locally"] == int(nl.clamp(max=s + 1).sum())
+        ejob = eng.dist_open_encoded(rows.data_ptr(), n_eff.data_ptr(), lens.data_ptr(), n, b0, b1 - b0, sketch_size=s, k=21, kmer_space=4.0 ** 21,
+                                     keepalive=(rows, n_eff, lens))
+        eres = ejob.run(0, n)
+        ejob.set_triangle(True)
+        tres = ejob.run(0, n)
+        ejob.close()
+        np.savez(os.path.join(tmp, f"edist{rank}.npz"), **eres)
+        np.savez(os.path.join(tmp, f"tdist{rank}.npz"), **tres)
+        np.save(os.path.join(tmp, f"rows{rank}.npy"), rows.cpu().numpy().view(np.uint32))
         # ---- screen
         p = eng.params(k=21, s=300)
         g = [synth_genome(70 + i, 120_000) for i in range(3)]
@@ -87,9 +104,10 @@ def test_two_gpu_paths(tmp_path, oracle):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    from fixtures import synth_sketches, synth_genome
+    from fixtures import synth_sketches, synth_genome, dense_rank_rows
     from mash_b200.shard import shard_bounds
-    world = 2
+    world = min(torch.cuda.device_count(), 8)
+    print(f"multi-GPU parity on {world} ranks")
     po = oracle.params(k=21)
     g = [synth_genome(70 + i, 120_000) for i in range(3)]
     refs = np.full((3, 300), np.uint64(2**64 - 1)); refs_n = np.zeros(3, np.uint32)
@@ -108,7 +126,22 @@ def test_two_gpu_paths(tmp_path, oracle):
     dist = np.concatenate([b["distance"] for b in blocks], axis=1)
     assert np.array_equal(numer, want["numer"]) and np.array_equal(denom, want["denom"])
     assert np.all(np.abs(dist - want["distance"]) <= 1e-12)
-    # screen: both ranks hold the global answer
+    # dist (b): every rank holds the dense ranks of the whole collection; encoded jobs give the same grid; triangle too
+    want_rows, _ = dense_rank_rows(H, N, s)
+    eb = [np.load(tmp_path / f"edist{r}.npz") for r in range(world)]
+    tb = [np.load(tmp_path / f"tdist{r}.npz") for r in range(world)]
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"rows{r}.npy"), want_rows)
+    for key in ("numer", "denom"):
+        assert np.array_equal(np.concatenate([b[key] for b in eb], axis=1), want[key])
+    assert np.array_equal(np.concatenate([b["distance"] for b in eb], axis=1), dist)
+    pv = np.concatenate([b["pvalue"] for b in eb], axis=1)
+    big = want["pvalue"] > 1e-290
+    assert np.all(np.abs(pv[big] - want["pvalue"][big]) <= 1e-12 * want["pvalue"][big])
+    lower = np.arange(n)[None, :] < np.arange(n)[:, None]
+    tn = np.concatenate([b["numer"] for b in tb], axis=1)
+    assert np.array_equal(tn[lower], want["numer"][lower]) and np.all(tn[~lower] == 0)
+    # screen: every rank holds the global answer
     rng = np.random.Generator(np.random.PCG64(5))
     reads = []
     for _ in range(4000):

@@ -77,3 +77,32 @@ def test_file_path_equals_in_memory_path(reflib, tmp_path):
     h, n, lens = reflib.sketch_files([str(path)], p, s=500, threads=1)
     hm, _, lm = reflib.sketch_unit([bytes(g), b"ACGT"], p, s=500)
     assert int(lens[0]) == lm == g.size and np.array_equal(h[0, :n[0]], hm)
+
+
+def test_ref_screen_many_matches_oracle(oracle, reflib):
+    """The multi-threaded CPU arm of bench.py's screen leg (reference hash + heap object code, the reference's robin_hood table
+    type) against the plain-C oracle: same counters, same mixture bottom-s."""
+    from fixtures import synth_genome
+    p = oracle.params(k=21)
+    g = [synth_genome(40 + i, 60_000) for i in range(3)]
+    refs = np.full((3, 200), np.uint64(2**64 - 1)); refs_n = np.zeros(3, np.uint32)
+    for i, gg in enumerate(g):
+        h, _, _ = oracle.sketch_unit([bytes(gg)], p, s=200)
+        refs[i, :h.size] = h; refs_n[i] = h.size
+    rng = np.random.Generator(np.random.PCG64(9))
+    chunks = []
+    for c in range(7):
+        reads = []
+        for _ in range(300):
+            gg = g[int(rng.integers(0, 2))]
+            a = int(rng.integers(0, gg.size - 150))
+            reads.append(bytes(gg[a:a + 150]))
+        chunks.append(b"".join(b"*" + r for r in reads))
+    want = oracle.screen(refs, refs_n, chunks, p, s=200)
+    t = reflib.screen_table(want["keys"])
+    try:
+        mix = reflib.screen_many(t, chunks, p, s=200, threads=3)
+        counts = reflib.screen_table_counts(t, want["keys"])
+    finally:
+        reflib.screen_table_free(t)
+    assert np.array_equal(counts, want["counts"]) and np.array_equal(mix, want["mixture"])

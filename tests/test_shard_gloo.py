@@ -63,3 +63,42 @@ def test_reference_axis_sharding_world2(tmp_path, oracle):
     assert got.shape == (n, n) and np.array_equal(got, want.astype(np.int64))
     assert shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert shard_bounds(0, 2) == [(0, 0), (0, 0)]
+
+
+def _dict_worker(rank, world, port, n, s, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fixtures import synth_sketches, NumpyDictOps
+        from mash_b200.shard import shard_bounds, sharded_dictionary
+        H, N, L = synth_sketches(n, s, seed=29, n_families=3, ragged=True)
+        b0, b1 = shard_bounds(n, world)[rank]
+        hl = torch.from_numpy(H[b0:b1].view(np.int64).copy())
+        nl = torch.from_numpy(N[b0:b1].astype(np.int32))
+        ll = torch.from_numpy(L[b0:b1].astype(np.int64))
+        rows, n_eff, lens, counts, stats = sharded_dictionary(NumpyDictOps(), hl, nl, ll, s, n_samples=64)
+        assert counts == [e - b for b, e in shard_bounds(n, world)]
+        np.savez(os.path.join(tmp, f"dict{rank}.npz"), rows=rows.numpy().view(np.uint32), n_eff=n_eff.numpy(), lens=lens.numpy(),
+                 ranked=stats["keys_ranked"], local=stats["keys_sorted_locally"])
+        td.barrier()
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 37), (3, 20), (3, 2)])
+def test_sharded_dictionary_protocol(tmp_path, world, n):
+    """shard.sharded_dictionary (sample sort over hash ranges) with a numpy stand-in for the device steps: every rank must end
+    with the dense ranks of the WHOLE collection, although no rank ever saw more than its rows and its hash range."""
+    from fixtures import synth_sketches, dense_rank_rows
+    s = 60
+    mp.spawn(_dict_worker, args=(world, _free_port(), n, s, str(tmp_path)), nprocs=world, join=True)
+    H, N, L = synth_sketches(n, s, seed=29, n_families=3, ragged=True)
+    want_rows, want_neff = dense_rank_rows(H, N, s)
+    total_ranked = 0
+    for r in range(world):
+        got = np.load(tmp_path / f"dict{r}.npz")
+        assert np.array_equal(got["rows"], want_rows), f"rank {r}"
+        assert np.array_equal(got["n_eff"].astype(np.uint32), want_neff) and np.array_equal(got["lens"].astype(np.uint64), L)
+        total_ranked += int(got["ranked"])
+    assert total_ranked == int(want_neff.sum())          # every hash was ranked exactly once, on the rank that owns its range
