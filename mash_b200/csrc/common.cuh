@@ -60,8 +60,14 @@ struct mashgpu_ctx {
     mashgpu::Scratch sc_start, sc_t, sc_off, sc_log2, sc_flags, sc_maxhash, sc_keys, sc_cnt, sc_tmax, sc_first, sc_last, sc_qtarget, sc_qtstar;
     // mashgpu_sketch_batch: wave stream buffers and outputs
     mashgpu::Scratch sc_wave[2], sc_inval[2], sc_runs[2], sc_out_hashes, sc_out_n, sc_out_counts;
-    mashgpu::Scratch sc_sep[2];
+    mashgpu::Scratch sc_sep[2], sc_codes[2];
     void *pinned_sep[2] = {nullptr, nullptr};
+    void *pinned_codes[2] = {nullptr, nullptr};     // packed feed path: host code buffers
+    size_t pinned_codes_bytes[2] = {0, 0};
+    cudaEvent_t pack_copied[2] = {nullptr, nullptr};
+    void *flags_pinned = nullptr;                   // per-unit status flags of the sketch pass in flight (sketch.cu)
+    size_t flags_pinned_n = 0;
+    cudaStream_t pack_stream = nullptr;             // packed uploads (next to the ASCII copies on copy_stream)
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
     cudaEvent_t wave_copied[2] = {nullptr, nullptr};

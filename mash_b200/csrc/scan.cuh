@@ -62,6 +62,9 @@ struct ScanArgs {
     uint32_t *ref_cnt;            // hit counters, indexed by that key index
     uint32_t ref_log2;
     uint64_t ref_hmax;            // largest reference hash (probe prefilter)
+    const uint32_t *ref_bitmap;   // optional second prefilter: bit (hash >> ref_bitmap_shift) is set iff some reference hash has these
+    uint32_t ref_bitmap_shift;    //   top bits (indexed by value, not hashed: reference hashes crowd the low end of the range)
+    uint64_t screen_mix_t;        // screen: largest unit threshold -- only hashes at or below it can enter the mixture's bottom-s
     // dump
     uint64_t *out_hash;
     uint8_t *out_valid;
@@ -108,17 +111,7 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
         if (hash == a.count_target && pos >= a.count_lo && pos <= a.count_hi) atomicAdd(a.count_out, 1u);
         return;
     }
-    if (a.mode == SCAN_SCREEN && hash <= a.ref_hmax) {
-        // hashCounts[key]++ iff key is a reference hash (CommandScreen.cpp:571-575)
-        const uint32_t mask = (1u << a.ref_log2) - 1;
-        uint32_t slot = slot_hash(hash, a.ref_log2);
-        for (;;) {
-            uint64_t k = a.ref_keys[slot];
-            if (k == hash) { atomicAdd(&a.ref_cnt[a.ref_idx[slot]], 1u); break; }
-            if (k == EMPTY_KEY) break;
-            slot = (slot + 1) & mask;
-        }
-    }
+    // (screen: the reference table was probed by screen_probe_lanes before the survivors were serialised)
     // unit of this position: last u with unit_start[u] <= pos
     uint32_t lo = 0, hi = a.n_units;
     while (hi - lo > 1) {
@@ -146,10 +139,57 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
 // a non-alphabet byte are garbage, and the few that slip under the threshold are rejected here by re-reading the
 // window's nibbles from the warp's shared-memory tile.  The fast-path filter only compares the high word (k > 16)
 // or the low word (k <= 16) of the hash with the tile threshold; the exact 64-bit test is in scan_emit.
+// window validity from the warp's tile: DNA kernels keep nibbles (bit 3 = outside the alphabet), byte kernels bytes (0 = outside)
+__device__ __forceinline__ bool window_valid(const uint32_t *sm_tile, uint32_t lp, int k)
+{
+    if (k > 0) {
+        uint32_t bad = 0;
+        for (int i = 0; i < k; i++) bad |= sm_tile[(lp + i) >> 3] >> (4 * ((lp + i) & 7));
+        return !(bad & 8u);
+    }
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(sm_tile);
+    bool ok = true;
+    for (int i = 0; i < -k; i++) ok &= bytes[lp + i] != 0;
+    return ok;
+}
+
+// Screen: hashCounts[key]++ iff key is a reference hash (CommandScreen.cpp:571-575).  Every lane probes for its own window --
+// with a reference set that spans the whole hash range (small genomes, plasmids, viruses in the .msh: their bottom-s reaches
+// up to 2^64 s / L) EVERY k-mer of the mixture is a candidate, so this cannot go through the serialised survivor path.
+// Order: largest reference hash -> value-indexed bitmap (L2 resident, rejects the sparse upper range without touching the
+// table) -> open-addressing table in HBM -> on a hit only, the window's validity (the fast path hashes invalid windows too).
+static __device__ __noinline__ void screen_probe_lanes(const ScanArgs &a, bool pass, uint32_t hash_lo, uint32_t hash_hi,
+                                                       uint32_t local_pos, const uint32_t *sm_tile, int k)
+{
+    const uint64_t hash = ((uint64_t)hash_hi << 32) | hash_lo;
+    bool go = pass && hash <= a.ref_hmax;
+    if (go && a.ref_bitmap) {
+        const uint64_t b = hash >> a.ref_bitmap_shift;
+        go = (__ldg(a.ref_bitmap + (b >> 5)) >> (b & 31)) & 1u;
+    }
+    if (!go) return;
+    const uint32_t mask = (1u << a.ref_log2) - 1;
+    uint32_t slot = slot_hash(hash, a.ref_log2);
+    for (;;) {
+        const uint64_t key = __ldg(a.ref_keys + slot);
+        if (key == hash) {
+            if (window_valid(sm_tile, local_pos, k)) atomicAdd(&a.ref_cnt[a.ref_idx[slot]], 1u);
+            return;
+        }
+        if (key == EMPTY_KEY) return;
+        slot = (slot + 1) & mask;
+    }
+}
+
 static __device__ __noinline__ void scan_emit_warp(const ScanArgs &a, bool pass, uint32_t hash_lo, uint32_t hash_hi,
                                                    uint64_t tile_base, uint32_t local_pos, const uint32_t *sm_tile, int k,
                                                    uint64_t tmax)
 {
+    if (a.mode == SCAN_SCREEN) {
+        screen_probe_lanes(a, pass, hash_lo, hash_hi, local_pos, sm_tile, k);
+        __syncwarp();
+        pass = pass && ((((uint64_t)hash_hi) << 32) | hash_lo) <= a.screen_mix_t;      // the rest is about the mixture's bottom-s only
+    }
     unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
     const int lane = threadIdx.x & 31;
     while (m) {
@@ -159,16 +199,7 @@ static __device__ __noinline__ void scan_emit_warp(const ScanArgs &a, bool pass,
         const uint32_t hi = __shfl_sync(0xFFFFFFFFu, hash_hi, src);
         const uint32_t lp = __shfl_sync(0xFFFFFFFFu, local_pos, src);
         if (lane == 0) {
-            bool ok = true;
-            if (k > 0) {            // nibble tile (DNA kernels): bit 3 marks a position outside the alphabet
-                uint32_t bad = 0;
-                for (int i = 0; i < k; i++) bad |= sm_tile[(lp + i) >> 3] >> (4 * ((lp + i) & 7));
-                ok = !(bad & 8u);
-            } else {                // byte tile (byte-alphabet kernels): 0 marks a position outside the alphabet
-                const uint8_t *bytes = reinterpret_cast<const uint8_t *>(sm_tile);
-                for (int i = 0; i < -k; i++) ok &= bytes[lp + i] != 0;
-            }
-            if (ok && ((((uint64_t)hi) << 32) | lo) <= tmax) scan_emit(a, lo, hi, tile_base, lp);
+            if (window_valid(sm_tile, lp, k) && ((((uint64_t)hi) << 32) | lo) <= tmax) scan_emit(a, lo, hi, tile_base, lp);
         }
         __syncwarp();
     }

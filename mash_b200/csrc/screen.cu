@@ -53,6 +53,23 @@ __global__ void screen_insert_kernel(const uint64_t *distinct, uint64_t n_distin
     }
 }
 
+// presence bitmap over the distinct reference hashes, indexed by the top bits of the value (scan.cuh, screen_probe_lanes)
+__global__ void screen_bitmap_kernel(const uint64_t *distinct, uint64_t n_distinct, uint32_t shift, uint32_t *bitmap)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_distinct) return;
+    const uint64_t b = distinct[t] >> shift;
+    atomicOr(&bitmap[b >> 5], 1u << (b & 31));
+}
+
+// {number of hashes, largest hash} of the running mixture list -> two words the host reads back with one copy
+__global__ void screen_mix_top_kernel(const uint64_t *mix, const uint32_t *mix_n, uint64_t *out)
+{
+    const uint32_t n = *mix_n;
+    out[0] = n;
+    out[1] = n ? mix[n - 1] : 0;
+}
+
 // merge ascending distinct lists -> ascending distinct, truncated to s, in `mix`: the running mixture (a) with n_lists more
 // lists (list i = lists[i * stride ...], list_n[i] entries; 1 list = a fed chunk, G lists = the ranks' mixtures).
 // Single CTA, bitonic sort of the concatenation in shared memory ((n_lists + 1) * s <= 2^14 entries).
@@ -202,7 +219,16 @@ struct mashgpu_screen_job {
     uint64_t hmax = 0;
     DevBuf<uint64_t> mix, chunk_hashes; DevBuf<uint32_t> mix_n, chunk_n;
     uint32_t h_mix_n = 0; uint64_t h_mix_top = 0;
-    DevBuf<uint8_t> stage;   // device staging for host chunks
+    DevBuf<uint32_t> bitmap; uint32_t bitmap_shift = 0;      // value-indexed presence bitmap (built when the table is large)
+    // host-chunk pipeline: two device staging buffers; the kernels of chunk i run while chunk i+1 crosses PCIe
+    DevBuf<uint8_t> stage[2];
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    int next_buf = 0;
+    SketchTicket ticket;
+    bool pending = false;            // a chunk's kernels are in flight (ticket + mixture read-back not yet collected)
+    DevBuf<uint64_t> d_mix_top; PinnedBuf<uint64_t> h_mix_top2;      // {n, top} of the mixture after the chunk in flight
+    PinnedBuf<uint8_t> acc; uint64_t acc_len = 0;                    // small host chunks are joined here before they are fed
+    ~mashgpu_screen_job() { for (int b = 0; b < 2; b++) if (copied[b]) cudaEventDestroy(copied[b]); }
     bool winner = false;     // -w
     std::vector<uint64_t> h_len;      // Reference::length per sketch (tie break of -w), zeros when the caller gave none
     std::vector<uint32_t> h_n;        // hashes per sketch
@@ -240,6 +266,7 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
     DevBuf<uint64_t> gathered, sorted, distinct; DevBuf<uint8_t> tmp; DevBuf<uint64_t> d_nsel;
     if (job->keys.alloc(cap) != cudaSuccess || job->slot_idx.alloc(cap) != cudaSuccess || job->mix.alloc(s) != cudaSuccess || job->chunk_hashes.alloc(s) != cudaSuccess ||
         job->mix_n.alloc(1) != cudaSuccess || job->chunk_n.alloc(1) != cudaSuccess || d_count.alloc(1) != cudaSuccess || d_err.alloc(1) != cudaSuccess ||
+        job->d_mix_top.alloc(2) != cudaSuccess || job->h_mix_top2.alloc(2) != cudaSuccess ||
         gathered.alloc(total) != cudaSuccess || sorted.alloc(total) != cudaSuccess || distinct.alloc(total) != cudaSuccess || d_nsel.alloc(1) != cudaSuccess)
         return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen table of %llu slots)", (unsigned long long)cap));
     cudaMemsetAsync(job->keys.p, 0xFF, cap * 8, st);
@@ -268,6 +295,18 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
             screen_insert_kernel<<<(unsigned)((n_distinct + 255) / 256), 256, 0, st>>>(distinct.p, n_distinct, job->keys.p, job->slot_idx.p, job->log2cap);
             cudaMemcpyAsync(&hmax, distinct.p + (n_distinct - 1), 8, cudaMemcpyDeviceToHost, st);     // ascending: the last one is the largest
             ctx->kernel_launches += 12;
+            // value-indexed bitmap, ~4 bits per key, 2^20 .. 2^28 bits (32 MB: stays in the 126 MB L2 next to the read stream).
+            // Reference hashes crowd the low end of the range (a sketch of a genome of length L reaches up to ~2^64 s/L): that
+            // region is all ones, while the long sparse tail contributed by small genomes is rejected here without a table probe.
+            const char *env_bm = getenv("MASHGPU_SCREEN_BITMAP");
+            if (!(env_bm && env_bm[0] == '0')) {
+                const uint32_t bits_log2 = std::min(28u, std::max(20u, ceil_log2(4 * n_distinct)));
+                job->bitmap_shift = (params->use64 ? 64u : 32u) - bits_log2;
+                if (job->bitmap.alloc((size_t)1 << (bits_log2 - 5)) != cudaSuccess) return bail(fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen bitmap)"));
+                cudaMemsetAsync(job->bitmap.p, 0, (size_t)4 << (bits_log2 - 5), st);
+                screen_bitmap_kernel<<<(unsigned)((n_distinct + 255) / 256), 256, 0, st>>>(distinct.p, n_distinct, job->bitmap_shift, job->bitmap.p);
+                ctx->kernel_launches++;
+            }
         }
     }
     job->n_distinct = n_distinct;
@@ -296,32 +335,99 @@ extern "C" int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params
     return MASHGPU_OK;
 }
 
-extern "C" int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64_t len)
+namespace {
+
+constexpr uint64_t SCREEN_SMALL_CHUNK = 4ull << 20;     // host chunks below this are joined before they are fed ...
+constexpr uint64_t SCREEN_FLUSH_BYTES = 32ull << 20;    // ... until this much has accumulated (the reference feeds 1 MiB HashInputs)
+
+// kernels of one chunk: scan (+ table probe) -> chunk bottom-s -> merge into the running mixture -> {n, top} read-back.  No sync.
+int screen_enqueue(mashgpu_screen_job *job, const void *d_chunk, uint64_t len)
 {
-    if (!job) return MASHGPU_ERR_INVALID;
     mashgpu_ctx *ctx = job->ctx;
-    if (len == 0) return MASHGPU_OK;
-    MG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t s = job->params.sketch_size;
     uint64_t unit_start[2] = {0, len};
     SketchStream S;
     S.d_stream = d_chunk; S.unit_start = unit_start; S.n_units = 1;
     if (job->h_mix_n == s) { S.t_cap = true; S.t_cap_value = job->h_mix_top; }   // nothing above the running s-th smallest can matter
-    ScreenProbe probe{job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, job->hmax};
-    MG_TRY(sketch_stream_core(ctx, &job->params, S, job->chunk_hashes.p, nullptr, job->chunk_n.p, st, &probe));
+    ScreenProbe probe{job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, job->hmax, job->bitmap.p, job->bitmap_shift};
+    MG_CUDA(ctx, cudaMemsetAsync(job->chunk_n.p, 0, 4, st));      // an overflowing chunk leaves an empty list until its exact re-run
+    MG_TRY(sketch_stream_enqueue(ctx, &job->params, S, job->chunk_hashes.p, nullptr, job->chunk_n.p, st, &probe, job->ticket));
     uint32_t N = 2;
     while (N < 2 * s) N <<= 1;
+    // merged optimistically: if the chunk turns out to need an exact re-run, the list merged here is a subset of the chunk's real
+    // hashes (harmless in a bottom-s of the union) and the exact list is merged again after the re-run (screen_collect)
     merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, 1, s, s);
-    ctx->kernel_launches++;
+    screen_mix_top_kernel<<<1, 1, 0, st>>>(job->mix.p, job->mix_n.p, job->d_mix_top.p);
+    ctx->kernel_launches += 2;
     MG_CUDA(ctx, cudaGetLastError());
-    MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_n, job->mix_n.p, 4, cudaMemcpyDeviceToHost, st));
-    MG_CUDA(ctx, cudaStreamSynchronize(st));
-    if (job->h_mix_n) {
-        MG_CUDA(ctx, cudaMemcpyAsync(&job->h_mix_top, job->mix.p + (job->h_mix_n - 1), 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(job->h_mix_top2.p, job->d_mix_top.p, 16, cudaMemcpyDeviceToHost, st));
+    job->pending = true;
+    return MASHGPU_OK;
+}
+
+// waits for the chunk in flight, re-runs it exactly if it was flagged, and takes over the mixture's {n, top}
+int screen_collect(mashgpu_screen_job *job)
+{
+    if (!job->pending) return MASHGPU_OK;
+    job->pending = false;
+    mashgpu_ctx *ctx = job->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t reruns_before = ctx->exact_reruns;
+    MG_TRY(sketch_stream_finalize(ctx, job->ticket));              // synchronises the stream
+    if (ctx->exact_reruns != reruns_before) {
+        const uint32_t s = job->params.sketch_size;
+        uint32_t N = 2;
+        while (N < 2 * s) N <<= 1;
+        merge_bottom_s_kernel<<<1, SCR_THREADS, (size_t)N * 8, st>>>(job->mix.p, job->mix_n.p, job->chunk_hashes.p, job->chunk_n.p, 1, s, s);
+        screen_mix_top_kernel<<<1, 1, 0, st>>>(job->mix.p, job->mix_n.p, job->d_mix_top.p);
+        ctx->kernel_launches += 2;
+        MG_CUDA(ctx, cudaGetLastError());
+        MG_CUDA(ctx, cudaMemcpyAsync(job->h_mix_top2.p, job->d_mix_top.p, 16, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    job->h_mix_n = (uint32_t)job->h_mix_top2.p[0];
+    job->h_mix_top = job->h_mix_top2.p[1];
     return MASHGPU_OK;
+}
+
+// host chunk -> staging buffer (async) while the previous chunk's kernels finish; returns once the caller's buffer is free
+int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)
+{
+    mashgpu_ctx *ctx = job->ctx;
+    const int b = job->next_buf;
+    job->next_buf ^= 1;
+    const uint64_t padded = ((len + 15) / 16) * 16;
+    if (job->stage[b].n < padded && job->stage[b].alloc(padded + (padded >> 2)) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+    if (!job->copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&job->copied[b], cudaEventDisableTiming));
+    MG_CUDA(ctx, cudaMemcpyAsync(job->stage[b].p, chunk, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MG_CUDA(ctx, cudaEventRecord(job->copied[b], ctx->copy_stream));
+    MG_TRY(screen_collect(job));                                    // the chunk before this one: its kernels overlapped the copy above
+    MG_CUDA(ctx, cudaEventSynchronize(job->copied[b]));
+    return screen_enqueue(job, job->stage[b].p, len);
+}
+
+int screen_flush_acc(mashgpu_screen_job *job)
+{
+    if (job->acc_len == 0) return MASHGPU_OK;
+    const uint64_t n = job->acc_len;
+    job->acc_len = 0;
+    return screen_feed_host(job, job->acc.p, n);
+}
+
+}  // namespace
+
+extern "C" int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64_t len)
+{
+    if (!job) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    if (len == 0) return MASHGPU_OK;
+    if (!d_chunk) return fail(ctx, MASHGPU_ERR_INVALID, "chunk is NULL");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_TRY(screen_collect(job));
+    MG_TRY(screen_enqueue(job, d_chunk, len));
+    return screen_collect(job);          // the caller's device buffer is free again when this returns
 }
 
 extern "C" int mashgpu_screen_feed(mashgpu_screen_job *job, const char *chunk, uint64_t len)
@@ -331,11 +437,16 @@ extern "C" int mashgpu_screen_feed(mashgpu_screen_job *job, const char *chunk, u
     if (len == 0) return MASHGPU_OK;
     if (!chunk) return fail(ctx, MASHGPU_ERR_INVALID, "chunk is NULL");
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t padded = ((len + 15) / 16) * 16;
-    if (job->stage.n < padded && job->stage.alloc(padded + (padded >> 2)) != cudaSuccess)
-        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
-    MG_CUDA(ctx, cudaMemcpyAsync(job->stage.p, chunk, len, cudaMemcpyHostToDevice, ctx->stream));
-    return mashgpu_screen_feed_dev(job, job->stage.p, len);
+    if (len >= SCREEN_SMALL_CHUNK) return screen_feed_host(job, chunk, len);
+    // small chunk: join it to the pending ones with a separator byte (any byte outside the alphabet separates reads,
+    // CommandScreen.cpp:254-258 uses '*'); one kernel pass per ~32 MiB instead of one per 1 MiB HashInput
+    if (job->acc.n < SCREEN_FLUSH_BYTES + SCREEN_SMALL_CHUNK + 16 && job->acc.alloc(SCREEN_FLUSH_BYTES + SCREEN_SMALL_CHUNK + 16) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (chunk accumulator)");
+    memcpy(job->acc.p + job->acc_len, chunk, len);
+    job->acc.p[job->acc_len + len] = 0;
+    job->acc_len += len + 1;
+    if (job->acc_len >= SCREEN_FLUSH_BYTES) return screen_flush_acc(job);
+    return MASHGPU_OK;
 }
 
 extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, uint64_t *median, double *identity,
@@ -344,6 +455,8 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
     if (!job) return MASHGPU_ERR_INVALID;
     mashgpu_ctx *ctx = job->ctx;
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_TRY(screen_flush_acc(job));
+    MG_TRY(screen_collect(job));
     cudaStream_t st = ctx->stream;
     const int k = job->params.kmer_size;
     int asize = 0;
@@ -424,6 +537,8 @@ extern "C" int mashgpu_screen_counters(mashgpu_screen_job *job, uint32_t **d_cou
 {
     if (!job || !d_counters || !n_slots) return MASHGPU_ERR_INVALID;
     cudaSetDevice(job->ctx->device);
+    MG_TRY(screen_flush_acc(job));
+    MG_TRY(screen_collect(job));
     cudaStreamSynchronize(job->ctx->stream);
     *d_counters = job->cnt.p;
     *n_slots = job->n_distinct;
@@ -439,6 +554,8 @@ extern "C" int mashgpu_screen_merge_mixture(mashgpu_screen_job *job, const uint6
     if (n == 0) return MASHGPU_OK;
     if (!hashes) return fail(ctx, MASHGPU_ERR_INVALID, "hashes is NULL");
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_TRY(screen_flush_acc(job));
+    MG_TRY(screen_collect(job));
     cudaStream_t st = ctx->stream;
     MG_CUDA(ctx, cudaMemcpyAsync(job->chunk_hashes.p, hashes, n * 8ull, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaMemcpyAsync(job->chunk_n.p, &n, 4, cudaMemcpyHostToDevice, st));
@@ -460,6 +577,8 @@ extern "C" int mashgpu_screen_mixture_dev(mashgpu_screen_job *job, uint64_t **d_
 {
     if (!job || !d_mix || !d_mix_n) return MASHGPU_ERR_INVALID;
     cudaSetDevice(job->ctx->device);
+    MG_TRY(screen_flush_acc(job));
+    MG_TRY(screen_collect(job));
     cudaStreamSynchronize(job->ctx->stream);
     *d_mix = job->mix.p;
     *d_mix_n = job->mix_n.p;
@@ -475,6 +594,8 @@ extern "C" int mashgpu_screen_merge_mixtures_dev(mashgpu_screen_job *job, const 
     if (!d_hashes || !d_n) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
     if (stride < s) return fail(ctx, MASHGPU_ERR_INVALID, "stride must be at least sketch_size");
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_TRY(screen_flush_acc(job));
+    MG_TRY(screen_collect(job));
     cudaStream_t st = ctx->stream;
     // as many lists per launch as the shared-memory sort holds (2^14 keys): all of them for 8 ranks x s = 1000
     const uint32_t per_launch = std::max<uint32_t>(1, std::min<uint32_t>(64, (1u << 14) / s > 1 ? (1u << 14) / s - 1 : 1));
@@ -499,7 +620,10 @@ extern "C" int mashgpu_screen_close(mashgpu_screen_job *job)
 {
     if (!job) return MASHGPU_ERR_INVALID;
     cudaSetDevice(job->ctx->device);
+    job->acc_len = 0;
+    screen_collect(job);                 // never leave a chunk in flight behind
     cudaStreamSynchronize(job->ctx->stream);
+    cudaStreamSynchronize(job->ctx->copy_stream);
     delete job;
     return MASHGPU_OK;
 }

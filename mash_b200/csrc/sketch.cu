@@ -16,6 +16,7 @@
 #include "scan.cuh"
 #include "sketch_core.cuh"
 #include "pack.h"
+#include <chrono>
 #include <future>
 #include <thread>
 #include <cstdlib>
@@ -436,8 +437,24 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
                        uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
                        const ScreenProbe *probe)
 {
-    const uint32_t n_units = (uint32_t)S.n_units;
+    SketchTicket t;
+    MG_TRY(sketch_stream_enqueue(ctx, p, S, d_out_hashes, d_out_counts, d_out_n, st, probe, t));
+    return sketch_stream_finalize(ctx, t);
+}
+
+int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S_in,
+                          uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
+                          const ScreenProbe *probe, SketchTicket &t)
+{
+    t.active = false;
+    const uint32_t n_units = (uint32_t)S_in.n_units;
     if (n_units == 0) return MASHGPU_OK;
+    t.params = *p;
+    t.S = S_in;
+    t.unit_start.assign(S_in.unit_start, S_in.unit_start + n_units + 1);
+    t.S.unit_start = t.unit_start.data();
+    t.d_out_hashes = d_out_hashes; t.d_out_counts = d_out_counts; t.d_out_n = d_out_n; t.st = st;
+    const SketchStream &S = t.S;
     const uint32_t s = p->sketch_size;
     const uint64_t stream_len = S.unit_start[n_units];
     const uint64_t ntiles = (stream_len + SCAN_TILE - 1) / SCAN_TILE;
@@ -508,6 +525,7 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
     a.only_unit = -1;
     if (probe) {
         a.ref_keys = probe->keys; a.ref_idx = probe->idx; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
+        a.ref_bitmap = probe->bitmap; a.ref_bitmap_shift = probe->bitmap_shift;
     }
     if (ntiles) {
         tile_tmax_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(d_start.p, n_units, d_t.p, stream_len, p->kmer_size, 0, ntiles, d_tmax.p);
@@ -520,6 +538,7 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
         uint64_t tm = 0;
         for (uint32_t u = 0; u < n_units; u++) tm = std::max(tm, h_t[u]);
         a.coarse_t = std::max(tm, probe->hmax);
+        a.screen_mix_t = tm;
     }
     MG_TRY(launch_scan(ctx, p, a, st));
 
@@ -542,9 +561,39 @@ int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const S
         MG_CUDA(ctx, cudaGetLastError());
     }
 
-    std::vector<uint32_t> h_flags(n_units);
-    MG_CUDA(ctx, cudaMemcpyAsync(h_flags.data(), d_flags.p, n_units * 4ull, cudaMemcpyDeviceToHost, st));
+    if (ctx->flags_pinned_n < n_units) {          // one ticket in flight per context: its flags land in the context's pinned buffer
+        if (ctx->flags_pinned) cudaFreeHost(ctx->flags_pinned);
+        ctx->flags_pinned = nullptr; ctx->flags_pinned_n = 0;
+        const size_t want = (size_t)n_units + n_units / 4 + 64;
+        if (cudaMallocHost(&ctx->flags_pinned, want * 4) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (unit flags)");
+        ctx->flags_pinned_n = want;
+    }
+    MG_CUDA(ctx, cudaMemcpyAsync(ctx->flags_pinned, d_flags.p, n_units * 4ull, cudaMemcpyDeviceToHost, st));
+    t.d_qtarget = d_qtarget; t.d_qtstar = d_qtstar;
+    t.scan_args.resize(sizeof(ScanArgs));
+    memcpy(t.scan_args.data(), &a, sizeof(ScanArgs));
+    t.active = true;
+    return MASHGPU_OK;
+}
+
+int sketch_stream_finalize(mashgpu_ctx *ctx, SketchTicket &t)
+{
+    if (!t.active) return MASHGPU_OK;
+    t.active = false;
+    const mashgpu_sketch_params *p = &t.params;
+    const SketchStream &S = t.S;
+    const uint32_t n_units = (uint32_t)S.n_units;
+    const uint32_t s = p->sketch_size;
+    cudaStream_t st = t.st;
+    uint64_t *d_out_hashes = t.d_out_hashes; uint32_t *d_out_counts = t.d_out_counts, *d_out_n = t.d_out_n;
+    uint64_t *d_qtarget = t.d_qtarget, *d_qtstar = t.d_qtstar;
+    ScanArgs a;
+    memcpy(&a, t.scan_args.data(), sizeof(ScanArgs));
     MG_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t *h_flags = (const uint32_t *)ctx->flags_pinned;
+    bool any_flag = false;
+    for (uint32_t u = 0; u < n_units; u++) any_flag |= h_flags[u] != 0;
+    if (!any_flag) return MASHGPU_OK;
     bool any_recount = false;
     for (uint32_t u = 0; u < n_units; u++) any_recount |= (h_flags[u] & 8u) && !(h_flags[u] & 7u);
     std::vector<uint64_t> h_qtarget, h_qtstar;
@@ -601,7 +650,7 @@ namespace {
 
 struct Wave { uint64_t unit_begin, unit_end, rec_begin, rec_end, bytes; };
 
-constexpr uint64_t WAVE_BYTES = 1ull << 31;        // stream bytes per wave
+constexpr uint64_t WAVE_BYTES = 1ull << 30;        // stream bytes per wave (the two feed paths share the waves of a batch: finer than 2 GiB balances better)
 constexpr uint32_t SEP_LIST_MAX = 1u << 15;        // directly copied records per wave whose separators go through the list
 constexpr uint64_t DIRECT_COPY_MIN = 1ull << 18;   // records at least this long are copied straight from the caller's buffer
 
@@ -646,12 +695,17 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
             out_length[u] = L;
         }
 
-    // waves
+    // waves: cut by stream bytes and by unit count (outputs and candidate tables grow with the number of units, not with their
+    // length -- a multi-FASTA of millions of short records must not allocate units x s outputs at once)
+    uint64_t wave_units_max = std::max<uint64_t>(64, (1ull << 28) / ((uint64_t)s * 8));
+    uint64_t wave_bytes = WAVE_BYTES;
+    if (const char *env = getenv("MASHGPU_WAVE_BYTES")) wave_bytes = std::max<uint64_t>(1024, strtoull(env, nullptr, 10));      // tests: many waves from little data
+    if (const char *env = getenv("MASHGPU_WAVE_UNITS")) wave_units_max = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
     std::vector<Wave> waves;
     {
         Wave w{0, 0, 0, 0, 0};
         for (uint64_t u = 0; u < n_units; u++) {
-            if (w.unit_end > w.unit_begin && w.bytes + unit_bytes[u] > WAVE_BYTES) {
+            if (w.unit_end > w.unit_begin && (w.bytes + unit_bytes[u] > wave_bytes || w.unit_end - w.unit_begin >= wave_units_max)) {
                 w.rec_end = unit_rec_begin[u];
                 waves.push_back(w);
                 w = Wave{u, u, unit_rec_begin[u], 0, 0};
@@ -662,161 +716,86 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         w.rec_end = n_records;
         waves.push_back(w);
     }
-    // ---- packed feed path (opt-in, MASHGPU_HOST_PACK=1): host threads pack each wave to 2 bits/base (+ invalid runs) while
-    // the GPU works on the previous wave; H2D moves a quarter of the bytes.  Measured on the B200 box of this pool (128
-    // vCPUs but ~16 cores' worth of host throughput, profiles/r01_feed_path.md): packing sustains 16.5 Gbp/s against
-    // 49 Gbp/s for the plain pinned ASCII copy below, so ASCII stays the default; on hosts with real cores to spare the
-    // packed path removes the PCIe bound (4x fewer bytes).
-    {
-        const char *env = getenv("MASHGPU_HOST_PACK");
-        if (env && env[0] == '1' && is_dna_alphabet(params)) {
-            uint64_t max_bytes = 32, max_units = 1;
-            for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
-            const uint64_t max_tiles = (max_bytes + SCAN_TILE - 1) / SCAN_TILE;
-            const uint64_t groups_alloc = max_tiles * (SCAN_TILE / 32) + 64;       // tile-padded + halo
-            // as many packer threads as the process may actually run: a container's CPU quota (cgroup v2 cpu.max) can be far
-            // below the visible core count, and threads beyond it are throttled together -- measured on this pool's B200 box
-            // (128 vCPUs visible, quota 16): 61 GB/s with 16 threads, 13 GB/s with 128 (tools/pack_bench.py)
-            int threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 96u);
-            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
-                long long quota = 0, period = 0;
-                if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
-                    threads = std::min(threads, (int)std::max(1ll, (quota + period - 1) / period));
-                fclose(f);
-            }
-            if (const char *t = getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, atoi(t));
-            const int nbuf = waves.size() > 1 ? 2 : 1;
-            uint64_t *d_codes[2] = {nullptr, nullptr}; uint32_t *d_inval[2] = {nullptr, nullptr};
-            uint64_t *h_codes[2] = {nullptr, nullptr};
-            for (int b = 0; b < nbuf; b++) {
-                d_codes[b] = ctx->sc_wave[b].get<uint64_t>(groups_alloc);
-                d_inval[b] = ctx->sc_inval[b].get<uint32_t>(groups_alloc);
-                if (!d_codes[b] || !d_inval[b]) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (packed stream of %llu groups)", (unsigned long long)groups_alloc);
-                if (ctx->pinned_bytes[b] < groups_alloc * 8) {
-                    if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
-                    ctx->pinned[b] = nullptr; ctx->pinned_bytes[b] = 0;
-                    if (cudaMallocHost(&ctx->pinned[b], groups_alloc * 8) != cudaSuccess)
-                        return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)(groups_alloc * 8));
-                    ctx->pinned_bytes[b] = groups_alloc * 8;
-                }
-                h_codes[b] = (uint64_t *)ctx->pinned[b];
-                if (!ctx->wave_copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wave_copied[b], cudaEventDisableTiming));
-            }
-            uint64_t *d_hashes = ctx->sc_out_hashes.get<uint64_t>(max_units * s);
-            uint32_t *d_n = ctx->sc_out_n.get<uint32_t>(max_units);
-            uint32_t *d_counts = out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr;
-            if (!d_hashes || !d_n || (out_counts && !d_counts)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+    const size_t n_waves = waves.size();
+    uint64_t max_bytes = 32, max_units = 1;
+    for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
 
-            struct Packed { std::vector<uint64_t> unit_start; std::vector<PackRun> runs; uint64_t len = 0; };
-            std::vector<Packed> packed(waves.size());
-            auto pack_wave = [&](size_t wi) {
-                const Wave &w = waves[wi];
-                Packed &P = packed[wi];
-                std::vector<PackSegment> segs;
-                segs.reserve(w.rec_end - w.rec_begin);
-                P.unit_start.assign(w.unit_end - w.unit_begin + 1, 0);
-                uint64_t off = 0;
-                for (uint64_t u = w.unit_begin; u < w.unit_end; u++) {
-                    P.unit_start[u - w.unit_begin] = off;
-                    for (uint64_t r = unit_rec_begin[u]; r < unit_rec_begin[u + 1]; r++) {
-                        if (len[r] < k) continue;
-                        segs.push_back(PackSegment{(const uint8_t *)seq[r], off, len[r]});
-                        off += len[r] + 1;                     // one separator position after every record
-                    }
+    // ---- feed paths.  A wave reaches the GPU either as ASCII (DMA straight from the caller's buffers: no host CPU work, 1 byte
+    // per base over PCIe) or 2-bit packed by host threads (pack.cpp: a quarter of the bytes, but ~6 GB/s per host core).  The two
+    // producers run side by side and claim waves from one list, so the split follows their real speeds: PCIe carries
+    // ~52 GB/s of ASCII, 15 packer threads add ~60 GB/s of bases at 15 GB/s of PCIe (hybrid: ~2x the ASCII-only rate, measured
+    // in profiles/r02_feed_path.md).  Packing is the only producer for waves with small records or pageable buffers (a
+    // cudaMemcpyAsync from pageable memory is staged by the driver at a fraction of the PCIe rate and blocks this thread).
+    // MASHGPU_HOST_PACK=0: ASCII only; =1: packed only; unset: both.  Non-DNA alphabets are ASCII only.
+    enum { FEED_ASCII = 1, FEED_PACK = 2 };
+    int feed = FEED_ASCII | FEED_PACK;
+    if (const char *env = getenv("MASHGPU_HOST_PACK")) feed = env[0] == '0' ? FEED_ASCII : (env[0] == '1' ? FEED_PACK : feed);
+    if (!is_dna_alphabet(params)) feed = FEED_ASCII;
+    // ASCII-eligible waves: every kept record is long enough for a direct copy and lies in pinned (page-locked) memory
+    std::vector<uint8_t> ascii_ok(n_waves, 1);
+    if (feed == (FEED_ASCII | FEED_PACK)) {
+        for (size_t wi = 0; wi < n_waves; wi++) {
+            const Wave &w = waves[wi];
+            bool ok = true;
+            bool probed = false;
+            for (uint64_t r = w.rec_begin; r < w.rec_end && ok; r++) {
+                if (len[r] < k) continue;
+                if (len[r] < DIRECT_COPY_MIN) ok = false;
+                else if (!probed) {          // one probe per wave: callers allocate their records the same way
+                    cudaPointerAttributes at;
+                    if (cudaPointerGetAttributes(&at, seq[r]) != cudaSuccess) { cudaGetLastError(); ok = false; }
+                    else if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) ok = false;
+                    probed = true;
                 }
-                P.unit_start[w.unit_end - w.unit_begin] = off;
-                P.len = off;
-                pack_stream(segs.data(), segs.size(), off, params->preserve_case, threads, h_codes[wi % nbuf], P.runs);
-                // everything from the end of the stream to the end of the allocation is invalid
-                P.runs.push_back(PackRun{off, groups_alloc * 32 - off});
-            };
-            auto upload_wave = [&](size_t wi) -> int {
-                const int b = (int)(wi % nbuf);
-                Packed &P = packed[wi];
-                const uint64_t groups = (P.len + 31) / 32;
-                cudaStream_t cs = ctx->copy_stream;
-                if (groups) MG_CUDA(ctx, cudaMemcpyAsync(d_codes[b], h_codes[b], groups * 8, cudaMemcpyHostToDevice, cs));
-                MG_CUDA(ctx, cudaMemsetAsync(d_inval[b], 0, groups_alloc * 4, cs));
-                PackRun *d_runs = ctx->sc_runs[b].get<PackRun>(P.runs.size());
-                if (!d_runs) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (invalid runs)");
-                MG_CUDA(ctx, cudaMemcpyAsync(d_runs, P.runs.data(), P.runs.size() * sizeof(PackRun), cudaMemcpyHostToDevice, cs));
-                const uint64_t nr = P.runs.size();
-                const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, 148 * 16);
-                apply_runs_kernel<<<std::max(1u, blocks), 256, 0, cs>>>(d_runs, nr, d_inval[b]);
-                ctx->kernel_launches++;
-                MG_CUDA(ctx, cudaGetLastError());
-                MG_CUDA(ctx, cudaEventRecord(ctx->wave_copied[b], cs));
-                return MASHGPU_OK;
-            };
-
-            // three-stage software pipeline over waves: host pack (w+2) | H2D + mask build (w+1) | kernels (w)
-            pack_wave(0);
-            MG_TRY(upload_wave(0));
-            if (waves.size() > 1) pack_wave(1);
-            int rc = MASHGPU_OK;
-            for (size_t wi = 0; wi < waves.size() && rc == MASHGPU_OK; wi++) {
-                const Wave &w = waves[wi];
-                const int b = (int)(wi % nbuf);
-                if (wi + 1 < waves.size()) rc = upload_wave(wi + 1);       // device buffer (wi+1)%2 was last used by core(wi-1): done
-                if (rc != MASHGPU_OK) break;
-                std::future<void> next_pack;
-                if (wi + 2 < waves.size()) {
-                    MG_CUDA(ctx, cudaEventSynchronize(ctx->wave_copied[b]));   // upload(wi) must have drained pinned buffer b
-                    next_pack = std::async(std::launch::async, pack_wave, wi + 2);
-                }
-                MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->wave_copied[b], 0));
-                const uint64_t nu = w.unit_end - w.unit_begin;
-                SketchStream S;
-                S.d_codes = d_codes[b]; S.d_inval = d_inval[b]; S.unit_start = packed[wi].unit_start.data(); S.n_units = nu;
-                rc = sketch_stream_core(ctx, params, S, d_hashes, d_counts, d_n, ctx->stream, nullptr);
-                if (next_pack.valid()) next_pack.get();
-                if (rc != MASHGPU_OK) break;
-                MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.unit_begin * s, d_hashes, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
-                MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.unit_begin, d_n, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
-                if (out_counts)
-                    MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.unit_begin * s, d_counts, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
-                MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             }
-            cudaStreamSynchronize(ctx->copy_stream);
-            return rc;
+            ascii_ok[wi] = ok;
         }
     }
+    // packer threads: as many as the process may actually run -- a container's CPU quota (cgroup v2 cpu.max) can be far below
+    // the visible core count, and threads beyond it are throttled together (measured on this pool's B200 box, 128 vCPUs visible,
+    // quota 16: 61 GB/s with 16 threads, 13 GB/s with 128; tools/pack_bench.py) -- minus one for this thread
+    int threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 96u);
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        long long quota = 0, period = 0;
+        if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+            threads = std::min(threads, (int)std::max(1ll, (quota + period - 1) / period));
+        fclose(f);
+    }
+    if (feed & FEED_ASCII) threads = std::max(1, threads - 1);
+    if (const char *t = getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, atoi(t));
 
-    uint64_t max_bytes = 16, max_units = 1;
-    for (auto &w : waves) { max_bytes = std::max(max_bytes, w.bytes); max_units = std::max(max_units, w.unit_end - w.unit_begin); }
+    uint64_t *d_hashes = ctx->sc_out_hashes.get<uint64_t>(max_units * s);
+    uint32_t *d_n = ctx->sc_out_n.get<uint32_t>(max_units);
+    uint32_t *d_counts = out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr;
+    if (!d_hashes || !d_n || (out_counts && !d_counts)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+
+    // ---- ASCII producer: two device wave buffers, copies on copy_stream
+    struct AsciiSlot { int64_t wave = -1; uint8_t *d = nullptr; std::vector<uint64_t> unit_start; };
+    AsciiSlot aslot[2];
     const uint64_t buf_bytes = ((max_bytes + 15) / 16) * 16 + 16;
-
-    const int nbuf = waves.size() > 1 ? 2 : 1;
-    struct { uint8_t *p; } d_stream[2] = {{nullptr}, {nullptr}};
-    struct { uint8_t *p; size_t n; } staging[2] = {{(uint8_t *)ctx->pinned[0], ctx->pinned_bytes[0]}, {(uint8_t *)ctx->pinned[1], ctx->pinned_bytes[1]}};
+    const int n_aslots = (feed & FEED_ASCII) ? (n_waves > 1 ? 2 : 1) : 0;
     cudaEvent_t *copied = ctx->wave_copied;
-    for (int b = 0; b < nbuf; b++) {
-        d_stream[b].p = ctx->sc_wave[b].get<uint8_t>(buf_bytes);
-        if (!d_stream[b].p) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (stream buffer %llu B)", (unsigned long long)buf_bytes);
+    for (int b = 0; b < n_aslots; b++) {
+        aslot[b].d = ctx->sc_wave[b].get<uint8_t>(buf_bytes);
+        if (!aslot[b].d) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (stream buffer %llu B)", (unsigned long long)buf_bytes);
         if (!copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
-    struct { uint64_t *p; } d_hashes{ctx->sc_out_hashes.get<uint64_t>(max_units * s)};
-    struct { uint32_t *p; } d_n{ctx->sc_out_n.get<uint32_t>(max_units)}, d_counts{out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr};
-    if (!d_hashes.p || !d_n.p || (out_counts && !d_counts.p)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
-
-    std::vector<std::vector<uint64_t>> wave_unit_start(waves.size());
-    auto issue_copy = [&](size_t wi) -> int {
+    auto issue_copy = [&](size_t wi, int b) -> int {
         const Wave &w = waves[wi];
-        const int b = (int)(wi % nbuf);
-        uint8_t *dst = d_stream[b].p;
+        uint8_t *dst = aslot[b].d;
         // staging size: all small records of the wave
         uint64_t small_bytes = 0;
         for (uint64_t r = w.rec_begin; r < w.rec_end; r++)
             if (len[r] >= k && len[r] < DIRECT_COPY_MIN) small_bytes += len[r] + 1;
-        if (staging[b].n < small_bytes) {
+        if (ctx->pinned_bytes[b] < small_bytes) {
             if (ctx->pinned[b]) cudaFreeHost(ctx->pinned[b]);
             ctx->pinned[b] = nullptr; ctx->pinned_bytes[b] = 0;
             if (cudaMallocHost(&ctx->pinned[b], small_bytes + small_bytes / 8) != cudaSuccess)
                 return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)small_bytes);
             ctx->pinned_bytes[b] = small_bytes + small_bytes / 8;
-            staging[b].p = (uint8_t *)ctx->pinned[b]; staging[b].n = ctx->pinned_bytes[b];
         }
-        std::vector<uint64_t> &us = wave_unit_start[wi];
+        uint8_t *stage = (uint8_t *)ctx->pinned[b];
+        std::vector<uint64_t> &us = aslot[b].unit_start;
         us.assign(w.unit_end - w.unit_begin + 1, 0);
         // separator offsets of the directly copied records (pinned list -> device -> one kernel); list full: 1-byte memsets
         if (!ctx->pinned_sep[b]) {
@@ -830,7 +809,7 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         uint64_t run_dst = 0, run_src = 0, run_len = 0;   // pending staged run
         auto flush_run = [&]() -> cudaError_t {
             if (!run_len) return cudaSuccess;
-            cudaError_t e = cudaMemcpyAsync(dst + run_dst, staging[b].p + run_src, run_len, cudaMemcpyHostToDevice, ctx->copy_stream);
+            cudaError_t e = cudaMemcpyAsync(dst + run_dst, stage + run_src, run_len, cudaMemcpyHostToDevice, ctx->copy_stream);
             run_len = 0;
             return e;
         };
@@ -845,8 +824,8 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
                     else MG_CUDA(ctx, cudaMemsetAsync(dst + off + len[r], 0, 1, ctx->copy_stream));
                 } else {
                     if (!run_len) { run_dst = off; run_src = st_off; }
-                    memcpy(staging[b].p + st_off, seq[r], len[r]);
-                    staging[b].p[st_off + len[r]] = 0;
+                    memcpy(stage + st_off, seq[r], len[r]);
+                    stage[st_off + len[r]] = 0;
                     st_off += len[r] + 1;
                     run_len += len[r] + 1;
                 }
@@ -862,29 +841,179 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         }
         us[w.unit_end - w.unit_begin] = off;
         MG_CUDA(ctx, cudaEventRecord(copied[b], ctx->copy_stream));
+        aslot[b].wave = (int64_t)wi;
         return MASHGPU_OK;
     };
 
-    MG_TRY(issue_copy(0));
-    int rc = MASHGPU_OK;
-    for (size_t wi = 0; wi < waves.size() && rc == MASHGPU_OK; wi++) {
-        const Wave &w = waves[wi];
-        const int b = (int)(wi % nbuf);
-        if (wi + 1 < waves.size()) rc = issue_copy(wi + 1);    // overlaps with this wave's kernels
-        if (rc != MASHGPU_OK) break;
-        MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, copied[b], 0));
-        const uint64_t nu = w.unit_end - w.unit_begin;
-        SketchStream S;
-        S.d_stream = d_stream[b].p; S.unit_start = wave_unit_start[wi].data(); S.n_units = nu;
-        rc = sketch_stream_core(ctx, params, S, d_hashes.p, out_counts ? d_counts.p : nullptr, d_n.p, ctx->stream, nullptr);
-        if (rc != MASHGPU_OK) break;
-        MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.unit_begin * s, d_hashes.p, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
-        MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.unit_begin, d_n.p, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_counts)
-            MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.unit_begin * s, d_counts.p, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
-        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // ---- packed producer: two pinned code buffers, one packing job at a time on `threads` host threads; the job itself enqueues
+    // its upload (codes, invalid runs -> mask) on pack_stream, so a finished future means "event recorded"
+    struct PackSlot {
+        int64_t wave = -1;
+        uint64_t *h_codes = nullptr, *d_codes = nullptr; uint32_t *d_inval = nullptr;
+        std::vector<uint64_t> unit_start; std::vector<PackRun> runs; uint64_t len = 0;
+        std::future<int> job;
+    };
+    PackSlot pslot[2];
+    const int n_pslots = (feed & FEED_PACK) ? (n_waves > 1 ? 2 : 1) : 0;
+    const uint64_t max_tiles = (max_bytes + SCAN_TILE - 1) / SCAN_TILE;
+    const uint64_t groups_alloc = max_tiles * (SCAN_TILE / 32) + 64;       // tile-padded + halo
+    for (int b = 0; b < n_pslots; b++) {
+        pslot[b].d_codes = ctx->sc_codes[b].get<uint64_t>(groups_alloc);
+        pslot[b].d_inval = ctx->sc_inval[b].get<uint32_t>(groups_alloc);
+        if (!pslot[b].d_codes || !pslot[b].d_inval) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (packed stream of %llu groups)", (unsigned long long)groups_alloc);
+        if (ctx->pinned_codes_bytes[b] < groups_alloc * 8) {
+            if (ctx->pinned_codes[b]) cudaFreeHost(ctx->pinned_codes[b]);
+            ctx->pinned_codes[b] = nullptr; ctx->pinned_codes_bytes[b] = 0;
+            if (cudaMallocHost(&ctx->pinned_codes[b], groups_alloc * 8) != cudaSuccess)
+                return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (%llu B)", (unsigned long long)(groups_alloc * 8));
+            ctx->pinned_codes_bytes[b] = groups_alloc * 8;
+        }
+        pslot[b].h_codes = (uint64_t *)ctx->pinned_codes[b];
+        if (!ctx->pack_copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pack_copied[b], cudaEventDisableTiming));
     }
+    if (n_pslots && !ctx->pack_stream) MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pack_stream, cudaStreamNonBlocking));
+    auto pack_job = [&](size_t wi, int b) -> int {
+        cudaSetDevice(ctx->device);
+        const Wave &w = waves[wi];
+        PackSlot &P = pslot[b];
+        std::vector<PackSegment> segs;
+        segs.reserve(w.rec_end - w.rec_begin);
+        P.unit_start.assign(w.unit_end - w.unit_begin + 1, 0);
+        uint64_t off = 0;
+        for (uint64_t u = w.unit_begin; u < w.unit_end; u++) {
+            P.unit_start[u - w.unit_begin] = off;
+            for (uint64_t r = unit_rec_begin[u]; r < unit_rec_begin[u + 1]; r++) {
+                if (len[r] < k) continue;
+                segs.push_back(PackSegment{(const uint8_t *)seq[r], off, len[r]});
+                off += len[r] + 1;                     // one separator position after every record
+            }
+        }
+        P.unit_start[w.unit_end - w.unit_begin] = off;
+        P.len = off;
+        pack_stream(segs.data(), segs.size(), off, params->preserve_case, threads, P.h_codes, P.runs);
+        P.runs.push_back(PackRun{off, groups_alloc * 32 - off});      // everything from the end of the stream to the end of the allocation is invalid
+        // upload: codes, zeroed mask, runs -> mask
+        const uint64_t groups = (P.len + 31) / 32;
+        cudaStream_t cs = ctx->pack_stream;
+        if (groups && cudaMemcpyAsync(P.d_codes, P.h_codes, groups * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) return MASHGPU_ERR_CUDA;
+        if (cudaMemsetAsync(P.d_inval, 0, groups_alloc * 4, cs) != cudaSuccess) return MASHGPU_ERR_CUDA;
+        PackRun *d_runs = ctx->sc_runs[b].get<PackRun>(P.runs.size());
+        if (!d_runs) return MASHGPU_ERR_NOMEM;
+        if (cudaMemcpyAsync(d_runs, P.runs.data(), P.runs.size() * sizeof(PackRun), cudaMemcpyHostToDevice, cs) != cudaSuccess) return MASHGPU_ERR_CUDA;
+        const uint64_t nr = P.runs.size();
+        const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, 148 * 16);
+        apply_runs_kernel<<<std::max(1u, blocks), 256, 0, cs>>>(d_runs, nr, P.d_inval);
+        if (cudaGetLastError() != cudaSuccess) return MASHGPU_ERR_CUDA;
+        if (cudaEventRecord(ctx->pack_copied[b], cs) != cudaSuccess) return MASHGPU_ERR_CUDA;
+        if (cudaEventSynchronize(ctx->pack_copied[b]) != cudaSuccess) return MASHGPU_ERR_CUDA;      // P.runs / pinned codes are reused by the next job
+        return MASHGPU_OK;
+    };
+
+    // ---- scheduler: both producers claim the next unclaimed wave they may take; this thread runs the kernels of whichever
+    // wave is ready first and hands its sketches back
+    std::vector<uint8_t> claimed(n_waves, 0);
+    size_t a_cursor = 0, p_cursor = 0, done = 0;
+    auto claim = [&](size_t &cursor, bool need_ascii) -> int64_t {
+        for (size_t wi = cursor; wi < n_waves; wi++) {
+            if (claimed[wi]) { if (wi == cursor) cursor++; continue; }
+            if (need_ascii && !ascii_ok[wi] && (feed & FEED_PACK)) continue;      // left to the packer
+            claimed[wi] = 1;
+            return (int64_t)wi;
+        }
+        return -1;
+    };
+    int rc = MASHGPU_OK;
+    bool packer_busy = false;
+    auto run_wave = [&](size_t wi, const SketchStream &S) -> int {
+        const Wave &w = waves[wi];
+        const uint64_t nu = w.unit_end - w.unit_begin;
+        int r = sketch_stream_core(ctx, params, S, d_hashes, d_counts, d_n, ctx->stream, nullptr);
+        if (r != MASHGPU_OK) return r;
+        MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.unit_begin * s, d_hashes, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.unit_begin, d_n, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_counts)
+            MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.unit_begin * s, d_counts, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MASHGPU_OK;
+    };
+    while (done < n_waves && rc == MASHGPU_OK) {
+        // 1. keep the producers busy
+        for (int b = 0; b < n_aslots && rc == MASHGPU_OK; b++)
+            if (aslot[b].wave < 0) {
+                const int64_t wi = claim(a_cursor, true);
+                if (wi >= 0) rc = issue_copy((size_t)wi, b);
+            }
+        if (rc != MASHGPU_OK) break;
+        if (!packer_busy)
+            for (int b = 0; b < n_pslots; b++)
+                if (pslot[b].wave < 0) {
+                    const int64_t wi = claim(p_cursor, false);
+                    if (wi >= 0) {
+                        pslot[b].wave = wi;
+                        pslot[b].job = std::async(std::launch::async, pack_job, (size_t)wi, b);
+                        packer_busy = true;
+                    }
+                    break;
+                }
+        // 2. a finished wave?  packed first (its slot also frees the packer), then ASCII copies in issue order
+        int ready_p = -1, ready_a = -1;
+        for (int b = 0; b < n_pslots; b++)
+            if (pslot[b].wave >= 0 && pslot[b].job.valid() && pslot[b].job.wait_for(std::chrono::seconds(0)) == std::future_status::ready) { ready_p = b; break; }
+        if (ready_p < 0) {
+            int64_t best = -1;
+            for (int b = 0; b < n_aslots; b++)
+                if (aslot[b].wave >= 0 && (best < 0 || aslot[b].wave < best)) {
+                    const cudaError_t q = cudaEventQuery(copied[b]);
+                    if (q == cudaSuccess) { ready_a = b; best = aslot[b].wave; }
+                    else if (q != cudaErrorNotReady) { rc = fail(ctx, MASHGPU_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(q)); break; }
+                    else cudaGetLastError();
+                }
+        }
+        if (rc != MASHGPU_OK) break;
+        if (ready_p >= 0) {
+            PackSlot &P = pslot[ready_p];
+            rc = P.job.get();
+            packer_busy = false;
+            if (rc != MASHGPU_OK) { rc = fail(ctx, rc, "packed upload of wave %lld failed", (long long)P.wave); break; }
+            ctx->kernel_launches++;             // apply_runs_kernel
+            SketchStream S;
+            S.d_codes = P.d_codes; S.d_inval = P.d_inval; S.unit_start = P.unit_start.data(); S.n_units = waves[P.wave].unit_end - waves[P.wave].unit_begin;
+            // the other pinned buffer is free: let the packer start on its next wave while the kernels of this one run
+            for (int b = 0; b < n_pslots; b++)
+                if (pslot[b].wave < 0) {
+                    const int64_t wi = claim(p_cursor, false);
+                    if (wi >= 0) { pslot[b].wave = wi; pslot[b].job = std::async(std::launch::async, pack_job, (size_t)wi, b); packer_busy = true; }
+                    break;
+                }
+            rc = run_wave((size_t)P.wave, S);
+            P.wave = -1;
+            done++;
+        } else if (ready_a >= 0) {
+            AsciiSlot &A = aslot[ready_a];
+            SketchStream S;
+            S.d_stream = A.d; S.unit_start = A.unit_start.data(); S.n_units = waves[A.wave].unit_end - waves[A.wave].unit_begin;
+            const size_t wi = (size_t)A.wave;
+            rc = run_wave(wi, S);
+            A.wave = -1;
+            done++;
+        } else {
+            // nothing ready: wait for whichever producer is in flight
+            bool waited = false;
+            for (int b = 0; b < n_pslots && !waited; b++)
+                if (pslot[b].wave >= 0 && pslot[b].job.valid()) { pslot[b].job.wait_for(std::chrono::microseconds(200)); waited = true; }
+            if (!waited) {
+                int64_t best = -1; int bb = -1;
+                for (int b = 0; b < n_aslots; b++)
+                    if (aslot[b].wave >= 0 && (best < 0 || aslot[b].wave < best)) { best = aslot[b].wave; bb = b; }
+                if (bb >= 0) MG_CUDA(ctx, cudaEventSynchronize(copied[bb]));
+                else { rc = fail(ctx, MASHGPU_ERR_INVALID, "feed scheduler stalled (%zu of %zu waves done)", done, n_waves); break; }
+            }
+        }
+    }
+    for (int b = 0; b < n_pslots; b++)
+        if (pslot[b].job.valid()) pslot[b].job.wait();          // never leave a packing thread behind (it references this frame)
     cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->pack_stream) cudaStreamSynchronize(ctx->pack_stream);
     return rc;
 }
 

@@ -23,6 +23,22 @@ struct ScreenProbe {
     uint32_t *cnt;
     uint32_t log2cap;
     uint64_t hmax;
+    const uint32_t *bitmap;     // value-indexed presence bitmap over the reference hashes (NULL: none), see scan.cuh
+    uint32_t bitmap_shift;
+};
+
+// One sketch_stream pass in flight: the kernels are enqueued by sketch_stream_enqueue and the per-unit status flags come back
+// into pinned memory; sketch_stream_finalize waits for them and re-runs flagged units exactly.  The stream data, the output
+// buffers and the context's scratch must stay untouched between the two calls (one ticket in flight per context).
+struct SketchTicket {
+    bool active = false;
+    mashgpu_sketch_params params{};
+    SketchStream S;
+    std::vector<uint64_t> unit_start;       // own copy of S.unit_start
+    uint64_t *d_out_hashes = nullptr; uint32_t *d_out_counts = nullptr, *d_out_n = nullptr;
+    cudaStream_t st = nullptr;
+    uint64_t *d_qtarget = nullptr, *d_qtstar = nullptr;
+    std::vector<uint8_t> scan_args;         // the ScanArgs of the pass (base of the re-runs), kept opaque here
 };
 
 int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p);
@@ -30,5 +46,9 @@ bool is_dna_alphabet(const mashgpu_sketch_params *p);
 int sketch_stream_core(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S,
                        uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
                        const ScreenProbe *probe);
+int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const SketchStream &S,
+                          uint64_t *d_out_hashes, uint32_t *d_out_counts, uint32_t *d_out_n, cudaStream_t st,
+                          const ScreenProbe *probe, SketchTicket &t);
+int sketch_stream_finalize(mashgpu_ctx *ctx, SketchTicket &t);
 
 }  // namespace mashgpu

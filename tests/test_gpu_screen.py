@@ -98,3 +98,73 @@ def test_winner_take_all_matches_oracle(gpu, oracle):
         job.close()
     check(res, want)
     assert not np.array_equal(want["shared"], want_plain["shared"])
+
+
+def _refs_and_reads(oracle, po, s, n_reads, seed, with_tiny=True):
+    genomes = [synth_genome(140 + i, 120_000) for i in range(3)]
+    tiny = [synth_genome(700 + i, 1500 + 211 * i) for i in range(6)] if with_tiny else []     # sketches that span the whole hash range
+    allg = genomes + tiny
+    ref = np.full((len(allg), s), np.uint64(2**64 - 1)); ref_n = np.zeros(len(allg), np.uint32)
+    for i, g in enumerate(allg):
+        h, _, _ = oracle.sketch_unit([bytes(g)], po, s=s)
+        ref[i, :h.size] = h; ref_n[i] = h.size
+    rng = np.random.Generator(np.random.PCG64(seed))
+    reads = []
+    pool = genomes[:2] + tiny[:2]
+    for _ in range(n_reads):
+        g = pool[int(rng.integers(0, len(pool)))]
+        a = int(rng.integers(0, g.size - 150))
+        r = g[a:a + 150].copy()
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, 150))] = ord("N")
+        reads.append(bytes(r))
+    return ref, ref_n, reads
+
+
+@pytest.mark.parametrize("bitmap", ["1", "0"])
+def test_table_spanning_the_whole_hash_range(gpu, oracle, monkeypatch, bitmap):
+    # A reference .msh with small genomes: their bottom-s reaches up to ~2^64, so EVERY k-mer of the mixture is a table
+    # candidate (no "largest reference hash" shortcut).  Per-lane probe, with and without the value-indexed bitmap.
+    monkeypatch.setenv("MASHGPU_SCREEN_BITMAP", bitmap)
+    s = 300
+    p = gpu.params(k=21, s=s)
+    po = oracle.params(k=21)
+    ref, ref_n, reads = _refs_and_reads(oracle, po, s, 5000, seed=11)
+    assert ref[:, :][np.arange(ref.shape[0]), ref_n - 1].max() > np.uint64(2**63)       # the table really spans the range
+    chunks = [b"".join(b"*" + r for r in reads[i:i + 1000]) for i in range(0, len(reads), 1000)]
+    want = oracle.screen(ref, ref_n, chunks, po, s=s)
+    check(run_screen(gpu, ref, ref_n, p, chunks), want)
+    assert want["shared"][3] > 0 and want["shared"][5] == 0
+
+
+def test_many_small_host_chunks_are_joined(gpu, oracle):
+    # the reference feeds 1 MiB HashInputs; smaller host chunks are joined inside the library before a kernel pass
+    s = 200
+    p = gpu.params(k=21, s=s)
+    po = oracle.params(k=21)
+    ref, ref_n, reads = _refs_and_reads(oracle, po, s, 3000, seed=12, with_tiny=False)
+    chunks = [b"".join(b"*" + r for r in reads[i:i + 7]) for i in range(0, len(reads), 7)]       # ~1 KB each
+    want = oracle.screen(ref, ref_n, chunks, po, s=s)
+    check(run_screen(gpu, ref, ref_n, p, chunks), want)
+
+
+def test_large_host_chunks_are_pipelined(gpu, oracle):
+    # chunks above the joining threshold go through the two-buffer pipeline (copy of chunk i+1 overlaps the kernels of chunk i)
+    s = 300
+    p = gpu.params(k=21, s=s)
+    po = oracle.params(k=21)
+    ref, ref_n, reads = _refs_and_reads(oracle, po, s, 90_000, seed=13)
+    per = 30_000                                                   # 30 000 x 151 B = 4.5 MB per chunk
+    chunks = [b"".join(b"*" + r for r in reads[i:i + per]) for i in range(0, len(reads), per)]
+    assert min(len(c) for c in chunks) >= 4 << 20
+    want = oracle.screen(ref, ref_n, chunks, po, s=s)
+    job = gpu.screen_open(ref, ref_n, p)
+    try:
+        for c in chunks:
+            buf = bytearray(c)
+            job.feed(bytes(buf))
+            buf[:] = b"N" * len(buf)          # the caller may reuse its buffer as soon as feed() returns
+        res = job.finish()
+    finally:
+        job.close()
+    check(res, want)

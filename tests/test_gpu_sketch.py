@@ -247,6 +247,36 @@ def test_multi_wave_batch(gpu, oracle, monkeypatch, pack):
         assert_sketch_equal(out, u, oh)
 
 
+@pytest.mark.parametrize("mode", ["hybrid", "ascii", "packed"])
+def test_feed_scheduler_many_waves_pinned_buffers(gpu, oracle, monkeypatch, mode):
+    # The two feed paths of mashgpu_sketch_batch side by side: records in page-locked memory (eligible for the direct ASCII
+    # copy), waves cut small (MASHGPU_WAVE_BYTES / MASHGPU_WAVE_UNITS are test hooks) so that the ASCII producer and the host
+    # packer both claim waves of one batch; some units are made of small records, which only the packer (or, ASCII only, the
+    # pinned staging buffer) takes.  Same sketches whichever producer fed a wave.
+    import torch
+    monkeypatch.setenv("MASHGPU_WAVE_BYTES", str(700_000))
+    monkeypatch.setenv("MASHGPU_WAVE_UNITS", "3")
+    if mode != "hybrid":
+        monkeypatch.setenv("MASHGPU_HOST_PACK", "0" if mode == "ascii" else "1")
+    p = gpu.params(k=21, s=400)
+    po = oracle.params(k=21)
+    recs, uor, keep = [], [], []
+    for u in range(14):
+        n_rec = 1 if u % 4 else 3
+        for r in range(n_rec):
+            ln = (300_000 + 4099 * u) if n_rec == 1 else (5_000 + 911 * r)
+            g = synth_genome(900 + 10 * u + r, ln, n_runs=2 if u % 3 == 0 else 0, lower_frac=0.03 if u % 5 == 0 else 0.0)
+            t = torch.from_numpy(g.copy()).pin_memory()
+            keep.append(t)
+            recs.append(t.numpy()); uor.append(u)
+    out = gpu.sketch(recs, p, unit_of_record=uor, n_units=14, counts=True)
+    for u in range(14):
+        oh, oc, olen = oracle.sketch_unit([bytes(r) for r, x in zip(recs, uor) if x == u], po, s=400, counts=True)
+        assert out[2][u] == olen
+        assert_sketch_equal(out, u, oh)
+        assert np.array_equal(out[3][u, :out[1][u]], oc)
+
+
 def test_large_sketch_size_goes_through_global_sort(gpu, oracle):
     # s = 5000: the unit's candidate table (2^16 slots) does not fit select_kernel's shared-memory sort, so the unit takes
     # the exact re-run path (global-memory table + radix sort) -- same answer, `mash sketch -s 5000`
