@@ -51,6 +51,9 @@ typedef struct mashgpu_sketch_params {
     int32_t noncanonical;
     int32_t preserve_case;
     uint8_t alphabet[256];    /* Parameters::alphabet; filled by mashgpu_set_alphabet */
+    uint32_t min_copies;      /* `-m`: MinHashHeap multiplicityMinimum (Sketch.cpp:1186, reads mode; MinHashHeap.cpp:96-118): a hash enters
+                                 the sketch at its m-th occurrence.  0 or 1 = off.  The sketch is then the s smallest hashes seen at
+                                 least m times, and the multiplicities follow the heap exactly (tests/test_gpu_sketch.py). */
 } mashgpu_sketch_params;
 /* GPU path coverage: alphabet == {A,C,G,T} (canonical or not, any k 1..32, either case mode) runs the 4-bit
  * packed DNA kernels; any other alphabet requires noncanonical != 0 (the protein setting of the reference,

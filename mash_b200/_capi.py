@@ -31,7 +31,7 @@ class SketchParams(C.Structure):
     """mashgpu_sketch_params (Sketch::Parameters subset, reference Sketch.h:34-109)."""
     _fields_ = [("kmer_size", C.c_int32), ("sketch_size", C.c_uint32), ("seed", C.c_uint32),
                 ("use64", C.c_int32), ("noncanonical", C.c_int32), ("preserve_case", C.c_int32),
-                ("alphabet", C.c_uint8 * 256)]
+                ("alphabet", C.c_uint8 * 256), ("min_copies", C.c_uint32)]
 
     @property
     def kmer_space(self):
@@ -170,8 +170,9 @@ class Engine:
             raise MashGpuError(rc, (self.lib.mashgpu_last_error(self.h) or b"").decode())
 
     # ---- parameters (sketchParameterSetup / setAlphabetFromString) --------------------------------------
-    def params(self, k=21, s=1000, seed=42, alphabet=ALPHABET_NUCLEOTIDE, noncanonical=False, preserve_case=False):
+    def params(self, k=21, s=1000, seed=42, alphabet=ALPHABET_NUCLEOTIDE, noncanonical=False, preserve_case=False, min_copies=1):
         p = SketchParams()
+        p.min_copies = min_copies
         p.kmer_size = k
         p.sketch_size = s
         p.seed = seed

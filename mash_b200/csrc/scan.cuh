@@ -56,6 +56,7 @@ struct ScanArgs {
     uint32_t *unit_flags;         // bit0: table overflow
     uint32_t *unit_maxhash;       // occurrences of the hash value 2^64-1 (cannot be a table key)
     int64_t only_unit;            // >= 0: ignore every other unit (exact re-run)
+    uint32_t min_copies;          // `-m` (>= 1): tab_first holds min_copies positions per slot, the smallest stream positions of the key
     // screen: reference hash table (distinct keys, EMPTY_KEY when free) with u32 hit counters
     const uint64_t *ref_keys;
     const uint32_t *ref_idx;      // slot -> index of the key in the sorted distinct key list (deterministic across ranks)
@@ -125,7 +126,17 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
     const int64_t slot = table_add(a.tab_keys + a.tab_off[u], a.tab_cnt + a.tab_off[u], a.tab_log2[u], hash);
     if (slot < 0) { atomicOr(&a.unit_flags[u], 1u); return; }
     if (a.tab_first) {
-        atomicMin((unsigned long long *)&a.tab_first[a.tab_off[u] + slot], (unsigned long long)pos);
+        // the m smallest positions of the key, ascending: a cascade of atomic minima -- level i ends up with the (i+1)-th smallest
+        // position whatever the arrival order, because every value that reaches a level is either its final minimum or is passed
+        // on exactly once.  Level m-1 is the position at which MinHashHeap promotes the hash (MinHashHeap.cpp:96-100); m = 1: the
+        // first occurrence.
+        unsigned long long *f = (unsigned long long *)a.tab_first + (a.tab_off[u] + (uint64_t)slot) * a.min_copies;
+        unsigned long long x = pos;
+        for (uint32_t i = 0; i < a.min_copies; i++) {
+            const unsigned long long old = atomicMin(&f[i], x);
+            if (old == EMPTY_KEY) break;            // the level was empty: nothing to pass on
+            if (old > x) x = old;
+        }
         atomicMax((unsigned long long *)&a.tab_last[a.tab_off[u] + slot], (unsigned long long)pos);
     }
 }

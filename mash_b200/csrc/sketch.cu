@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t table_count(const uint64_t *keys, const uint
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     uint32_t unit_begin, uint32_t n_units, const uint64_t *unit_t, const uint64_t *tab_off, const uint32_t *tab_log2,
     const uint64_t *tab_keys, const uint32_t *tab_cnt, const uint32_t *unit_maxhash, uint32_t *unit_flags,
-    uint32_t s, uint64_t capped_t, uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n)
+    uint32_t s, uint64_t capped_t, uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint32_t min_copies)
 {
     extern __shared__ uint64_t sk[];
     __shared__ uint32_t n_s;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < cap; i += SEL_THREADS) {
         uint64_t k = keys[i];
-        if (k != EMPTY_KEY) sk[atomicAdd(&n_s, 1u)] = k;
+        if (k != EMPTY_KEY && cnt[i] >= min_copies) sk[atomicAdd(&n_s, 1u)] = k;      // `-m`: only hashes seen at least m times qualify
     }
     __syncthreads();
     const uint32_t n = n_s;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
             __syncthreads();
         }
     }
-    const uint32_t n_max = unit_maxhash[u] ? 1u : 0u;          // the value 2^64-1 itself, largest possible
+    const uint32_t n_max = (unit_maxhash[u] && unit_maxhash[u] >= min_copies) ? 1u : 0u;          // the value 2^64-1 itself, largest possible
     const uint32_t total = n + n_max;
     const uint32_t m = total < s ? total : s;
     if (threadIdx.x == 0) {
@@ -166,8 +166,9 @@ __device__ __forceinline__ int64_t table_find(const uint64_t *keys, uint32_t log
 __global__ void __launch_bounds__(SEL_THREADS) quirk_kernel(
     uint32_t unit_begin, uint32_t n_units, uint32_t s, const uint64_t *out_hashes, uint32_t *out_counts, const uint32_t *out_n,
     const uint64_t *tab_off, const uint32_t *tab_log2, const uint64_t *tab_keys, const uint32_t *tab_cnt,
-    const uint64_t *tab_first, const uint64_t *tab_last, uint32_t *unit_flags, uint64_t *quirk_target, uint64_t *quirk_tstar)
+    const uint64_t *tab_first, const uint64_t *tab_last, uint32_t *unit_flags, uint64_t *quirk_target, uint64_t *quirk_tstar, uint32_t m)
 {
+    // m = multiplicityMinimum: a hash is promoted into the heap at its m-th occurrence (tab_first level m-1) holding count m
     __shared__ unsigned long long tstar_s;
     const uint32_t u = unit_begin + blockIdx.x;
     if (u >= unit_begin + n_units) return;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(SEL_THREADS) quirk_kernel(
     unsigned long long local = 0;
     for (uint32_t i = threadIdx.x; i < s; i += SEL_THREADS) {
         int64_t slot = table_find(keys, lg, out_hashes[(uint64_t)u * s + i]);
-        if (slot >= 0) local = max(local, (unsigned long long)tab_first[tab_off[u] + slot]);
+        if (slot >= 0) local = max(local, (unsigned long long)tab_first[(tab_off[u] + slot) * m + (m - 1)]);
     }
     atomicMax(&tstar_s, local);
     __syncthreads();
@@ -190,9 +191,9 @@ __global__ void __launch_bounds__(SEL_THREADS) quirk_kernel(
         int64_t slot = table_find(keys, lg, key);
         if (slot >= 0) {
             const uint32_t c = tab_cnt[tab_off[u] + slot];
-            const uint64_t f = tab_first[tab_off[u] + slot], l = tab_last[tab_off[u] + slot];
-            if (c > 1 && l > tstar) {
-                if (f == tstar) out_counts[(uint64_t)u * s + s - 1] = 1;
+            const uint64_t f = tab_first[(tab_off[u] + slot) * m + (m - 1)], l = tab_last[tab_off[u] + slot];
+            if (c > m && l > tstar) {
+                if (f == tstar) out_counts[(uint64_t)u * s + s - 1] = m;
                 else { quirk_target[u] = key; quirk_tstar[u] = tstar; atomicOr(&unit_flags[u], 8u); }
             }
         }
@@ -200,12 +201,12 @@ __global__ void __launch_bounds__(SEL_THREADS) quirk_kernel(
 }
 
 // Large tables: compact non-empty keys to scratch (then cub radix sort on the host side of this file).
-__global__ void compact_table_kernel(const uint64_t *keys, uint64_t cap, uint64_t *out, unsigned long long *out_n)
+__global__ void compact_table_kernel(const uint64_t *keys, const uint32_t *cnt, uint32_t min_copies, uint64_t cap, uint64_t *out, unsigned long long *out_n)
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= cap) return;
     uint64_t k = keys[i];
-    if (k != EMPTY_KEY) out[atomicAdd(out_n, 1ull)] = k;
+    if (k != EMPTY_KEY && cnt[i] >= min_copies) out[atomicAdd(out_n, 1ull)] = k;
 }
 
 // Packed source: expand the host's list of invalid runs into the 1-bit-per-position mask.  One warp per run; runs
@@ -258,6 +259,7 @@ int validate_sketch_params(mashgpu_ctx *ctx, const mashgpu_sketch_params *p)
     if ((p->use64 != 0) != (std::pow((double)n, (double)p->kmer_size) > std::pow(2.0, 32.0)))
         return fail(ctx, MASHGPU_ERR_INVALID, "use64=%d contradicts the reference rule alphabetSize^k > 2^32 for k=%d, %d letters (Sketch.cpp:1136)", p->use64, p->kmer_size, n);
     if (p->alphabet[0]) return fail(ctx, MASHGPU_ERR_INVALID, "byte 0 cannot be an alphabet letter");
+    if (p->min_copies > 255) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "min_copies (-m) above 255");
     if (!dna && !p->noncanonical)
         return fail(ctx, MASHGPU_ERR_UNSUPPORTED,
                     "canonical k-mers are only defined for the alphabet {A,C,G,T}; other alphabets must be non-canonical "
@@ -344,6 +346,7 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
 {
     const uint64_t span = S.unit_start[u + 1] - S.unit_start[u];
     const uint32_t s = p->sketch_size;
+    const uint32_t mc = std::max(1u, p->min_copies);
     double factor = SURVIVOR_FACTOR;
     ctx->exact_reruns++;
     for (int attempt = 0; attempt < 64; attempt++) {
@@ -357,12 +360,12 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
         DevBuf<uint64_t> first, last;
         const bool want_counts = d_out_counts != nullptr;
         if (keys.alloc(cap) != cudaSuccess || cnt.alloc(cap) != cudaSuccess || meta.alloc(4) != cudaSuccess || small.alloc(3) != cudaSuccess ||
-            (want_counts && (first.alloc(cap) != cudaSuccess || last.alloc(cap) != cudaSuccess)))
+            (want_counts && (first.alloc(cap * mc) != cudaSuccess || last.alloc(cap) != cudaSuccess)))
             return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory in exact re-run (table of %llu slots)", (unsigned long long)cap);
         MG_CUDA(ctx, cudaMemsetAsync(keys.p, 0xFF, cap * 8, st));
         MG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, cap * 4, st));
         if (want_counts) {
-            MG_CUDA(ctx, cudaMemsetAsync(first.p, 0xFF, cap * 8, st));
+            MG_CUDA(ctx, cudaMemsetAsync(first.p, 0xFF, cap * mc * 8, st));
             MG_CUDA(ctx, cudaMemsetAsync(last.p, 0, cap * 8, st));
         }
         uint64_t h_meta[4] = {t, 0, 0, 0};
@@ -394,12 +397,12 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
         if (comp.alloc(cap) != cudaSuccess || sorted.alloc(cap) != cudaSuccess || d_n.alloc(1) != cudaSuccess)
             return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory in exact re-run");
         MG_CUDA(ctx, cudaMemsetAsync(d_n.p, 0, 8, st));
-        compact_table_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(keys.p, cap, comp.p, d_n.p);
+        compact_table_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(keys.p, cnt.p, mc, cap, comp.p, d_n.p);
         ctx->kernel_launches++;
         unsigned long long n = 0;
         MG_CUDA(ctx, cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
-        const uint64_t total = n + (h_small[2] ? 1 : 0);
+        const uint64_t total = n + ((h_small[2] && h_small[2] >= mc) ? 1 : 0);
         if (total < s && !keep_all) continue;                                     // still too few: grow
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, comp.p, sorted.p, (int)n, 0, 64, st);
@@ -418,7 +421,7 @@ static int rerun_unit(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, const Sk
         MG_CUDA(ctx, cudaMemcpyAsync(d_out_n + u, &m, 4, cudaMemcpyHostToDevice, st));
         if (want_counts && m == s) {   // the reference's top-of-heap counting quirk (see quirk_kernel)
             quirk_kernel<<<1, SEL_THREADS, 0, st>>>(u, 1, s, d_out_hashes, d_out_counts, d_out_n, meta.p + 1 - u, small.p - u, keys.p, cnt.p,
-                                                    first.p, last.p, small.p + 1 - u, meta.p + 2 - u, meta.p + 3 - u);
+                                                    first.p, last.p, small.p + 1 - u, meta.p + 2 - u, meta.p + 3 - u, mc);
             ctx->kernel_launches++;
             MG_CUDA(ctx, cudaMemcpyAsync(h_small, small.p, sizeof h_small, cudaMemcpyDeviceToHost, st));
             MG_CUDA(ctx, cudaMemcpyAsync(h_meta, meta.p, sizeof h_meta, cudaMemcpyDeviceToHost, st));
@@ -481,12 +484,13 @@ int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, cons
     if (!d_start.p || !d_t.p || !d_off.p || !d_log2.p || !d_flags.p || !d_maxhash.p || !d_keys.p || !d_cnt.p || !d_tmax.p)
         return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (%llu candidate slots for %u units)", (unsigned long long)slots, n_units);
     const bool want_counts = d_out_counts != nullptr;
+    const uint32_t mc = probe ? 1u : std::max(1u, p->min_copies);      // the screen mixture is a plain MinHashHeap (CommandScreen.cpp:114-119)
     uint64_t *d_first = nullptr, *d_last = nullptr, *d_qtarget = nullptr, *d_qtstar = nullptr;
     if (want_counts) {
-        d_first = ctx->sc_first.get<uint64_t>(slots); d_last = ctx->sc_last.get<uint64_t>(slots);
+        d_first = ctx->sc_first.get<uint64_t>(slots * mc); d_last = ctx->sc_last.get<uint64_t>(slots);
         d_qtarget = ctx->sc_qtarget.get<uint64_t>(n_units); d_qtstar = ctx->sc_qtstar.get<uint64_t>(n_units);
         if (!d_first || !d_last || !d_qtarget || !d_qtstar) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (first/last occurrence tables)");
-        MG_CUDA(ctx, cudaMemsetAsync(d_first, 0xFF, slots * 8ull, st));
+        MG_CUDA(ctx, cudaMemsetAsync(d_first, 0xFF, slots * mc * 8ull, st));
         MG_CUDA(ctx, cudaMemsetAsync(d_last, 0, slots * 8ull, st));
     }
     MG_CUDA(ctx, cudaMemcpyAsync(d_start.p, S.unit_start, (n_units + 1) * 8ull, cudaMemcpyHostToDevice, st));
@@ -523,6 +527,7 @@ int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, cons
     a.tab_first = d_first;
     a.tab_last = d_last;
     a.only_unit = -1;
+    a.min_copies = mc;
     if (probe) {
         a.ref_keys = probe->keys; a.ref_idx = probe->idx; a.ref_cnt = probe->cnt; a.ref_log2 = probe->log2cap; a.ref_hmax = probe->hmax;
         a.ref_bitmap = probe->bitmap; a.ref_bitmap_shift = probe->bitmap_shift;
@@ -551,12 +556,12 @@ int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, cons
     for (uint32_t u = 0; u < n_units; u++) max_log2 = std::max(max_log2, std::min(h_log2[u], SEL_MAX_LOG2));
     select_kernel<<<n_units, SEL_THREADS, (size_t)8 << max_log2, st>>>(0, n_units, d_t.p, d_off.p, d_log2.p, d_keys.p, d_cnt.p,
                                                                      d_maxhash.p, d_flags.p, s, S.t_cap ? S.t_cap_value : EMPTY_KEY,
-                                                                     d_out_hashes, d_out_counts, d_out_n);
+                                                                     d_out_hashes, d_out_counts, d_out_n, mc);
     ctx->kernel_launches++;
     MG_CUDA(ctx, cudaGetLastError());
     if (want_counts) {
         quirk_kernel<<<n_units, SEL_THREADS, 0, st>>>(0, n_units, s, d_out_hashes, d_out_counts, d_out_n, d_off.p, d_log2.p, d_keys.p, d_cnt.p,
-                                                      d_first, d_last, d_flags.p, d_qtarget, d_qtstar);
+                                                      d_first, d_last, d_flags.p, d_qtarget, d_qtstar, mc);
         ctx->kernel_launches++;
         MG_CUDA(ctx, cudaGetLastError());
     }

@@ -45,6 +45,7 @@ void fillGpuParams(mashgpu_sketch_params &p, const Sketch::Parameters &parameter
     p.noncanonical = parameters.noncanonical;
     p.preserve_case = parameters.preserveCase;
     for (int i = 0; i < 256; i++) p.alphabet[i] = parameters.alphabet[i];
+    p.min_copies = parameters.reads ? parameters.minCov : 1;      // reference Sketch.cpp:1186: MinHashHeap(use64, s, reads ? minCov : 1, ...)
 }
 
 bool hasSuffix(string const &whole, string const &suffix)   // reference Sketch.cpp:897-905
@@ -162,8 +163,9 @@ void Sketch::flushBatch(Batch &batch)
 
 static void unsupportedReadsOptions(const Sketch::Parameters &parameters)
 {
-    if (parameters.memoryBound != 0 || parameters.minCov > 1 || parameters.targetCov > 0) {
-        cerr << "ERROR: the read filters -b, -m and -c are not available in the GPU engine (see DESIGN.md, out of scope)." << endl;
+    if (parameters.memoryBound != 0 || parameters.targetCov > 0) {
+        cerr << "ERROR: the read filters -b and -c are not available in the GPU engine: both depend on the order in which reads arrive "
+                "(a Bloom filter with false positives, a stop at the first read boundary that reaches the target coverage); -m is (see DESIGN.md)." << endl;
         exit(1);
     }
 }

@@ -386,6 +386,119 @@ MO_API uint64_t mo_sketch_unit(const mo_params *p, uint64_t sketch_size,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * MinHashHeap with multiplicityMinimum > 1 (`mash sketch -m`, MinHashHeap.cpp:96-144): a hash enters the bottom-s only at its
+ * m-th accepted occurrence; until then it waits in hashesPending (hash -> count) with a max-queue hashesQueuePending beside it.
+ * Restated with two more containers of the same kind as above (an open-addressing count map and a max-heap that may hold
+ * "zombies" -- hashes already promoted or purged from the map, :114-118, :131-141).  Bloom filter (-b): not restated.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mo_heap_m {
+    mo_heap *acc;        /* hashes + hashesQueue */
+    mo_heap *pend;       /* hashesPending (map part) + hashesQueuePending (heap part, with zombies) */
+    uint64_t m;          /* multiplicityMinimum */
+} mo_heap_m;
+
+MO_API mo_heap_m *mo_heap_m_new(int use64, uint64_t cap, uint64_t multiplicity_min)
+{
+    mo_heap_m *h = (mo_heap_m *)calloc(1, sizeof(mo_heap_m));
+    h->acc = mo_heap_new(use64, cap);
+    h->pend = mo_heap_new(use64, 64);
+    h->m = multiplicity_min < 1 ? 1 : multiplicity_min;
+    return h;
+}
+
+MO_API void mo_heap_m_free(mo_heap_m *h)
+{
+    if (!h) return;
+    mo_heap_free(h->acc); mo_heap_free(h->pend); free(h);
+}
+
+/* the pending containers grow without bound (the reference's do too) */
+static void pend_reserve(mo_heap *q)
+{
+    if (q->heap_n + 2 >= q->cap) {
+        q->cap *= 2;
+        q->heap = (uint64_t *)realloc(q->heap, sizeof(uint64_t) * (q->cap + 2));
+    }
+    if (4 * (q->size + 2) >= q->tcap) {          /* rehash at load 1/4 */
+        uint64_t ocap = q->tcap, *okey = q->tkey; uint32_t *ocnt = q->tcnt;
+        q->tcap = ocap * 4;
+        q->tkey = (uint64_t *)malloc(sizeof(uint64_t) * q->tcap);
+        q->tcnt = (uint32_t *)calloc(q->tcap, sizeof(uint32_t));
+        for (uint64_t i = 0; i < ocap; i++)
+            if (ocnt[i]) map_insert_new(q, okey[i], ocnt[i]);
+        free(okey); free(ocnt);
+    }
+}
+
+/* MinHashHeap::tryInsert (MinHashHeap.cpp:68-146) for any multiplicityMinimum, bloomFilter == 0 */
+MO_API void mo_heap_m_try_insert(mo_heap_m *hm, uint64_t hash)
+{
+    mo_heap *h = hm->acc, *q = hm->pend;
+    if (h->cap == 0) return;
+    if (!(h->size < h->cap || hash < h->heap[0])) return;                  /* :70-74 */
+    uint32_t *c = map_find(h, hash);
+    if (!c) {                                                              /* :76 hashes.count(hash) == 0 */
+        uint32_t *pc = map_find(q, hash);
+        const uint64_t pending = pc ? *pc : 0;
+        if (hm->m == 1 || pending == hm->m - 1) {                          /* :96 */
+            map_insert_new(h, hash, (uint32_t)hm->m);                      /* :98 hashes.insert(hash, multiplicityMinimum) */
+            heap_push(h, hash);
+            h->size++;
+            h->multiplicity_sum += hm->m;
+            if (hm->m > 1 && pc) { map_erase(q, hash); q->size--; }        /* :102-108 (stays in the pending queue as a zombie) */
+        } else {
+            if (!pc) {                                                     /* :112-115 */
+                pend_reserve(q);
+                heap_push(q, hash);
+                map_insert_new(q, hash, 1);                                /* :117 hashesPending.insert(hash, 1) */
+                q->size++;
+            } else {
+                (*pc)++;
+            }
+        }
+    } else {                                                               /* :120-124 */
+        (*c)++;
+        h->multiplicity_sum++;
+    }
+    if (h->size > h->cap) {                                                /* :126-144 */
+        const uint64_t top = h->heap[0];
+        uint32_t *tc = map_find(h, top);
+        h->multiplicity_sum -= tc ? *tc : 0;
+        map_erase(h, top);
+        while (q->heap_n > 0 && top < q->heap[0]) {                        /* :133 hashLessThan(hashesQueue.top(), hashesQueuePending.top()) */
+            if (map_find(q, q->heap[0])) { map_erase(q, q->heap[0]); q->size--; }
+            heap_pop(q);
+        }
+        heap_pop(h);
+        h->size--;
+    }
+}
+
+/* sketchFile's record loop with `-m min_copies` (Sketch.cpp:1186 constructs MinHashHeap(use64, s, reads ? minCov : 1, ...)) */
+MO_API uint64_t mo_sketch_unit_m(const mo_params *p, uint64_t sketch_size, uint64_t min_copies,
+                                 uint64_t n_records, const char *const *seqs, const uint64_t *lens,
+                                 int reads, uint64_t genome_size,
+                                 uint64_t *out_hashes, uint32_t *out_counts, uint64_t *out_length)
+{
+    mo_heap_m *hm = mo_heap_m_new(p->use64, sketch_size, min_copies);
+    uint64_t length = 0;
+    uint64_t *buf = NULL, cap = 0;
+    for (uint64_t r = 0; r < n_records; r++) {
+        if (lens[r] < (uint64_t)p->kmer_size) continue;
+        if (!reads) length += lens[r];
+        if (lens[r] > cap) { cap = lens[r]; buf = (uint64_t *)realloc(buf, sizeof(uint64_t) * cap); }
+        const uint64_t n = mo_all_hashes(seqs[r], lens[r], p, buf);        /* the hashes addMinHashes feeds to tryInsert, in order */
+        for (uint64_t i = 0; i < n; i++) mo_heap_m_try_insert(hm, buf[i]);
+    }
+    free(buf);
+    if (reads) length = genome_size ? genome_size : (uint64_t)mo_heap_estimate_set_size(hm->acc);
+    const uint64_t n = mo_heap_to_list(hm->acc, out_hashes, out_counts);
+    if (out_length) *out_length = length;
+    mo_heap_m_free(hm);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Binomial upper tail P[Bin(n, r) >= x]  ==  gsl_cdf_binomial_Q(x-1, r, n)
  * (call sites CommandDistance.cpp:444-446, CommandScreen.cpp:611-613).  GSL/Boost are not in
  * the reference tree; this is an independent evaluation of the same mathematical quantity

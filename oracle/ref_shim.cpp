@@ -290,3 +290,22 @@ REF_API void ref_screen_many(ref_screen_table *t, uint64_t n_chunks, const char 
     }
     if (out_hashes && out_n) *out_n = (uint32_t)emit(merged, p->use64 != 0, out_hashes, nullptr);
 }
+
+// `mash sketch -m min_copies` / `-b bloom_bytes`: the record loop of ref_sketch_unit around the reference's own MinHashHeap
+// constructed as sketchFile does (Sketch.cpp:1186: MinHashHeap(use64, minHashesPerWindow, reads ? minCov : 1, memoryBound)).
+REF_API uint64_t ref_sketch_unit_m(const ref_params *p, uint64_t sketch_size, uint64_t min_copies, uint64_t bloom_bytes,
+                                   uint64_t n_records, const char *const *seqs, const uint64_t *lens,
+                                   int reads, uint64_t genome_size,
+                                   uint64_t *out_hashes, uint32_t *out_counts, uint64_t *out_length)
+{
+    MinHashHeap heap(p->use64 != 0, sketch_size, min_copies, bloom_bytes);
+    uint64_t length = 0;
+    for (uint64_t r = 0; r < n_records; r++) {
+        if (lens[r] < (uint64_t)p->kmer_size) continue;
+        if (!reads) length += lens[r];
+        add_min_hashes(heap, seqs[r], lens[r], *p);
+    }
+    if (reads) length = genome_size ? genome_size : (uint64_t)heap.estimateSetSize();
+    if (out_length) *out_length = length;
+    return emit(heap, p->use64 != 0, out_hashes, out_counts);
+}

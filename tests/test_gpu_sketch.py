@@ -290,3 +290,38 @@ def test_large_sketch_size_goes_through_global_sort(gpu, oracle):
         assert out[2][u] == olen
         assert_sketch_equal(out, u, oh)
         assert np.array_equal(out[3][u, :out[1][u]], oc)
+
+
+def _reads(seed, genome_len, n_reads, err=0.01, read_len=100):
+    g = synth_genome(seed, genome_len)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    out = []
+    for _ in range(n_reads):
+        a = int(rng.integers(0, g.size - read_len))
+        r = g[a:a + read_len].copy()
+        m = rng.random(read_len) < err
+        r[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, read_len))] = ord("N")
+        out.append(bytes(r))
+    return out
+
+
+@pytest.mark.parametrize("m,s,k,cov", [(2, 200, 21, 8), (3, 100, 16, 12), (2, 50, 11, 3), (5, 300, 21, 6), (2, 1000, 21, 1), (2, 400, 21, 30)])
+def test_min_copies_filter_matches_reference_heap(gpu, oracle, m, s, k, cov):
+    # `mash sketch -r -m m` (MinHashHeap.cpp:96-144, pinned to the reference's object code in tests/test_oracle_vs_ref.py): a hash
+    # enters the sketch at its m-th occurrence.  Hash set, multiplicities (incl. the top-of-heap quirk, now on the m-th
+    # occurrence) and units that end with fewer than s qualified hashes (low coverage: exact re-run up to keep-all).
+    p = gpu.params(k=k, s=s, min_copies=m)
+    po = oracle.params(k=k)
+    units = [_reads(300 + 7 * u + m + s, 20_000 + 1000 * u, 200 * cov) for u in range(3)]
+    recs = [r for u in units for r in u]
+    uor = [u for u, rs in enumerate(units) for _ in rs]
+    out = gpu.sketch(recs, p, unit_of_record=uor, n_units=3, counts=True)
+    plain = gpu.sketch(recs, gpu.params(k=k, s=s), unit_of_record=uor, n_units=3)
+    for u, rs in enumerate(units):
+        oh, oc, _ = oracle.sketch_unit_m(rs, po, s=s, min_copies=m, counts=True)
+        assert_sketch_equal(out, u, oh)
+        assert np.array_equal(out[3][u, :out[1][u]], oc)
+    assert any(not np.array_equal(out[0][u, :out[1][u]], plain[0][u, :plain[1][u]]) for u in range(3))     # the filter really bites

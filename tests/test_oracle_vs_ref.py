@@ -106,3 +106,38 @@ def test_ref_screen_many_matches_oracle(oracle, reflib):
     finally:
         reflib.screen_table_free(t)
     assert np.array_equal(counts, want["counts"]) and np.array_equal(mix, want["mixture"])
+
+
+def _read_set(seed, genome_len, n_reads, err=0.01):
+    from fixtures import synth_genome
+    g = synth_genome(seed, genome_len)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    reads = []
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for _ in range(n_reads):
+        a = int(rng.integers(0, g.size - 100))
+        r = g[a:a + 100].copy()
+        m = rng.random(100) < err
+        r[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, 100))] = ord("N")
+        reads.append(bytes(r))
+    return reads
+
+
+@pytest.mark.parametrize("m,s,k,cov", [(2, 200, 21, 8), (3, 100, 16, 12), (2, 50, 11, 3), (5, 300, 21, 6), (2, 1000, 21, 1)])
+def test_min_copies_heap_oracle_equals_reference_object_code(oracle, reflib, m, s, k, cov):
+    """`-m`: the oracle's restated pending-set logic against the reference's own MinHashHeap(use64, s, m, 0): same bottom-s,
+    same multiplicities (incl. the top-of-heap quirk), same -r length."""
+    p = oracle.params(k=k)
+    reads = _read_set(100 + m + s, 20_000, 200 * cov)
+    oh, oc, ol = oracle.sketch_unit_m(reads, p, s=s, min_copies=m, counts=True)
+    rh, rc, rl = reflib.sketch_unit_m(reads, p, s=s, min_copies=m, counts=True)
+    assert np.array_equal(oh, rh) and np.array_equal(oc, rc) and ol == rl
+    # order-independent characterisation used by the GPU path: the s smallest hashes seen at least m times
+    allh = np.concatenate([oracle.all_hashes(r, p) for r in reads if len(r) >= k])
+    u, c = np.unique(allh, return_counts=True)
+    want = u[c >= m][:s]
+    assert np.array_equal(oh, want)
+    assert np.all(oc[:-1] == c[np.searchsorted(u, oh[:-1])]) if oh.size else True
+    assert oh.size == 0 or m <= oc[-1] <= c[np.searchsorted(u, oh[-1])]
