@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--skip-screen", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-cli", action="store_true")
+    ap.add_argument("--cli-files", type=int, default=1000, help="FASTA files in the file -> .msh side measurement of the host shim")
     return ap.parse_args()
 
 
@@ -371,19 +373,63 @@ def cpu_sketch_rate_from_files(n_units, genome_len, threads, seed=321):
     seqs = host_genomes(n_units, genome_len, seed)
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     with tempfile.TemporaryDirectory(dir=base) as d:
-        paths = []
-        for i, q in enumerate(seqs):
-            a = np.frombuffer(q, np.uint8)
-            full = (a.size // 70) * 70
-            lines = np.concatenate([a[:full].reshape(-1, 70), np.full((full // 70, 1), 10, np.uint8)], axis=1).tobytes()
-            path = os.path.join(d, f"g{i}.fna")
-            with open(path, "wb") as f:
-                f.write(b">g%d synthetic\n" % i + lines + a[full:].tobytes() + b"\n")
-            paths.append(path)
+        paths = write_fasta_files(seqs, d)
         t0 = time.perf_counter()
         ref.sketch_files(paths, p, s=S, threads=threads)
         dt = time.perf_counter() - t0
     return n_units * genome_len / dt / 1e9, dt
+
+
+def write_fasta_files(seqs, d):
+    """uncompressed 70-column FASTA, one file per genome"""
+    paths = []
+    for i, q in enumerate(seqs):
+        a = np.frombuffer(q, np.uint8)
+        full = (a.size // 70) * 70
+        lines = np.concatenate([a[:full].reshape(-1, 70), np.full((full // 70, 1), 10, np.uint8)], axis=1).tobytes()
+        path = os.path.join(d, f"g{i}.fna")
+        with open(path, "wb") as f:
+            f.write(b">g%d synthetic\n" % i + lines + a[full:].tobytes() + b"\n")
+        paths.append(path)
+    return paths
+
+
+def cli_sketch_rate(n_files, genome_len, threads, seed=4321):
+    """File -> .msh wall clock of the host shim: `mash sketch -p threads -o out -l list` on n_files uncompressed FASTA files on tmpfs
+    (process start, CUDA context, parse, sketch, .msh write all inside).  Returns dict or None."""
+    mash = os.path.join(ROOT, "mash_b200", "host", "mash")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    if not os.path.exists(mash) or base is None:
+        return None
+    try:
+        st = os.statvfs(base)
+        room = st.f_bavail * st.f_frsize
+    except OSError:
+        return None
+    n_files = int(min(n_files, max(0, room // 2) // (genome_len + genome_len // 70 + 64)))
+    if n_files < 8:
+        return None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        paths = []
+        for c0 in range(0, n_files, 64):
+            seqs = host_genomes(min(64, n_files - c0), genome_len, seed + c0)
+            sub = os.path.join(d, f"b{c0}")
+            os.mkdir(sub)
+            paths += write_fasta_files(seqs, sub)
+        lst = os.path.join(d, "list.txt")
+        open(lst, "w").write("\n".join(paths) + "\n")
+        out = os.path.join(d, "out")
+        t0 = time.perf_counter()
+        pr = subprocess.run([mash, "sketch", "-p", str(threads), "-o", out, "-l", lst], capture_output=True, text=True, env=dict(os.environ, MASHGPU_TRACE="1"))
+        dt = time.perf_counter() - t0
+        sys.stderr.write("cli trace:\n" + "\n".join(l for l in (pr.stderr or "").splitlines() if l.startswith("[mash")) + "\n")
+        if pr.returncode != 0 or not os.path.exists(out + ".msh"):
+            return {"error": (pr.stderr or "")[-300:]}
+        size = os.path.getsize(out + ".msh")
+    return {"value": n_files * genome_len / dt / 1e9, "unit": "Gbp/s", "seconds": dt, "files": n_files, "threads": threads, "msh_bytes": size,
+            "command": f"mash sketch -p {threads} -o out -l list.txt  ({n_files} uncompressed 70-column FASTA files of {genome_len} bp on tmpfs)",
+            "note": "wall clock of the whole process: start-up and CUDA context creation, FASTA parse on the host threads, sketching on the GPU, "
+                    ".msh (Cap'n Proto) write"}
 
 
 def run_reference_arm(args):
@@ -468,6 +514,9 @@ def main():
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
+    # host packer threads of the hybrid feed path: the ranks of one node share its CPUs
+    local_world_n = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("MASHGPU_PACK_THREADS", str(max(1, usable_cpus() // max(1, local_world_n) - 1)))
     eng = mash_b200.Engine(local)
     eng_sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     p = eng.params(k=K, s=S, seed=SEED)
@@ -542,8 +591,6 @@ def main():
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
         budget = max(1 << 30, int(avail * 0.35 / max(1, local_world)))
         e2e_units = args.e2e_units or max(1, min(n_units, budget // (glen + 1)))
-        if world > 1 and not args.e2e_units:
-            e2e_units = min(e2e_units, 4000)      # N > 1: 20 GB of pinned host memory per rank instead of 50 GB (stated in e2e.units_per_step)
         span = glen + 1
         host = torch.empty(e2e_units * span, dtype=torch.uint8, pin_memory=True)
         host.copy_(stream[:e2e_units * span])
@@ -574,7 +621,46 @@ def main():
         e2e = {"value": world * e2e_units * glen * Ksteps / dt / 1e9, "unit": "Gbp/s",
                "h2d_bytes_per_step": int(e2e_units * span), "d2h_bytes_per_step": int(e2e_units * (S * 8 + 4)),
                "units_per_step": e2e_units, "ms_per_step": dt / Ksteps * 1e3, "matches_device_path": same,
+               "feed": os.environ.get("MASHGPU_HOST_PACK", "hybrid: ASCII DMA and host 2-bit packer side by side (default)"),
                "api": "mashgpu_sketch_batch (host pinned buffers; H2D + kernels + D2H inside the timed region)"}
+        # ---- the same batch from a collection the caller keeps 2-bit packed (mashgpu_sketch_batch_packed): packing is done once,
+        # outside the timed region (that is the premise: a cached packed collection); per step 0.25 B/base cross PCIe
+        e2e_packed = None
+        try:
+            total_pos = e2e_units * span
+            pk_codes = torch.empty((total_pos + 31) // 32, dtype=torch.int64, pin_memory=True)
+            cap_runs = 1 << 22
+            pk_runs = torch.empty(2 * cap_runs, dtype=torch.int64, pin_memory=True)
+            n_runs = C.c_uint64(0)
+            t_pack = time.perf_counter()
+            eng._check(eng.lib.mashgpu_host_pack(C.byref(p), e2e_units, C.cast(ptrs, C.c_void_p), lens.ctypes.data_as(u64p), usable_cpus(),
+                                                 C.cast(pk_codes.data_ptr(), u64p), C.cast(pk_runs.data_ptr(), u64p), cap_runs, C.byref(n_runs)))
+            t_pack = time.perf_counter() - t_pack
+            if n_runs.value <= cap_runs:
+                ustart = (np.arange(e2e_units + 1, dtype=np.uint64) * np.uint64(span))
+                out_h2 = torch.empty((e2e_units, S), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+
+                def packed_step():
+                    eng._check(eng.lib.mashgpu_sketch_batch_packed(eng.h, C.byref(p), C.cast(pk_codes.data_ptr(), u64p), total_pos, C.cast(pk_runs.data_ptr(), u64p),
+                                                                   n_runs.value, ustart.ctypes.data_as(u64p), e2e_units, out_h2.ctypes.data_as(u64p), None,
+                                                                   out_n.ctypes.data_as(u32p)))
+
+                for _ in range(min(W, 2)):
+                    packed_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(Ksteps):
+                    packed_step()
+                torch.cuda.synchronize()
+                dtp = max_over_ranks(time.perf_counter() - t0)
+                e2e_packed = {"value": world * e2e_units * glen * Ksteps / dtp / 1e9, "unit": "Gbp/s", "ms_per_step": dtp / Ksteps * 1e3,
+                              "h2d_bytes_per_step": int(pk_codes.numel() * 8 + n_runs.value * 16), "d2h_bytes_per_step": int(e2e_units * (S * 8 + 4)),
+                              "matches_ascii_path": bool(np.array_equal(out_h2, out_h)), "one_off_pack_seconds": t_pack, "pack_threads": usable_cpus(),
+                              "api": "mashgpu_sketch_batch_packed (caller-packed 2-bit stream + invalid runs in pinned host memory; H2D + kernels + D2H inside)"}
+            del pk_codes, pk_runs
+        except AttributeError:
+            e2e_packed = None
+        e2e["packed_collection"] = e2e_packed
         del host
 
     # ---------------- hot path 2: dist ---------------------------------------------------------------------------
@@ -688,7 +774,8 @@ def main():
                     "algorithm": "tile prefilter (cuckoo filter per 32-reference tile; closed form for pairs without shared hashes) + sorted merge of the "
                                  "rest + dense p-value pass; results identical to merging every pair (tests/test_gpu_dist_prefilter.py)",
                     "prefilter": {"query_tile_combinations_probed": pf["combos_probed"], "sent_to_merge": pf["combos_flagged"],
-                                  "fraction_merged": (pf["combos_flagged"] / pf["combos_probed"]) if pf["combos_probed"] else None},
+                                  "fraction_merged": (pf["combos_flagged"] / pf["combos_probed"]) if pf["combos_probed"] else None,
+                                  "pairs_merged_from_pair_lists": pf["pairs_from_lists"]},
                     "one_off_ms": open_ms, "first_pass_ms": first_pass_ms,
                     "value_first_pass_incl_one_off": total_pairs / ((open_ms + first_pass_ms) * 1e-3),
                     "one_off": ("dictionary build inside mashgpu_dist_open (radix sort of all hashes)" if not dist_on else
@@ -786,7 +873,8 @@ def main():
                          "query_tiles": n_tiles5, "queries_per_tile": q_tile5, "passing_pairs": pass_all, "largest_tile_list": max_tile_pass,
                          "last_list_within_max_distance": last_ok, "gpu_launches": int(st5["kernel_launches"]),
                          "prefilter": {"query_tile_combinations_probed": pf5["combos_probed"], "sent_to_merge": pf5["combos_flagged"],
-                                       "fraction_merged": (pf5["combos_flagged"] / pf5["combos_probed"]) if pf5["combos_probed"] else None},
+                                       "fraction_merged": (pf5["combos_flagged"] / pf5["combos_probed"]) if pf5["combos_probed"] else None,
+                                       "pairs_merged_from_pair_lists": pf5["pairs_from_lists"]},
                          "sharded_dictionary": dstat5,
                          "hbm_roofline_note": "algorithmic HBM bytes = rank rows read once per reference tile pass (L2-resident re-reads) + 32 B per passing pair: "
                                               "far below the HBM roofline; the probe kernel's shared-memory lookups bound this workload (DESIGN.md 3.3)"}
@@ -824,53 +912,109 @@ def main():
             idx = torch.arange(read_len, device=dev)[None, :]
             # the reference table is replicated: every rank screens its reads against ALL sketches (QH = the gathered set)
             sset = mash_b200._capi._Set(QH.data_ptr(), QN.data_ptr(), QL.data_ptr(), on_device=True, n=QH.shape[0], stride=S)
-            chunk = torch.empty(chunk_reads * span_r + 64, dtype=torch.uint8, device=dev)
+            n_chunks = max(1, n_reads // chunk_reads)
+            chunk_bytes = chunk_reads * span_r
+            chunk_pitch = (chunk_bytes + 64 + 255) // 256 * 256
+            chunks = torch.zeros((n_chunks, chunk_pitch), dtype=torch.uint8, device=dev)       # n_chunks DISTINCT chunks, resident in HBM
 
-            def make_chunk():
+            def make_chunk(c):
                 starts = torch.randint(0, pool.numel() - read_len, (chunk_reads,), generator=g, device=dev)
                 body = pool[(starts[:, None] + idx)]
                 err = torch.rand((chunk_reads, read_len), generator=g, device=dev) < 0.005
                 body = torch.where(err, lut[torch.randint(0, 4, (chunk_reads, read_len), generator=g, device=dev, dtype=torch.uint8).long()], body)
                 body = torch.where(torch.rand((chunk_reads, read_len), generator=g, device=dev) < 0.001, torch.full_like(body, ord("N")), body)
-                v = chunk[:chunk_reads * span_r].view(chunk_reads, span_r)
+                v = chunks[c, :chunk_bytes].view(chunk_reads, span_r)
                 v[:, 0] = ord("*")
                 v[:, 1:] = body
 
-            make_chunk()
-            torch.cuda.synchronize()          # the chunk is written on torch's stream, the engine reads it on its own
-            n_chunks = max(1, n_reads // chunk_reads)
-            sjob = mash_b200._capi.ScreenJob(eng, sset, None, p)
-            for _ in range(2):
-                sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)
-            eng.set_timing(True); eng.stats(reset=True)
-            barrier()
-            t0 = time.perf_counter()
-            feed_ms = []
-            for _ in range(n_chunks):
-                tf = time.perf_counter()
-                sjob.feed_dev(chunk.data_ptr(), chunk_reads * span_r)     # the same device chunk again: the table and mixture logic still run
-                feed_ms.append((time.perf_counter() - tf) * 1e3)          # feed_dev returns after its own stream sync
-            t_fin = time.perf_counter()
+            for c in range(n_chunks):
+                make_chunk(c)
+            torch.cuda.synchronize()          # the chunks are written on torch's stream, the engine reads them on its own
             if dist_on:
                 from mash_b200.shard import screen_allreduce
-                screen_allreduce(sjob)                                    # reads sharded over ranks: sum the counters, merge the mixtures
-            res = sjob.finish()
-            torch.cuda.synchronize()
-            fin_ms = (time.perf_counter() - t_fin) * 1e3
-            dt = max_over_ranks(time.perf_counter() - t0)
+
+            def screen_pass(job, feed, n):
+                """n chunks through `feed`, then the cross-rank reduce and finish(); returns (seconds max over ranks, result, per-feed ms, finish ms)"""
+                barrier()
+                t0 = time.perf_counter()
+                feed_ms = []
+                for c in range(n):
+                    tf = time.perf_counter()
+                    feed(job, c)
+                    feed_ms.append((time.perf_counter() - tf) * 1e3)
+                t_fin = time.perf_counter()
+                if dist_on:
+                    screen_allreduce(job)                                 # reads sharded over ranks: sum the counters, merge the mixtures
+                res = job.finish()
+                torch.cuda.synchronize()
+                fin_ms = (time.perf_counter() - t_fin) * 1e3
+                return max_over_ranks(time.perf_counter() - t0), res, feed_ms, fin_ms
+
+            # ---- value: chunks resident in HBM
+            sjob = mash_b200._capi.ScreenJob(eng, sset, None, p)
+            for c in range(2):
+                sjob.feed_dev(chunks[c].data_ptr(), chunk_bytes)          # warm-up (counts towards the counters; the timed pass below re-opens the job)
+            sjob.close()
+            sjob = mash_b200._capi.ScreenJob(eng, sset, None, p)
+            eng.set_timing(True); eng.stats(reset=True)
+            dt, res, feed_ms, fin_ms = screen_pass(sjob, lambda j, c: j.feed_dev(chunks[c].data_ptr(), chunk_bytes), n_chunks)
             sstats = eng.stats(reset=True)
             eng.set_timing(False)
             sjob.close()
             bases = n_chunks * chunk_reads * read_len
+            # ---- e2e: the same chunks from pinned host memory through mashgpu_screen_feed (H2D inside, two-buffer pipeline)
+            host_chunks = torch.empty((n_chunks, chunk_bytes), dtype=torch.uint8, pin_memory=True)
+            host_chunks.copy_(chunks[:, :chunk_bytes])
+            torch.cuda.synchronize()
+            hnp = host_chunks.numpy()
+            ejob = mash_b200._capi.ScreenJob(eng, sset, None, p)
+            dt_e, res_e, feed_e, fin_e = screen_pass(ejob, lambda j, c: j.feed(hnp[c]), n_chunks)
+            ejob.close()
+            same_e2e = bool(np.array_equal(res_e["shared"], res["shared"]) and res_e["set_size"] == res["set_size"])
             screen_obj = {"metric": "Gbp_per_s_screened", "value": world * bases / dt / 1e9, "unit": "Gbp/s",
                           "workload": f"configs[3]: {QH.shape[0]}-sketch reference table ({int(QN.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
-                                      f"fed as {n_chunks} device-resident '*'-joined chunks of {chunk_reads} reads per rank (one chunk re-fed; inputs in HBM); "
-                                      f"{'counters all-reduced over NCCL + mixtures merged, ' if dist_on else ''}finish() included",
+                                      f"per rank in {n_chunks} distinct '*'-joined chunks of {chunk_reads} reads resident in HBM; "
+                                      f"{'counters all-reduced over NCCL + mixtures merged on the device, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"],
                           "host_ms": {"feed_first": feed_ms[0], "feed_median": float(np.median(feed_ms)), "feed_max": max(feed_ms), "allreduce_and_finish": fin_ms}, "gpu_launches": int(sstats["kernel_launches"]),
+                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * chunk_bytes), "ms_total": dt_e * 1e3,
+                                  "feed_median_ms": float(np.median(feed_e)), "allreduce_and_finish_ms": fin_e, "matches_device_path": same_e2e,
+                                  "api": "mashgpu_screen_feed with pinned host chunks: the copy of chunk i+1 overlaps the kernels of chunk i; finish() and its D2H inside"},
                           "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()), "exact_reruns": int(sstats["exact_reruns"]),
                           "source_genomes": n_src, "median_multiplicity_of_hit_references": float(np.median(res["median"][res["shared"] > 0])) if (res["shared"] > 0).any() else 0.0,
                           "mean_identity_of_source_genomes": float(np.mean(res["identity"][:n_src]))}
+            del host_chunks, hnp
+            if rank == 0:
+                # ---- side measurement: a reference .msh that also holds small genomes.  Their sketches are ALL their k-mers, i.e. hashes
+                # spread over the whole 64-bit range, so the largest reference hash no longer filters anything: every k-mer of the
+                # mixture is a table candidate.  With and without the value-indexed bitmap in front of the table.
+                n_small = 2000
+                gs = torch.Generator(device=dev); gs.manual_seed(99)
+                v = torch.randint(-2 ** 63, 2 ** 63 - 1, (n_small, S), generator=gs, device=dev, dtype=torch.int64)
+                sign = torch.tensor(-2 ** 63, dtype=torch.int64, device=dev)
+                v = (torch.sort(v ^ sign, dim=1)[0]) ^ sign                  # ascending as unsigned
+                WH = torch.cat([QH, v]); WN = torch.cat([QN, torch.full((n_small,), S, dtype=torch.int32, device=dev)])
+                WL = torch.cat([QL, torch.full((n_small,), 1020, dtype=QL.dtype, device=dev)])
+                wset = mash_b200._capi._Set(WH.data_ptr(), WN.data_ptr(), WL.data_ptr(), on_device=True, n=WH.shape[0], stride=S)
+                side = {}
+                n_side = min(n_chunks, 8)
+                for label, env in (("bitmap", "1"), ("no_bitmap", "0")):
+                    os.environ["MASHGPU_SCREEN_BITMAP"] = env
+                    wjob = mash_b200._capi.ScreenJob(eng, wset, None, p)
+                    wjob.feed_dev(chunks[0].data_ptr(), chunk_bytes)
+                    torch.cuda.synchronize()
+                    tw = time.perf_counter()
+                    for c in range(n_side):
+                        wjob.feed_dev(chunks[c].data_ptr(), chunk_bytes)
+                    torch.cuda.synchronize()
+                    side[label] = n_side * chunk_reads * read_len / (time.perf_counter() - tw) / 1e9
+                    wjob.close()
+                os.environ.pop("MASHGPU_SCREEN_BITMAP", None)
+                screen_obj["whole_range_table"] = {"Gbp_per_s_with_bitmap": side["bitmap"], "Gbp_per_s_without_bitmap": side["no_bitmap"], "chunks": n_side,
+                                                   "table": f"the {QH.shape[0]} sketches above + {n_small} sketches of genomes shorter than s k-mers (hashes uniform over "
+                                                            "the whole 64-bit range): the largest reference hash is ~2^64, every k-mer is a table candidate",
+                                                   "note": "rank 0, chunks resident in HBM, outside the timed region of `value`"}
+                del WH, WN, WL, v
         else:
             screen_obj = None
 
@@ -889,6 +1033,8 @@ def main():
                          f"container's quota -- and one per visible CPU), {dt:.1f} s wall; reference MurmurHash3/hash/MinHashHeap "
                          "object code (oracle/_ref), restated addMinHashes loop, in-memory input"}
         cpu.update(cpu_arms(cores))
+        if not args.skip_cli:
+            cpu["gpu_cli_file_to_msh"] = cli_sketch_rate(args.cli_files, glen, usable_cpus())
 
     if rank == 0:
         line = {"metric": "Gbp_per_s_sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": Ksteps, "warmup": W,

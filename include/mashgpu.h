@@ -54,6 +54,8 @@ typedef struct mashgpu_sketch_params {
     uint32_t min_copies;      /* `-m`: MinHashHeap multiplicityMinimum (Sketch.cpp:1186, reads mode; MinHashHeap.cpp:96-118): a hash enters
                                  the sketch at its m-th occurrence.  0 or 1 = off.  The sketch is then the s smallest hashes seen at
                                  least m times, and the multiplicities follow the heap exactly (tests/test_gpu_sketch.py). */
+    double target_cov;        /* `-c`: stop after the first read that brings the heap's average multiplicity to this value
+                                 (Sketch.cpp:1258-1262).  Only mashgpu_sketch_reads looks at it; <= 0 = off. */
 } mashgpu_sketch_params;
 /* GPU path coverage: alphabet == {A,C,G,T} (canonical or not, any k 1..32, either case mode) runs the 4-bit
  * packed DNA kernels; any other alphabet requires noncanonical != 0 (the protein setting of the reference,
@@ -89,6 +91,18 @@ int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
                          const uint32_t *unit_of_record, uint64_t n_units,
                          uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_length);
 
+/* One sketch of a read set, `mash sketch -r [-m min_copies] [-c target_cov]` (sketchFile with parameters.reads, Sketch.cpp:1186-1282):
+ * all records in the order given (the caller interleaves several files round robin as Sketch.cpp:1202-1270 does).  With
+ * target_cov > 0 the result is the heap as it stood after the first kept record that brought estimateMultiplicity() to the target
+ * (Sketch.cpp:1258-1262) and *out_records_used (the "Reads used" line, :1324-1327) is the number of kept records up to and
+ * including it; otherwise all kept records are used.  The stop depends on the order of the reads; it is found exactly: the
+ * exact top of the heap at geometrically spaced prefixes bounds which k-mers can pass the heap's gate afterwards, those
+ * k-mers are collected as events and replayed in stream order through the reference's heap logic on the device
+ * (DESIGN.md 2.6).  out_counts nullable.  DNA alphabet only. */
+int mashgpu_sketch_reads(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                         uint64_t n_records, const char *const *seq, const uint64_t *len,
+                         uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_records_used);
+
 /* Same computation on a sequence stream already resident in device memory.  d_stream holds the units back to
  * back; unit u occupies bytes [unit_start[u], unit_start[u+1]) (host array of n_units+1 offsets); records inside
  * a unit are separated by at least one byte outside the alphabet (e.g. 0).  d_stream must be readable up to
@@ -106,6 +120,18 @@ int mashgpu_sketch_stream_dev(mashgpu_ctx *ctx, const mashgpu_sketch_params *par
  * up to runs_capacity {start, length} pairs; *n_runs is the number of runs found. */
 int mashgpu_host_pack(const mashgpu_sketch_params *params, uint64_t n_records, const char *const *seq, const uint64_t *len,
                       int threads, uint64_t *codes, uint64_t *runs, uint64_t runs_capacity, uint64_t *n_runs);
+
+/* Sketching from a stream the caller already keeps 2-bit packed (the format mashgpu_host_pack writes): a collection cached in
+ * this form crosses PCIe at a quarter of a byte per base and no host thread touches the bases again, so the call runs at the
+ * rate of the scan kernel instead of the rate of PCIe-ASCII.  codes: ceil(stream_len / 32) words, base p at bits 2 (p % 32) of
+ * codes[p / 32] (A0 C1 G2 T3); runs: n_runs {start, length} pairs, ascending and disjoint, covering every position that is not
+ * a base of the alphabet (the separator after each record included); unit u = positions [unit_start[u], unit_start[u+1])
+ * (n_units + 1 ascending offsets, unit_start[n_units] <= stream_len).  Same outputs as mashgpu_sketch_batch (without
+ * out_length: record lengths are the caller's).  Pinned host buffers make the copies asynchronous.  DNA alphabet only. */
+int mashgpu_sketch_batch_packed(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                const uint64_t *codes, uint64_t stream_len, const uint64_t *runs, uint64_t n_runs,
+                                const uint64_t *unit_start, uint64_t n_units,
+                                uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n);
 
 /* getHash over every window (hash.cpp:10-38 applied as in Sketch.cpp:540-576): out_hash[i]/out_valid[i] for each
  * window start i in [0, len-k]; invalid windows (a byte outside the alphabet) have out_valid[i] == 0.
@@ -147,6 +173,8 @@ int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref, const mas
 /* Compares queries [q_begin, q_begin+q_count) with every reference: pair (q, r) is written at index
  * (q - q_begin) * n_ref + r, the reference's query-major order (CommandDistance.cpp:213-232, 306-334).
  * Per pair (PairOutput, CommandDistance.h:63-70): numer (shared hashes), denom, distance, pvalue, pass.
+ * Sketch sizes up to 1035 run the tiled lockstep merge (32 references per shared-memory tile); larger ones (`-s 10000`) a
+ * warp-per-pair merge; beyond ~28 000 hashes per sketch one thread per pair from global memory.
  * Where the reference leaves numer/denom/distance/pValue unset (distance > max_distance, :409-412) this
  * engine still writes the computed numer/denom/distance and pvalue = 0, with pass = 0.
  * Any output pointer may be NULL.  Host buffers. */
@@ -183,6 +211,12 @@ int mashgpu_dist_set_prefilter(mashgpu_dist_job *job, int mode);
 /* Counters of the prefilter since the job was opened: (query, tile) combinations probed, those that went on to the merge,
  * and whether the next run would probe.  Synchronises the device.  Any pointer may be NULL. */
 int mashgpu_dist_prefilter_stats(mashgpu_dist_job *job, uint64_t *combos_probed, uint64_t *combos_flagged, int *active);
+/* The prefilter also learns WHICH references of a tile a query may share a hash with (one owner byte per filter slot).  A
+ * combination with at most 4 candidate references (MASHGPU_DIST_PAIR_MAX, 0 = off) is not merged as a whole: its candidate
+ * pairs go to a list and are merged one warp per pair, the other references of the tile get the closed form.  This keeps the
+ * run fast when related sketches are scattered over the collection instead of stored next to each other.
+ * *pairs_merged_from_lists: pairs that took this path since the job was opened.  Synchronises the device. */
+int mashgpu_dist_pair_stats(mashgpu_dist_job *job, uint64_t *pairs_merged_from_lists);
 
 /* ---- Sharded dictionary build (multi-GPU all-vs-all).  With the reference axis sharded over G ranks the
  * dictionary of mashgpu_dist_open would be rebuilt in full on every rank.  These entry points split it by HASH RANGE

@@ -31,7 +31,7 @@ class SketchParams(C.Structure):
     """mashgpu_sketch_params (Sketch::Parameters subset, reference Sketch.h:34-109)."""
     _fields_ = [("kmer_size", C.c_int32), ("sketch_size", C.c_uint32), ("seed", C.c_uint32),
                 ("use64", C.c_int32), ("noncanonical", C.c_int32), ("preserve_case", C.c_int32),
-                ("alphabet", C.c_uint8 * 256), ("min_copies", C.c_uint32)]
+                ("alphabet", C.c_uint8 * 256), ("min_copies", C.c_uint32), ("target_cov", C.c_double)]
 
     @property
     def kmer_space(self):
@@ -83,6 +83,8 @@ def load_library():
                                        u64p, u32p, u32p, u64p]
     L.mashgpu_sketch_stream_dev.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, u64p, C.c_uint64,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mashgpu_sketch_reads.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_uint64, C.c_void_p, u64p, u64p, u32p, u32p, u64p]
+    L.mashgpu_sketch_batch_packed.argtypes = [C.c_void_p, C.POINTER(SketchParams), u64p, C.c_uint64, u64p, C.c_uint64, u64p, C.c_uint64, u64p, u32p, u32p]
     L.mashgpu_host_pack.argtypes = [C.POINTER(SketchParams), C.c_uint64, C.c_void_p, u64p, C.c_int, u64p, u64p, C.c_uint64, u64p]
     L.mashgpu_hash_windows.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.c_void_p, C.c_uint64, u64p, u8p]
     L.mashgpu_dist_open.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), C.POINTER(C.c_void_p)]
@@ -93,6 +95,7 @@ def load_library():
     L.mashgpu_dist_set_prefilter.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_dist_set_triangle.argtypes = [C.c_void_p, C.c_int]
     L.mashgpu_dist_prefilter_stats.argtypes = [C.c_void_p, u64p, u64p, C.POINTER(C.c_int)]
+    L.mashgpu_dist_pair_stats.argtypes = [C.c_void_p, u64p]
     L.mashgpu_dist.argtypes = [C.c_void_p, C.POINTER(SketchSet), C.POINTER(SketchSet), C.POINTER(DistParams), u32p, u32p, f64p, f64p, u8p]
     L.mashgpu_screen_open.argtypes = [C.c_void_p, C.POINTER(SketchParams), C.POINTER(SketchSet), C.POINTER(C.c_void_p)]
     L.mashgpu_screen_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -170,9 +173,10 @@ class Engine:
             raise MashGpuError(rc, (self.lib.mashgpu_last_error(self.h) or b"").decode())
 
     # ---- parameters (sketchParameterSetup / setAlphabetFromString) --------------------------------------
-    def params(self, k=21, s=1000, seed=42, alphabet=ALPHABET_NUCLEOTIDE, noncanonical=False, preserve_case=False, min_copies=1):
+    def params(self, k=21, s=1000, seed=42, alphabet=ALPHABET_NUCLEOTIDE, noncanonical=False, preserve_case=False, min_copies=1, target_cov=0.0):
         p = SketchParams()
         p.min_copies = min_copies
+        p.target_cov = target_cov
         p.kmer_size = k
         p.sketch_size = s
         p.seed = seed
@@ -202,6 +206,51 @@ class Engine:
         self._check(self.lib.mashgpu_sketch_batch(self.h, C.byref(p), len(bufs), C.cast(ptrs, C.c_void_p), _p(lens, u64p),
                                                   _p(uor, u32p), n_units, _p(out, u64p), _p(out_c, u32p), _p(out_n, u32p), _p(out_len, u64p)))
         return (out, out_n, out_len, out_c) if counts else (out, out_n, out_len)
+
+    def sketch_reads(self, records, p, counts=False):
+        """`mash sketch -r [-m] [-c]` of one read set.  Returns (hashes[:n], counts[:n] | None, records_used)."""
+        bufs = [_as_u8(r) for r in records]
+        ptrs = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data if b.size else None for b in bufs])
+        lens = np.array([b.size for b in bufs], dtype=np.uint64)
+        s = p.sketch_size
+        out = np.zeros(s, np.uint64); out_c = np.zeros(s, np.uint32) if counts else None
+        n = C.c_uint32(0); used = C.c_uint64(0)
+        self._check(self.lib.mashgpu_sketch_reads(self.h, C.byref(p), len(bufs), C.cast(ptrs, C.c_void_p), _p(lens, u64p), _p(out, u64p), _p(out_c, u32p),
+                                                  C.byref(n), C.byref(used)))
+        return out[:n.value].copy(), (out_c[:n.value].copy() if counts else None), used.value
+
+    def host_pack(self, records, p, threads=1):
+        """records -> (codes u64[ceil(L/32)], runs u64[n, 2], record_start u64[n_records + 1]) in the packed stream format
+        (every record followed by one separator position).  No GPU involved."""
+        bufs = [_as_u8(r) for r in records]
+        ptrs = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data if b.size else None for b in bufs])
+        lens = np.array([b.size for b in bufs], dtype=np.uint64)
+        total = int(lens.sum()) + len(bufs)
+        codes = np.zeros(max(1, (total + 31) // 32), np.uint64)
+        cap = 1 << 16
+        while True:
+            runs = np.zeros(2 * cap, np.uint64)
+            n_runs = C.c_uint64(0)
+            self._check(self.lib.mashgpu_host_pack(C.byref(p), len(bufs), C.cast(ptrs, C.c_void_p), _p(lens, u64p), threads, _p(codes, u64p),
+                                                   _p(runs, u64p), cap, C.byref(n_runs)))
+            if n_runs.value <= cap:
+                break
+            cap = int(n_runs.value)
+        starts = np.zeros(len(bufs) + 1, np.uint64)
+        starts[1:] = np.cumsum(lens + np.uint64(1))
+        return codes, runs[:2 * n_runs.value].reshape(-1, 2).copy(), starts
+
+    def sketch_packed(self, codes, stream_len, runs, unit_start, p, counts=False):
+        """mashgpu_sketch_batch_packed: units of a caller-packed 2-bit stream.  Returns (hashes, n[, counts])."""
+        codes = np.ascontiguousarray(codes, np.uint64); runs = np.ascontiguousarray(runs, np.uint64).reshape(-1)
+        us = np.ascontiguousarray(unit_start, np.uint64)
+        n_units = us.size - 1
+        s = p.sketch_size
+        out = np.zeros((n_units, s), np.uint64); out_n = np.zeros(n_units, np.uint32)
+        out_c = np.zeros((n_units, s), np.uint32) if counts else None
+        self._check(self.lib.mashgpu_sketch_batch_packed(self.h, C.byref(p), _p(codes, u64p), stream_len, _p(runs, u64p) if runs.size else None, runs.size // 2,
+                                                         _p(us, u64p), n_units, _p(out, u64p), _p(out_c, u32p), _p(out_n, u32p)))
+        return (out, out_n, out_c) if counts else (out, out_n)
 
     def sketch_stream_dev(self, p, d_stream_ptr, unit_start, d_out_hashes, d_out_n, d_out_counts=None, stream=None):
         us = np.ascontiguousarray(unit_start, np.uint64)
@@ -338,7 +387,9 @@ class DistJob:
     def prefilter_stats(self):
         probed = C.c_uint64(0); flagged = C.c_uint64(0); active = C.c_int(0)
         self.eng._check(self.eng.lib.mashgpu_dist_prefilter_stats(self.h, C.byref(probed), C.byref(flagged), C.byref(active)))
-        return {"combos_probed": probed.value, "combos_flagged": flagged.value, "active": bool(active.value)}
+        pairs = C.c_uint64(0)
+        self.eng._check(self.eng.lib.mashgpu_dist_pair_stats(self.h, C.byref(pairs)))
+        return {"combos_probed": probed.value, "combos_flagged": flagged.value, "active": bool(active.value), "pairs_from_lists": pairs.value}
 
     def close(self):
         if self.h:

@@ -61,6 +61,7 @@ struct mashgpu_ctx {
     // mashgpu_sketch_batch: wave stream buffers and outputs
     mashgpu::Scratch sc_wave[2], sc_inval[2], sc_runs[2], sc_out_hashes, sc_out_n, sc_out_counts;
     mashgpu::Scratch sc_sep[2], sc_codes[2];
+    mashgpu::Scratch sc_big_units, sc_big_n, sc_big_off, sc_big_bounds, sc_big_comp, sc_big_sorted, sc_big_tmp;   // select of tables > 2^14 slots
     void *pinned_sep[2] = {nullptr, nullptr};
     void *pinned_codes[2] = {nullptr, nullptr};     // packed feed path: host code buffers
     size_t pinned_codes_bytes[2] = {0, 0};

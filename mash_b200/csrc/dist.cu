@@ -66,6 +66,11 @@ struct DistArgs {
     int probe_prefetch;         // dist_probe_kernel: request the query lines two groups ahead into L1
     int triangle;               // lower triangle only: pairs with tri_r0 + r >= q are neither computed nor written
     uint32_t tri_r0;            // row of reference 0 in the query numbering (0 for a self comparison; the shard offset of an encoded job)
+    // sparse related pairs (dist_probe_kernel -> dist_pair_kernel): when a query may share hashes with at most pair_max references
+    // of a tile, only those (query, reference) pairs are merged, one warp per pair, instead of all 32 in lockstep
+    uint2 *pair_list; unsigned long long *pair_count; uint64_t pair_capacity; unsigned long long *pair_total;
+    int pair_max;               // 0: every flagged (query, tile) combination goes to the tile's work list
+    int pair_dense;             // dist_pair_kernel enumerates every pair of the run itself (sketch sizes beyond the tiled merge)
     // deferred p-values (dist_fix_kernel): pairs with shared hashes whose binomial tail is evaluated in a dense second pass
     struct FixEntry *fix_list; unsigned long long *fix_count; uint64_t fix_capacity;
 };
@@ -154,11 +159,20 @@ __global__ void __launch_bounds__(256) dist_fix_kernel(const DistArgs a)
     }
 }
 
+// BULK: the query rows are staged by the TMA engine (cp.async.bulk global -> shared, completion on a per-warp mbarrier) instead
+// of a coalesced LDG/STS loop.  A row of P ranks starts at a 4-byte aligned address (pitch P words), the bulk copy needs 16:
+// the copy covers the 16-byte aligned span around the row and the merge starts `skew` bytes into the warp's buffer.
+// A/B measured in profiles/r02_dist_bulk_copy.md (MASHGPU_DIST_BULK=1); the staging is ~2.5 % of the kernel's instructions.
+__device__ __forceinline__ uint32_t dist_qpitch(uint32_t P, bool bulk) { return bulk ? ((P + 4u + 3u) & ~3u) : P; }
+
+template <bool BULK>
 __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t qpitch = dist_qpitch(a.P, BULK);
     uint32_t *s_ref = smem;                                  // [P][32]
-    uint32_t *s_qry = smem + (size_t)a.P * DIST_TILE_R;      // [DIST_WARPS][DIST_ILP][P]
+    uint32_t *s_qry = smem + (((size_t)a.P * DIST_TILE_R + 3) & ~(size_t)3);      // [DIST_WARPS][DIST_ILP][qpitch]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qry + (size_t)DIST_WARPS * DIST_ILP * qpitch);     // BULK: one mbarrier per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r0 = blockIdx.x * DIST_TILE_R;
     const uint32_t r = r0 + lane;
@@ -179,7 +193,14 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
     const uint32_t nA = r_ok ? a.ref_n[r] : 0;
     const uint64_t lenA = r_ok ? a.ref_len[r] : 1;
     const uint32_t sref_base = (uint32_t)__cvta_generic_to_shared(s_ref) + lane * 4;
-    uint32_t *my_q = s_qry + (size_t)warp * DIST_ILP * a.P;
+    uint32_t *my_q = s_qry + (size_t)warp * DIST_ILP * qpitch;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar + warp);
+    uint32_t phase = 0;
+    if (BULK) {
+        if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
 
     for (uint64_t it_lo = (uint64_t)blockIdx.y * a.q_per_cta; it_lo < n_items; it_lo += (uint64_t)gridDim.y * a.q_per_cta) {
     const uint32_t it_hi = (uint32_t)min((uint64_t)n_items, it_lo + a.q_per_cta);
@@ -194,15 +215,53 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
             all_skipped &= qs[c] == 0xFFFFFFFFu;
         }
         if (all_skipped) continue;                      // warp-uniform
-        // load DIST_ILP query rows (coalesced) into this warp's buffers
+        // load DIST_ILP query rows into this warp's buffers: coalesced LDG/STS, or (BULK) one bulk copy per row
+        uint32_t skew[DIST_ILP];
 #pragma unroll
-        for (int c = 0; c < DIST_ILP; c++) {
-            uint32_t *dst = my_q + (size_t)c * a.P;
-            if (qs[c] != 0xFFFFFFFFu) {
-                const uint32_t *row = a.ranks + (a.qry_row0 + qs[c]) * (uint64_t)a.P;
-                for (uint32_t i = lane; i < a.P; i += 32) dst[i] = row[i];
-            } else {
-                for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
+        for (int c = 0; c < DIST_ILP; c++) skew[c] = 0;
+        if (BULK) {
+            uint32_t bytes[DIST_ILP], total = 0;
+            const uint32_t *src[DIST_ILP];
+#pragma unroll
+            for (int c = 0; c < DIST_ILP; c++) {
+                bytes[c] = 0; src[c] = nullptr;
+                if (qs[c] != 0xFFFFFFFFu) {
+                    const uintptr_t row = (uintptr_t)(a.ranks + (a.qry_row0 + qs[c]) * (uint64_t)a.P);
+                    const uintptr_t lo = row & ~(uintptr_t)15, hi = (row + (uintptr_t)a.P * 4 + 15) & ~(uintptr_t)15;
+                    skew[c] = (uint32_t)(row - lo);
+                    src[c] = reinterpret_cast<const uint32_t *>(lo);
+                    bytes[c] = (uint32_t)(hi - lo);
+                    total += bytes[c];
+                } else {
+                    uint32_t *dst = my_q + (size_t)c * qpitch;
+                    for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && total) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the lanes' reads of the previous rows precede the async writes
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(total) : "memory");
+#pragma unroll
+                for (int c = 0; c < DIST_ILP; c++)
+                    if (bytes[c])
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"((uint32_t)__cvta_generic_to_shared(my_q + (size_t)c * qpitch)), "l"(src[c]), "r"(bytes[c]), "r"(bar) : "memory");
+            }
+            if (total) {
+                asm volatile("{\n\t.reg .pred p;\n\tDIST_BULK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra DIST_BULK_WAIT;\n\t}"
+                             :: "r"(bar), "r"(phase) : "memory");
+                phase ^= 1;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < DIST_ILP; c++) {
+                uint32_t *dst = my_q + (size_t)c * qpitch;
+                if (qs[c] != 0xFFFFFFFFu) {
+                    const uint32_t *row = a.ranks + (a.qry_row0 + qs[c]) * (uint64_t)a.P;
+                    for (uint32_t i = lane; i < a.P; i += 32) dst[i] = row[i];
+                } else {
+                    for (uint32_t i = lane; i < a.P; i += 32) dst[i] = RANK_PAD;
+                }
             }
         }
         __syncwarp();
@@ -210,7 +269,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 #pragma unroll
         for (int c = 0; c < DIST_ILP; c++) {
             pa[c] = sref_base;
-            pb0[c] = pb[c] = (uint32_t)__cvta_generic_to_shared(my_q + (size_t)c * a.P);
+            pb0[c] = pb[c] = (uint32_t)__cvta_generic_to_shared(my_q + (size_t)c * qpitch) + skew[c];
             va[c] = lds32(pa[c]);
             vb[c] = lds32(pb[c]);
         }
@@ -265,22 +324,34 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_kernel(const DistArgs a)
 constexpr int PROBE_WARPS = 32;
 constexpr int PROBE_THREADS = PROBE_WARPS * 32;
 constexpr int PROBE_DEPTH = 4;          // 32-rank batches in flight per warp
+constexpr int PROBE_MAX_CONFIRMS = 3;   // exact confirmations of shared-slot hits per (query, tile) before the combination is merged as a whole
+constexpr size_t PROBE_SMEM = CF_BUCKETS * sizeof(uint32_t) + 2 * CF_BUCKETS;      // the filter + one owner byte per slot
 
-// A filter hit somewhere in the group b[] (ranks base + 32 c + lane): confirm exactly.  Filter hits are rare unless the query
-// really shares hashes with the tile; every lane searches the rank in its own reference's row (global memory).
+// A filter hit somewhere in the group b[] (ranks base + 32 c + lane): which references of the tile may share it?  The id side
+// table (dist_filter.cuh) names the reference when the fingerprint's slot belongs to one; slots shared by several references
+// (the rule in a tile of related sketches) and, when the pair path is off, every hit are confirmed exactly: each lane
+// binary-searches the rank in its own reference's row (global memory) and the ballot is the set of references that hold it.
+// Returns the updated candidate mask; stops confirming once more than pair_max references are in it (the combination is merged
+// as a whole then).
 template <bool FULL>
-__device__ __noinline__ bool probe_confirm(const uint32_t *s_tab, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t base, uint32_t nB, int lane,
-                                           const uint32_t *rowA, uint32_t nA_lim)
+__device__ __noinline__ uint32_t probe_resolve(const uint32_t *s_tab, const uint8_t *s_ids, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t base,
+                                               uint32_t nB, int lane, const uint32_t *rowA, uint32_t nA_lim, uint32_t mask, int pair_max, int &confirms)
 {
     const uint32_t b[PROBE_DEPTH] = {b0, b1, b2, b3};      // by value: an array reference would pin the caller's ranks in local memory
-    bool hit[PROBE_DEPTH];
-#pragma unroll
-    for (int c = 0; c < PROBE_DEPTH; c++) hit[c] = cf_lookup(s_tab, b[c]) && (FULL || base + 32 * c + lane < nB);
-    bool confirmed = false;
 #pragma unroll
     for (int c = 0; c < PROBE_DEPTH; c++) {
-        unsigned m = __ballot_sync(0xFFFFFFFFu, hit[c]);
-        while (m && !confirmed) {
+        bool multi = false;
+        uint32_t bits = 0;
+        if (FULL || base + 32 * c + lane < nB) {
+            if (pair_max > 0) bits = cf_owner_bits(s_tab, s_ids, b[c], &multi);
+            else multi = cf_lookup(s_tab, b[c]);             // pair path off (no owner bytes): a hit only counts once confirmed
+        }
+        mask |= __reduce_or_sync(0xFFFFFFFFu, bits);
+        unsigned m = __ballot_sync(0xFFFFFFFFu, multi);
+        while (m && __popc(mask) <= pair_max) {
+            // A confirmation costs ~10 dependent global loads.  A query that keeps hitting shared slots is related to several
+            // references of the tile (same family): after a few confirmations merge the whole combination instead.
+            if (pair_max > 0 && ++confirms > PROBE_MAX_CONFIRMS) return 0xFFFFFFFFu;
             const int src = __ffs(m) - 1;
             m &= m - 1;
             const uint32_t bb = __shfl_sync(0xFFFFFFFFu, b[c], src);
@@ -289,18 +360,16 @@ __device__ __noinline__ bool probe_confirm(const uint32_t *s_tab, uint32_t b0, u
                 const uint32_t mid = (lo + hi) >> 1;
                 if (rowA[mid] < bb) lo = mid + 1; else hi = mid;
             }
-            const bool found = lo < nA_lim && rowA[lo] == bb;
-            confirmed = __any_sync(0xFFFFFFFFu, found);
+            mask |= __ballot_sync(0xFFFFFFFFu, lo < nA_lim && rowA[lo] == bb);
         }
     }
-    return confirmed;
+    return mask;
 }
 
 // One group of PROBE_DEPTH x 32 ranks of a query against the filter.  FULL: the whole group lies inside the query's list.
-// Returns true when a rank is confirmed to be in one of the tile's references.
+// Returns true when some lane has a fingerprint match.
 template <bool FULL, bool LAZY>
-__device__ __forceinline__ bool probe_group(const uint32_t *s_tab, uint32_t tab_s, const uint32_t (&b)[PROBE_DEPTH], uint32_t base, uint32_t nB, int lane,
-                                            const uint32_t *rowA, uint32_t nA_lim)
+__device__ __forceinline__ bool probe_group(uint32_t tab_s, const uint32_t (&b)[PROBE_DEPTH], uint32_t base, uint32_t nB, int lane)
 {
     // b[c] = rank base + 32 c + lane of the query (RANK_PAD past the end of its list)
     static_assert(PROBE_DEPTH == 4, "cf_group_any takes four probes");
@@ -310,14 +379,14 @@ __device__ __forceinline__ bool probe_group(const uint32_t *s_tab, uint32_t tab_
         pr[c] = cf_fetch_s<LAZY>(tab_s, b[c]);
         if (!FULL && base + 32 * c + lane >= nB) pr[c].f2 = 0x7E007E00u;       // past the end of the list: never matches
     }
-    if (!cf_group_any(pr[0], pr[1], pr[2], pr[3])) return false;
-    return probe_confirm<FULL>(s_tab, b[0], b[1], b[2], b[3], base, nB, lane, rowA, nA_lim);
+    return cf_group_any(pr[0], pr[1], pr[2], pr[3]);
 }
 
 template <bool LAZY>
 __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const DistArgs a)
 {
-    extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words
+    extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words, then 2 * CF_BUCKETS id bytes
+    uint8_t *s_ids = reinterpret_cast<uint8_t *>(s_tab + CF_BUCKETS);
     __shared__ int s_fail;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r0 = blockIdx.x * DIST_TILE_R;
@@ -326,6 +395,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     if (q_lo >= q_hi) return;
 
     for (uint32_t i = threadIdx.x; i < CF_BUCKETS; i += PROBE_THREADS) s_tab[i] = 0;
+    if (a.pair_max > 0)       // the owner bytes exist only when the pair path is on (the launch then asks for 64 KB more shared memory)
+        for (uint32_t i = threadIdx.x; i < CF_BUCKETS / 2; i += PROBE_THREADS) reinterpret_cast<uint32_t *>(s_ids)[i] = 0xFFFFFFFFu;     // CF_ID_NONE
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
     for (uint32_t rr = warp; rr < DIST_TILE_R; rr += PROBE_WARPS) {
@@ -337,6 +408,17 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
             if (!cf_insert(s_tab, row[i], threadIdx.x * 2654435761u + i)) s_fail = 1;
     }
     __syncthreads();
+    // id side table: one reference per phase, so that only ranks of the same reference ever write a slot concurrently
+    if (a.pair_max > 0)
+        for (uint32_t rr = 0; rr < DIST_TILE_R; rr++) {
+            const uint32_t rb = r0 + rr;
+            if (rb < a.n_ref) {
+                const uint32_t n = min(a.ref_n[rb], a.S);
+                const uint32_t *row = a.ranks + (a.ref_row0 + rb) * (uint64_t)a.P;
+                for (uint32_t i = threadIdx.x; i < n; i += PROBE_THREADS) cf_mark_ids(s_tab, s_ids, row[i], rr);
+            }
+            __syncthreads();
+        }
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(s_tab);
     const bool tile_failed = s_fail != 0;       // filter overflow (cannot happen at <= 32 x 1035 ranks): merge everything
 
@@ -351,13 +433,16 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     const bool far = a.max_distance >= 0 && lut0 > a.max_distance;           // dist_emit: filtered by -d, p-value left 0
     const double p_const = far ? 0.0 : 1.0;
     const uint8_t pass_const = (far || (a.max_pvalue >= 0 && 1.0 > a.max_pvalue)) ? 0 : 1;
+    const int pair_max = a.pair_max;
 
     for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
         if (a.triangle && q <= a.tri_r0 + r0) continue;            // the whole tile lies on or above the diagonal
         const uint32_t nB_all = a.qry_n[q];
         const uint32_t nB = min(nB_all, a.S);
         const uint32_t *rowB = a.ranks + (a.qry_row0 + q) * (uint64_t)a.P;
-        bool confirmed = tile_failed;
+        uint32_t mask = tile_failed ? 0xFFFFFFFFu : 0u;     // references of the tile the query may share a hash with
+        bool dense = tile_failed;                           // more than pair_max of them: the combination is merged as a whole
+        int confirms = 0;
         uint32_t base = 0;
         const uint32_t *pB = rowB + lane;
         constexpr uint32_t GROUP = 32 * PROBE_DEPTH;
@@ -368,25 +453,45 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
         // (two groups per iteration -- 8 lookups in flight per lane, one vote per 256 ranks -- measured slower, 22.6 vs 20.8 ms
         // on the first query tile of configs[2]: the loop is bound by ALU-pipe and shared-memory throughput, not by latency)
         if (a.probe_prefetch && 2 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + GROUP + 32 * (lane & 3)));
-        while (base + GROUP <= nB && !confirmed) {
+        while (base + GROUP <= nB && !dense) {
             if (a.probe_prefetch && base + 3 * GROUP <= nB) asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + base + 2 * GROUP + 32 * (lane & 3)));
 #pragma unroll
             for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = __ldg(pB + 32 * c);
-            confirmed = probe_group<true, LAZY>(s_tab, tab_s, cur, base, nB, lane, rowA, nA_lim);
+            if (probe_group<true, LAZY>(tab_s, cur, base, nB, lane)) {
+                mask = probe_resolve<true>(s_tab, s_ids, cur[0], cur[1], cur[2], cur[3], base, nB, lane, rowA, nA_lim, mask, pair_max, confirms);
+                dense = __popc(mask) > pair_max;
+            }
             base += GROUP; pB += GROUP;
         }
-        if (base < nB && !confirmed) {      // ragged last group
+        if (base < nB && !dense) {      // ragged last group
 #pragma unroll
             for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = (base + 32 * c + lane < nB) ? __ldg(pB + 32 * c) : RANK_PAD;
-            confirmed = probe_group<false, LAZY>(s_tab, tab_s, cur, base, nB, lane, rowA, nA_lim);
+            if (probe_group<false, LAZY>(tab_s, cur, base, nB, lane)) {
+                mask = probe_resolve<false>(s_tab, s_ids, cur[0], cur[1], cur[2], cur[3], base, nB, lane, rowA, nA_lim, mask, pair_max, confirms);
+                dense = __popc(mask) > pair_max;
+            }
         }
-        if (confirmed) {
+        const bool mine = r_ok && !(a.triangle && a.tri_r0 + r >= q);       // this lane's pair exists
+        if (!dense && mask) {
+            // a few candidate references: their pairs go to the pair list (one warp merges one pair, dist_pair_kernel), the other
+            // lanes get the closed form below.  List full: merge the whole combination instead.
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, mine && ((mask >> lane) & 1u));
+            if (want) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(a.pair_count, (unsigned long long)__popc(want));
+                at = __shfl_sync(0xFFFFFFFFu, at, 0);
+                if (at + __popc(want) <= a.pair_capacity) {
+                    if ((want >> lane) & 1u) a.pair_list[at + __popc(want & ((1u << lane) - 1u))] = make_uint2(q, r);
+                } else dense = true;
+            }
+        }
+        if (dense) {
             if (lane == 0) {
                 const uint32_t at = atomicAdd(&a.qcount[blockIdx.x], 1u);
                 a.qlist[(uint64_t)blockIdx.x * a.qlist_stride + at] = q;
                 atomicAdd(a.flag_total, 1ull);
             }
-        } else if (r_ok && !(a.triangle && a.tri_r0 + r >= q)) {
+        } else if (mine && !((mask >> lane) & 1u)) {
             // empty intersection: the merge would take min(s', |A| + |B|) union steps and count nothing
             const uint32_t denom = min(a.S, nA + nB_all);
             if (denom == a.S && a.list_idx && pass_const == 0) {
@@ -402,6 +507,167 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
                 dist_emit(a, q, r, 0u, denom, lenA);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One warp per (query, reference) pair: the sorted merge of compareSketches (CommandDistance.cpp:347-385) as a union count.
+//   common = ties among the first min(s', |A u B|) elements of the sorted union, denom = min(s', |A u B|)
+// (lists cut to their first s' elements: an element beyond index s' can never be among the first s' of the union).
+// Both rows are staged in the warp's shared memory; the query row is cut into 32 runs, lane l takes run l and the reference
+// elements that fall into its value range (one binary search per lane), merges them sequentially counting union elements and
+// ties; a warp scan finds the lane in which the s'-th union element falls, and the search zooms into that lane's run with all 32
+// lanes again (runs of one query element end in a closed form).  ~2 log_32(s') rounds of ~2 s'/32 steps instead of s' lockstep
+// steps for 32 pairs: the path for the few related pairs of a (query, tile) combination (dist_probe_kernel's pair list), where the
+// lockstep kernel would run 32 lanes for one or two useful ones, and for sketch sizes whose 32-reference tile does not fit shared
+// memory (pair_dense).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PAIR_WARPS_MAX = 8;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Shared-memory layout: both rows linear, each preceded by up to 3 words of skew (the TMA bulk copy that stages a row needs
+// 16-byte aligned ends, a row starts on a 4-byte boundary) and followed by the sentinel 0xFFFFFFFF.  Bank conflicts are avoided by
+// the run length instead of padding: lane l's run starts at element l * run, and with an ODD run the 32 starts fall into 32
+// different banks, so lanes that step through their runs at similar speeds do not collide (an even run of 32 put every start
+// into bank 0: 32-way conflicts on every load, 2e7 pairs/s; the padded variant of the same idea measured 1.5e8).
+// The sequential part reads past a lane's ranges on purpose: the element after a lane's query run is the first of the next
+// lane's run, larger than every reference element of this lane, and the element after its reference range is not below that one
+// -- so an exhausted side never wins a comparison and the loop needs no bounds selects, only the two end tests.
+__global__ void __launch_bounds__(PAIR_WARPS_MAX * 32) dist_pair_kernel(const DistArgs a, uint32_t row_pitch, uint32_t run0)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    uint32_t *bufA = smem + (size_t)warp * 2 * row_pitch, *bufB = bufA + row_pitch;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + (size_t)warps * 2 * row_pitch);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar + warp);
+    uint32_t phase = 0;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint64_t total;
+    if (a.pair_dense) total = (uint64_t)a.q_count * a.n_ref;
+    else {
+        const unsigned long long listed = *a.pair_count;
+        total = listed < a.pair_capacity ? listed : a.pair_capacity;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.pair_total) atomicAdd(a.pair_total, (unsigned long long)total);
+    }
+    for (uint64_t idx = (uint64_t)blockIdx.x * warps + warp; idx < total; idx += (uint64_t)gridDim.x * warps) {
+        uint32_t q, r;
+        if (a.pair_dense) {
+            q = a.q_begin + (uint32_t)(idx / a.n_ref); r = (uint32_t)(idx % a.n_ref);
+            if (a.triangle && a.tri_r0 + r >= q) continue;
+        } else {
+            const uint2 e = a.pair_list[idx];
+            q = e.x; r = e.y;
+        }
+        const uint32_t nA = min(a.ref_n[r], a.S), nB = min(a.qry_n[q], a.S);
+        // stage both rows with one bulk copy each (16-byte aligned span around the first n elements), then the sentinels
+        const uintptr_t rowA = (uintptr_t)(a.ranks + (a.ref_row0 + r) * (uint64_t)a.P), rowB = (uintptr_t)(a.ranks + (a.qry_row0 + q) * (uint64_t)a.P);
+        const uintptr_t loA = rowA & ~(uintptr_t)15, loB = rowB & ~(uintptr_t)15;
+        const uint32_t bytesA = nA ? (uint32_t)(((rowA + (uintptr_t)nA * 4 + 15) & ~(uintptr_t)15) - loA) : 0;
+        const uint32_t bytesB = nB ? (uint32_t)(((rowB + (uintptr_t)nB * 4 + 15) & ~(uintptr_t)15) - loB) : 0;
+        uint32_t *sA = bufA + (rowA - loA) / 4, *sB = bufB + (rowB - loB) / 4;
+        __syncwarp();                                        // the previous pair's reads of the buffers are done
+        if (bytesA + bytesB) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytesA + bytesB) : "memory");
+                if (bytesA) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"((uint32_t)__cvta_generic_to_shared(bufA)), "l"(loA), "r"(bytesA), "r"(bar) : "memory");
+                if (bytesB) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"((uint32_t)__cvta_generic_to_shared(bufB)), "l"(loB), "r"(bytesB), "r"(bar) : "memory");
+            }
+            asm volatile("{\n\t.reg .pred p;\n\tPAIR_BULK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra PAIR_BULK_WAIT;\n\t}"
+                         :: "r"(bar), "r"(phase) : "memory");
+            phase ^= 1;
+        }
+        if (lane == 0) { sA[nA] = RANK_PAD; sB[nB] = RANK_PAD; }
+        __syncwarp();
+        uint32_t i0 = 0, i1 = nA, j0 = 0, j1 = nB;          // the segment still to be resolved
+        uint32_t need = a.S;                                 // union elements still to be taken
+        uint32_t common = 0, taken = 0;
+        bool first = true;
+        for (;;) {
+            const uint32_t lenB = j1 - j0;
+            // query elements per lane: odd (bank-conflict-free run starts); 0 when only reference elements are left
+            uint32_t run = first ? run0 : (lenB + 31) / 32;
+            if (run > 1) run |= 1u;
+            first = false;
+            const uint32_t jb = min(j0 + (uint32_t)lane * run, j1), je = min(jb + run, j1);
+            uint32_t ib;
+            if (lane == 0) ib = i0;                          // reference elements below the first query element belong to lane 0
+            else if (jb >= j1) ib = i1;
+            else {
+                const uint32_t v = sB[jb];
+                uint32_t lo = i0, hi = i1;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sA[mid] < v) lo = mid + 1; else hi = mid;
+                }
+                ib = lo;
+            }
+            uint32_t ie = __shfl_down_sync(0xFFFFFFFFu, ib, 1);
+            if (lane == 31) ie = i1;
+            uint32_t u = 0, t = 0;
+            if (ib < ie || jb < je) {
+                // pointers in the shared window; an exhausted side holds an element that cannot win (see above)
+                uint32_t pa = (uint32_t)__cvta_generic_to_shared(sA + ib), pb = (uint32_t)__cvta_generic_to_shared(sB + jb);
+                const uint32_t ea = (uint32_t)__cvta_generic_to_shared(sA + ie), eb = (uint32_t)__cvta_generic_to_shared(sB + je);
+                uint32_t av = lds32(pa), bv = lds32(pb);
+                // the element after the segment's last query element must exceed every reference element of the segment; at the top
+                // level that is the sentinel, below it the next lane's first query element -- except for the LAST lane with query
+                // elements of a zoomed segment, whose successor belongs to the parent's next lane: also larger.  A reference range
+                // that ends at i1 reads sA[i1]: the sentinel or the parent's next element, not below the query run's successor.
+                asm volatile("{\n\t.reg .pred pa, pb, pt, pc;\n\t"
+                             "PAIR_MERGE_LOOP:\n\t"
+                             "setp.le.u32 pa, %0, %1;\n\t"
+                             "setp.le.u32 pb, %1, %0;\n\t"
+                             "and.pred pt, pa, pb;\n\t"
+                             "@pa add.u32 %2, %2, 4;\n\t"
+                             "@pb add.u32 %3, %3, 4;\n\t"
+                             "@pt add.u32 %5, %5, 1;\n\t"
+                             "@pa ld.shared.u32 %0, [%2];\n\t"
+                             "@pb ld.shared.u32 %1, [%3];\n\t"
+                             "add.u32 %4, %4, 1;\n\t"
+                             "setp.lt.u32 pc, %2, %6;\n\t"
+                             "setp.lt.or.u32 pc, %3, %7, pc;\n\t"
+                             "@pc bra PAIR_MERGE_LOOP;\n\t}"
+                             : "+r"(av), "+r"(bv), "+r"(pa), "+r"(pb), "+r"(u), "+r"(t) : "r"(ea), "r"(eb) : "memory");
+            }
+            const uint32_t U = warp_incl_scan(u, lane), T = warp_incl_scan(t, lane);
+            const uint32_t totalU = __shfl_sync(0xFFFFFFFFu, U, 31), totalT = __shfl_sync(0xFFFFFFFFu, T, 31);
+            if (totalU <= need) { common += totalT; taken += totalU; break; }      // the segment ends before the s'-th union element
+            const int L = __ffs(__ballot_sync(0xFFFFFFFFu, U >= need)) - 1;       // the lane in which it falls
+            const uint32_t Uprev = __shfl_sync(0xFFFFFFFFu, U - u, L), Tprev = __shfl_sync(0xFFFFFFFFu, T - t, L);
+            common += Tprev; taken += Uprev; need -= Uprev;
+            i0 = __shfl_sync(0xFFFFFFFFu, ib, L); i1 = __shfl_sync(0xFFFFFFFFu, ie, L);
+            j0 = __shfl_sync(0xFFFFFFFFu, jb, L); j1 = __shfl_sync(0xFFFFFFFFu, je, L);
+            if (j1 - j0 <= 1) {
+                // at most one query element b left: the union runs (reference elements below b), b -- a tie when the next
+                // reference element equals it --, (the rest); `need` (>= 1, fewer than the segment holds) of them are taken
+                if (j1 > j0) {
+                    const uint32_t b = sB[j0];
+                    uint32_t k = 0;
+                    for (uint32_t i = i0 + lane; i < i1; i += 32) k += sA[i] < b;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) k += __shfl_xor_sync(0xFFFFFFFFu, k, d);
+                    const bool tie = i0 + k < i1 && sA[i0 + k] == b;
+                    if (tie && need >= k + 1) common++;
+                }
+                taken += need;
+                break;
+            }
+        }
+        if (lane == 0) dist_emit(a, q, r, common, taken, a.ref_len[r]);
     }
 }
 
@@ -545,7 +811,13 @@ struct mashgpu_dist_job {
                                         // Measured on configs[2], first query tile (B200): off/prefetch 20.9 ms, on/prefetch 21.8, off/no
                                         // prefetch 22.4, on/no prefetch 23.2 -- the predicate logic costs more than the LDS wavefronts saved
     bool auto_off = false;
+    bool bulk_rows = true;              // dist_kernel: stage the query rows with cp.async.bulk (TMA engine): +20 % on the merge-every-pair rate
+                                        // (2.84e9 -> 3.42e9 pairs/s, profiles/r02_dist_bulk_copy.md); MASHGPU_DIST_BULK=0 = coalesced load loop
     DevBuf<uint32_t> qlist, qcount;
+    DevBuf<uint2> pair_list;            // sparse related pairs of the run in flight (dist_probe_kernel -> dist_pair_kernel)
+    DevBuf<unsigned long long> pair_count;      // [0] pairs listed by the run in flight, [1] pairs merged from lists since the job was opened
+    int pair_max = 4;                   // a (query, tile) combination with at most this many candidate references goes to the pair list;
+                                        // 0 = pair path off (MASHGPU_DIST_PAIR_MAX)
     DevBuf<FixEntry> fix_list;
     DevBuf<unsigned long long> fix_count;
     DevBuf<unsigned long long> flag_total;
@@ -678,18 +950,22 @@ int dist_job_tables(mashgpu_ctx *ctx, mashgpu_dist_job *job, cudaStream_t st)
     MG_CUDA(ctx, cudaMemcpyAsync(job->binom_e.p, be.data(), (S + 1) * 4, cudaMemcpyHostToDevice, st));
     MG_CUDA(ctx, cudaStreamSynchronize(st));      // the host vectors go out of scope
     if (!ctx->attr_dist) {   // per context: function attributes are per device
-        cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(dist_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CF_BUCKETS * sizeof(uint32_t)));
+        e = cudaFuncSetAttribute(dist_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dist_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         ctx->attr_dist = true;
     }
+    if (const char *env = getenv("MASHGPU_DIST_PAIR_MAX")) job->pair_max = std::max(0, std::min(31, atoi(env)));
     if (const char *env = getenv("MASHGPU_CF_LAZY")) job->lazy_second = atoi(env) != 0;
     if (const char *env = getenv("MASHGPU_PROBE_PREFETCH")) job->probe_prefetch = atoi(env) != 0;
     if (const char *env = getenv("MASHGPU_DIST_PREFILTER")) job->prefilter_mode = atoi(env) > 0 ? 1 : (atoi(env) == 0 ? 0 : -1);
     // shared memory needed by the merge kernel; larger sketches run dist_kernel_general
-    job->tiled = ((size_t)job->P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * job->P) * 4 <= 227 * 1024;
+    job->tiled = ((((size_t)job->P * DIST_TILE_R + 3) & ~(size_t)3) + (size_t)DIST_WARPS * DIST_ILP * job->P) * 4 + DIST_WARPS * 8 <= 227 * 1024;
+    if (const char *env = getenv("MASHGPU_DIST_BULK")) job->bulk_rows = atoi(env) != 0;
     return MASHGPU_OK;
 }
 
@@ -935,6 +1211,20 @@ extern "C" int mashgpu_dist_prefilter_stats(mashgpu_dist_job *job, uint64_t *com
     return MASHGPU_OK;
 }
 
+extern "C" int mashgpu_dist_pair_stats(mashgpu_dist_job *job, uint64_t *pairs_merged_from_lists)
+{
+    if (!job || !pairs_merged_from_lists) return MASHGPU_ERR_INVALID;
+    mashgpu_ctx *ctx = job->ctx;
+    *pairs_merged_from_lists = 0;
+    if (!job->pair_count.p) return MASHGPU_OK;
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_CUDA(ctx, cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    MG_CUDA(ctx, cudaMemcpy(&v, job->pair_count.p + 1, 8, cudaMemcpyDeviceToHost));
+    *pairs_merged_from_lists = v;
+    return MASHGPU_OK;
+}
+
 extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uint64_t q_count,
                                     uint32_t *d_numer, uint32_t *d_denom, double *d_distance, double *d_pvalue, uint8_t *d_pass,
                                     void *stream)
@@ -960,6 +1250,7 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0; a.q_per_cta = 0;
     a.triangle = job->triangle ? 1 : 0;
     a.tri_r0 = job->self ? 0u : (uint32_t)job->ref_row0;
+    a.pair_list = nullptr; a.pair_count = nullptr; a.pair_capacity = 0; a.pair_total = nullptr; a.pair_max = 0; a.pair_dense = 0;
     a.probe_prefetch = job->probe_prefetch ? 1 : 0;
     {   // queue for the deferred p-values: 1/16 of the pairs (at least 2^20); beyond that dist_emit evaluates in place
         const uint64_t pairs = q_count * job->n_ref;
@@ -974,6 +1265,27 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         ctx->kernel_launches++;
         return cudaGetLastError();
     };
+    // warp-per-pair merge: shared memory for two rows of S ranks per warp
+    const uint32_t run0 = ((a.S + 31u) / 32u) | 1u;          // first-round run: odd, 32 runs cover the row
+    const uint32_t row_pitch = (a.S + 1u + 8u + 3u) & ~3u;    // S elements + sentinel + skew and 16-byte rounding of the bulk copy
+    const int pair_warps = (int)std::min<size_t>(PAIR_WARPS_MAX, (220 * 1024) / ((size_t)row_pitch * 8));
+    auto launch_pairs = [&]() {
+        const size_t smem_p = (size_t)pair_warps * 2 * row_pitch * 4 + (size_t)pair_warps * 8;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem_p, 1)));
+        dist_pair_kernel<<<ctx->sm_count * ctas_per_sm, pair_warps * 32, smem_p, st>>>(a, row_pitch, run0);
+        ctx->kernel_launches++;
+        return cudaGetLastError();
+    };
+    if (!job->tiled && pair_warps >= 1) {
+        // sketch sizes whose 32-reference tile does not fit shared memory (s > 1035, e.g. `-s 10000`): every pair by the warp-per-pair merge
+        a.pair_dense = 1;
+        time_begin(ctx, ctx->dist_events, st);
+        MG_CUDA(ctx, launch_pairs());
+        MG_CUDA(ctx, launch_fix());
+        time_end(ctx, ctx->dist_events, st);
+        ctx->dist_launches++;
+        return MASHGPU_OK;
+    }
     if (!job->tiled) {
         const uint64_t total = q_count * job->n_ref;
         time_begin(ctx, ctx->dist_events, st);
@@ -987,7 +1299,10 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     }
     const uint32_t r_tiles = (uint32_t)((job->n_ref + DIST_TILE_R - 1) / DIST_TILE_R);
     const uint32_t round = DIST_WARPS * DIST_ILP;
-    const size_t smem = ((size_t)a.P * DIST_TILE_R + (size_t)DIST_WARPS * DIST_ILP * a.P) * 4;
+    // query rows by TMA bulk copy (MASHGPU_DIST_BULK=1) when the padded buffers still fit; default: coalesced loads
+    const size_t smem_bulk = ((((size_t)a.P * DIST_TILE_R + 3) & ~(size_t)3) + (size_t)DIST_WARPS * DIST_ILP * (((size_t)a.P + 7) & ~(size_t)3)) * 4 + DIST_WARPS * 8;
+    const bool bulk = job->bulk_rows && smem_bulk <= 227 * 1024;
+    const size_t smem = bulk ? smem_bulk : ((((size_t)a.P * DIST_TILE_R + 3) & ~(size_t)3) + (size_t)DIST_WARPS * DIST_ILP * a.P) * 4 + DIST_WARPS * 8;
     a.qlist = nullptr; a.qcount = nullptr; a.qlist_stride = 0; a.flag_total = nullptr; a.use_qlist = 0;
     dist_collect_flags(job);
     const bool prefilter = job->prefilter_mode > 0 || (job->prefilter_mode < 0 && !job->auto_off);
@@ -1004,6 +1319,18 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         }
         MG_CUDA(ctx, cudaMemsetAsync(job->qcount.p, 0, (size_t)r_tiles * 4, st));
         a.qlist = job->qlist.p; a.qcount = job->qcount.p; a.qlist_stride = q_count; a.flag_total = job->flag_total.p;
+        if (job->pair_max > 0 && pair_warps >= 1) {
+            const uint64_t pairs = q_count * job->n_ref;
+            const uint64_t cap = std::max<uint64_t>(1ull << 20, pairs / 16);
+            if (job->pair_list.n < cap && job->pair_list.alloc(cap) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (pair list)");
+            if (!job->pair_count.p) {
+                if (job->pair_count.alloc(2) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (pair counter)");
+                MG_CUDA(ctx, cudaMemsetAsync(job->pair_count.p, 0, 16, st));
+            }
+            MG_CUDA(ctx, cudaMemsetAsync(job->pair_count.p, 0, 8, st));
+            a.pair_list = job->pair_list.p; a.pair_count = job->pair_count.p; a.pair_total = job->pair_count.p + 1;
+            a.pair_capacity = job->pair_list.n; a.pair_max = job->pair_max;
+        }
         // probe: one CTA keeps its filter for a long run of queries (the build costs about as much as probing ~100 queries)
         uint32_t p_slices = std::max(1u, (uint32_t)(2 * ctx->sm_count + r_tiles - 1) / r_tiles);
         uint32_t p_per_cta = (uint32_t)((q_count + p_slices - 1) / p_slices);
@@ -1011,8 +1338,10 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         p_slices = (uint32_t)((q_count + p_per_cta - 1) / p_per_cta);
         a.q_per_cta = p_per_cta;
         time_begin(ctx, ctx->dist_events, st);
-        if (job->lazy_second) dist_probe_kernel<true><<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
-        else dist_probe_kernel<false><<<dim3(r_tiles, p_slices), PROBE_THREADS, CF_BUCKETS * sizeof(uint32_t), st>>>(a);
+        // without the pair path the kernel keeps 128 KB of shared memory and twice the L1 (query rows stream through L1)
+        const size_t probe_smem = a.pair_max > 0 ? PROBE_SMEM : CF_BUCKETS * sizeof(uint32_t);
+        if (job->lazy_second) dist_probe_kernel<true><<<dim3(r_tiles, p_slices), PROBE_THREADS, probe_smem, st>>>(a);
+        else dist_probe_kernel<false><<<dim3(r_tiles, p_slices), PROBE_THREADS, probe_smem, st>>>(a);
         time_end(ctx, ctx->dist_events, st);
         MG_CUDA(ctx, cudaGetLastError());
         // merge the listed combinations: a few CTAs per tile walk its list (CTAs of tiles with short lists exit at once)
@@ -1020,8 +1349,10 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
         a.q_per_cta = 2 * round;
         const uint32_t m_slices = (uint32_t)std::min<uint64_t>(8, (q_count + a.q_per_cta - 1) / a.q_per_cta);
         time_begin(ctx, ctx->dist_events, st);
-        dist_kernel<<<dim3(r_tiles, m_slices), DIST_THREADS, smem, st>>>(a);
+        if (bulk) dist_kernel<true><<<dim3(r_tiles, m_slices), DIST_THREADS, smem, st>>>(a);
+        else dist_kernel<false><<<dim3(r_tiles, m_slices), DIST_THREADS, smem, st>>>(a);
         MG_CUDA(ctx, cudaGetLastError());
+        if (a.pair_list) MG_CUDA(ctx, launch_pairs());
         MG_CUDA(ctx, launch_fix());
         time_end(ctx, ctx->dist_events, st);
         job->combos_probed += need;
@@ -1043,7 +1374,8 @@ extern "C" int mashgpu_dist_run_dev(mashgpu_dist_job *job, uint64_t q_begin, uin
     a.q_per_cta = q_per_cta;
     dim3 grid(r_tiles, slices);
     time_begin(ctx, ctx->dist_events, st);
-    dist_kernel<<<grid, DIST_THREADS, smem, st>>>(a);
+    if (bulk) dist_kernel<true><<<grid, DIST_THREADS, smem, st>>>(a);
+    else dist_kernel<false><<<grid, DIST_THREADS, smem, st>>>(a);
     MG_CUDA(ctx, cudaGetLastError());
     MG_CUDA(ctx, launch_fix());
     time_end(ctx, ctx->dist_events, st);

@@ -121,6 +121,65 @@ MG_HD bool cf_lookup(const uint32_t *tab, uint32_t code)
     return cf_word_has(w1, fp) || cf_word_has(w2, fp);
 }
 
+// ---- which reference does a fingerprint belong to?  One byte per slot (2 slots per bucket), filled after the filter is built:
+// the reference index 0..31 when every rank that owns this slot's fingerprint comes from one reference of the tile, CF_ID_MULTI
+// when several do.  A filter hit then names the one reference the query may share the rank with -- no search -- and only
+// CF_ID_MULTI hits need the exact confirmation.  (A rank's fingerprint may sit in either of its two buckets, and another rank
+// with the same fingerprint and bucket pair shares the entry: every slot that shows the fingerprint is marked.)
+// The byte also carries 3 more bits of the rank (a second hash, values 0..6) above the 5-bit reference index: a query rank that
+// merely collides with the slot's 16-bit fingerprint is rejected 6 times out of 7 before it costs a spurious pair merge.
+constexpr uint32_t CF_ID_NONE = 0xFFu, CF_ID_MULTI = 0xFEu;
+
+MG_HD uint32_t cf_tag(uint32_t code)
+{
+    const uint32_t v = (code * 0x85EBCA6Bu) >> 29;
+    return v > 6u ? 6u : v;
+}
+
+MG_HD void cf_mark_slot(uint8_t *ids, uint32_t slot, uint32_t value)
+{
+    const uint32_t old = ids[slot];
+    ids[slot] = (uint8_t)((old == CF_ID_NONE || old == value) ? value : CF_ID_MULTI);
+}
+
+// marks the slots holding the fingerprint of `code` with reference r.  Calls for different r must not run concurrently
+// (the probe kernel processes one reference per phase); concurrent calls for the same r are fine.
+MG_HD void cf_mark_ids(const uint32_t *tab, uint8_t *ids, uint32_t code, uint32_t r)
+{
+    const uint32_t h = cf_hash(code);
+    const uint32_t fp = cf_fp(h);
+    const uint32_t b1 = cf_bucket(h), b2 = cf_alt(b1, fp);
+    const uint32_t w1 = tab[b1], w2 = tab[b2];
+    const uint32_t value = (cf_tag(code) << 5) | r;
+    if ((w1 & 0xFFFFu) == fp) cf_mark_slot(ids, 2 * b1, value);
+    if ((w1 >> 16) == fp) cf_mark_slot(ids, 2 * b1 + 1, value);
+    if ((w2 & 0xFFFFu) == fp) cf_mark_slot(ids, 2 * b2, value);
+    if ((w2 >> 16) == fp) cf_mark_slot(ids, 2 * b2 + 1, value);
+}
+
+// references that may hold `code`: bit r for every slot that shows its fingerprint and names reference r; *multi is set when
+// a matching slot is shared by several references.  0 / false: the code is not in the filter.
+MG_HD uint32_t cf_owner_bits(const uint32_t *tab, const uint8_t *ids, uint32_t code, bool *multi)
+{
+    const uint32_t h = cf_hash(code);
+    const uint32_t fp = cf_fp(h);
+    const uint32_t b1 = cf_bucket(h), b2 = cf_alt(b1, fp);
+    const uint32_t w1 = tab[b1], w2 = tab[b2];
+    uint32_t bits = 0;
+    bool m = false;
+    const uint32_t slot[4] = {2 * b1, 2 * b1 + 1, 2 * b2, 2 * b2 + 1};
+    const bool hit[4] = {(w1 & 0xFFFFu) == fp, (w1 >> 16) == fp, (w2 & 0xFFFFu) == fp, (w2 >> 16) == fp};
+    const uint32_t tag = cf_tag(code);
+    for (int i = 0; i < 4; i++)
+        if (hit[i]) {
+            const uint32_t id = ids[slot[i]];
+            if (id >= CF_ID_MULTI) m = true;              // shared slot (CF_ID_NONE: ids not built -- the caller confirms every hit)
+            else if ((id >> 5) == tag) bits |= 1u << (id & 31u);
+        }
+    *multi = m;
+    return bits;
+}
+
 // The probe kernel's form of the lookup: everything derives from ONE product h4 = rank * (C << 2) = h << 2:
 //   byte offset of bucket 1 = h4 & mask;  x = (h4 >> 16) & 0xBFFE = fp - 1;  offset 2 = offset 1 ^ ((x * K + K) & mask)
 //   with K = (alt multiplier << 2);  f2 = x * 0x10001 + 0x10001 = fp in both halves.

@@ -29,7 +29,7 @@ constexpr int SCAN_WARP_WORDS = SCAN_WARP_TILE / 8 + SCAN_HALO_WORDS;   // 136 n
 constexpr int SCAN_WARP_VECS = SCAN_WARP_WORDS / 2;                     // 68 16-byte vectors
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
 
-enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2, SCAN_COUNT = 3 };
+enum ScanMode : int { SCAN_SKETCH = 0, SCAN_SCREEN = 1, SCAN_DUMP = 2, SCAN_COUNT = 3, SCAN_EVENTS = 4 };
 
 struct ScanArgs {
     const uint8_t *stream;        // flat byte stream (ASCII source; NULL when the packed source is used)
@@ -75,6 +75,11 @@ struct ScanArgs {
     // SCAN_COUNT: occurrences of one hash at stream positions [count_lo, count_hi]
     uint64_t count_target, count_lo, count_hi;
     uint32_t *count_out;
+    // SCAN_EVENTS (`-c`): every k-mer whose hash is at or below the threshold of its position band (the "units" of this pass)
+    // is appended as an event {position, hash}; sketch.cu replays the events in stream order through the heap
+    uint64_t *ev_pos, *ev_hash;
+    unsigned long long *ev_count;
+    uint64_t ev_capacity;
 };
 
 __device__ __forceinline__ uint32_t slot_hash(uint64_t key, uint32_t log2cap)
@@ -122,6 +127,11 @@ static __device__ __noinline__ void scan_emit(const ScanArgs &a, uint32_t hash_l
     const uint32_t u = lo;
     if (a.only_unit >= 0 && (int64_t)u != a.only_unit) return;
     if (hash > a.unit_t[u]) return;
+    if (a.mode == SCAN_EVENTS) {
+        const unsigned long long at = atomicAdd(a.ev_count, 1ull);
+        if (at < a.ev_capacity) { a.ev_pos[at] = pos; a.ev_hash[at] = hash; }
+        return;
+    }
     if (hash == EMPTY_KEY) { atomicAdd(&a.unit_maxhash[u], 1u); return; }
     const int64_t slot = table_add(a.tab_keys + a.tab_off[u], a.tab_cnt + a.tab_off[u], a.tab_log2[u], hash);
     if (slot < 0) { atomicOr(&a.unit_flags[u], 1u); return; }

@@ -13,6 +13,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <chrono>
 #include <vector>
 #include <algorithm>
 #include "common.cuh"
@@ -455,8 +456,12 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
     if (!job) return MASHGPU_ERR_INVALID;
     mashgpu_ctx *ctx = job->ctx;
     MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool trace = getenv("MASHGPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     MG_TRY(screen_flush_acc(job));
     MG_TRY(screen_collect(job));
+    const double t1 = now();
     cudaStream_t st = ctx->stream;
     const int k = job->params.kmer_size;
     int asize = 0;
@@ -515,11 +520,14 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
             MG_CUDA(ctx, cudaGetLastError());
             MG_CUDA(ctx, cudaStreamSynchronize(st));      // d_prio / d_best go out of scope below
         }
+        const double t2 = now();
+        if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[mashgpu] screen_finish: collect %.2f ms, alloc+reduce %.2f ms (reduce done %.2f)\n", t1 - t0, t2 - t1, now() - t1); }
         if (shared) MG_CUDA(ctx, cudaMemcpyAsync(shared, d_shared.p, n * 8, cudaMemcpyDeviceToHost, st));
         if (median) MG_CUDA(ctx, cudaMemcpyAsync(median, d_median.p, n * 8, cudaMemcpyDeviceToHost, st));
         if (identity) MG_CUDA(ctx, cudaMemcpyAsync(identity, d_ident.p, n * 8, cudaMemcpyDeviceToHost, st));
         if (pvalue) MG_CUDA(ctx, cudaMemcpyAsync(pvalue, d_p.p, n * 8, cudaMemcpyDeviceToHost, st));
         MG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (trace) fprintf(stderr, "[mashgpu] screen_finish: total %.2f ms\n", now() - t0);
     } else {
         MG_CUDA(ctx, cudaStreamSynchronize(st));
     }

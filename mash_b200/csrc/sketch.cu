@@ -11,13 +11,16 @@
 #include <cmath>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "common.cuh"
 #include "scan.cuh"
 #include "sketch_core.cuh"
 #include "pack.h"
 #include <chrono>
+#include <condition_variable>
 #include <future>
+#include <mutex>
 #include <thread>
 #include <cstdlib>
 
@@ -88,7 +91,8 @@ __device__ __forceinline__ uint32_t table_count(const uint64_t *keys, const uint
 }
 
 // One CTA per unit; tables up to 2^SEL_MAX_LOG2 slots.  flags bit1 = fewer than s distinct survivors although
-// k-mers were filtered (unit_t != max); units whose table is too large for shared memory get bit2.
+// k-mers were filtered (unit_t != max); units whose table is too large for shared memory are left to the batched
+// segmented sort below (large sketch sizes: `-s 10000` needs ~2^17 candidate slots per unit).
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     uint32_t unit_begin, uint32_t n_units, const uint64_t *unit_t, const uint64_t *tab_off, const uint32_t *tab_log2,
     const uint64_t *tab_keys, const uint32_t *tab_cnt, const uint32_t *unit_maxhash, uint32_t *unit_flags,
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
     if (u >= unit_begin + n_units) return;
     const uint32_t log2cap = tab_log2[u];
     if (unit_flags[u] & 1u) return;                    // overflowed: will be re-run
-    if (log2cap > SEL_MAX_LOG2) { if (threadIdx.x == 0) atomicOr(&unit_flags[u], 4u); return; }
+    if (log2cap > SEL_MAX_LOG2) return;              // tables beyond the shared-memory sort: batched segmented sort (select_big_*)
     const uint32_t cap = 1u << log2cap;
     const uint64_t *keys = tab_keys + tab_off[u];
     const uint32_t *cnt = tab_cnt + tab_off[u];
@@ -141,6 +145,60 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(
         uint64_t key = i < n ? sk[i] : EMPTY_KEY;
         out_hashes[(uint64_t)u * s + i] = key;
         if (out_counts) out_counts[(uint64_t)u * s + i] = i < n ? table_count(keys, cnt, log2cap, key) : unit_maxhash[u];
+    }
+}
+
+// ---- big tables: compact the qualifying keys of every big unit into one buffer (segment b = unit big_units[b]), sort all
+// segments with one segmented radix sort, emit the first s of each.  Same outputs and flags as select_kernel.
+__global__ void select_big_compact_kernel(const uint32_t *big_units, uint32_t n_big, const uint64_t *seg_off, const uint64_t *tab_off, const uint32_t *tab_log2,
+                                          const uint64_t *tab_keys, const uint32_t *tab_cnt, const uint32_t *unit_flags, uint32_t min_copies,
+                                          uint64_t *comp, uint32_t *seg_n)
+{
+    const uint32_t b = blockIdx.y;
+    if (b >= n_big) return;
+    const uint32_t u = big_units[b];
+    if (unit_flags[u] & 1u) return;                    // overflowed: will be re-run
+    const uint64_t cap = 1ull << tab_log2[u];
+    const uint64_t *keys = tab_keys + tab_off[u];
+    const uint32_t *cnt = tab_cnt + tab_off[u];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        if (k != EMPTY_KEY && cnt[i] >= min_copies) comp[seg_off[b] + atomicAdd(&seg_n[b], 1u)] = k;
+    }
+}
+
+__global__ void select_big_bounds_kernel(const uint64_t *seg_off, const uint32_t *seg_n, uint32_t n_big, long long *seg_begin, long long *seg_end)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_big) return;
+    seg_begin[b] = (long long)seg_off[b];
+    seg_end[b] = (long long)(seg_off[b] + seg_n[b]);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_big_emit_kernel(
+    const uint32_t *big_units, uint32_t n_big, const uint64_t *seg_off, const uint32_t *seg_n, const uint64_t *sorted,
+    const uint64_t *unit_t, const uint64_t *tab_off, const uint32_t *tab_log2, const uint64_t *tab_keys, const uint32_t *tab_cnt,
+    const uint32_t *unit_maxhash, uint32_t *unit_flags, uint32_t s, uint64_t capped_t, uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n,
+    uint32_t min_copies)
+{
+    const uint32_t b = blockIdx.x;
+    if (b >= n_big) return;
+    const uint32_t u = big_units[b];
+    if (unit_flags[u] & 1u) return;
+    const uint32_t n = seg_n[b];
+    const uint32_t n_max = (unit_maxhash[u] && unit_maxhash[u] >= min_copies) ? 1u : 0u;
+    const uint64_t total = (uint64_t)n + n_max;
+    const uint32_t m = (uint32_t)(total < s ? total : s);
+    if (threadIdx.x == 0) {
+        out_n[u] = m;
+        if (total < s && unit_t[u] != EMPTY_KEY && unit_t[u] != capped_t) atomicOr(&unit_flags[u], 2u);
+    }
+    const uint64_t *keys = tab_keys + tab_off[u];
+    const uint32_t *cnt = tab_cnt + tab_off[u];
+    for (uint32_t i = threadIdx.x; i < m; i += SEL_THREADS) {
+        const uint64_t key = i < n ? sorted[seg_off[b] + i] : EMPTY_KEY;
+        out_hashes[(uint64_t)u * s + i] = key;
+        if (out_counts) out_counts[(uint64_t)u * s + i] = i < n ? table_count(keys, cnt, tab_log2[u], key) : unit_maxhash[u];
     }
 }
 
@@ -559,6 +617,37 @@ int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, cons
                                                                      d_out_hashes, d_out_counts, d_out_n, mc);
     ctx->kernel_launches++;
     MG_CUDA(ctx, cudaGetLastError());
+    {   // units whose candidate table exceeds the shared-memory sort (large sketch sizes): one segmented sort for all of them
+        std::vector<uint32_t> big;
+        std::vector<uint64_t> seg_off;
+        uint64_t comp_total = 0, max_cap = 0;
+        for (uint32_t u = 0; u < n_units; u++)
+            if (h_log2[u] > SEL_MAX_LOG2) { big.push_back(u); seg_off.push_back(comp_total); comp_total += 1ull << h_log2[u]; max_cap = std::max<uint64_t>(max_cap, 1ull << h_log2[u]); }
+        if (!big.empty()) {
+            if (comp_total >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "candidate tables of one wave exceed 2^31 slots (sketch_size %u x %zu units): feed fewer units per call", s, big.size());
+            const uint32_t n_big = (uint32_t)big.size();
+            uint32_t *d_big = ctx->sc_big_units.get<uint32_t>(n_big), *d_seg_n = ctx->sc_big_n.get<uint32_t>(n_big);
+            uint64_t *d_seg_off = ctx->sc_big_off.get<uint64_t>(n_big);
+            long long *d_bounds = ctx->sc_big_bounds.get<long long>(2ull * n_big);
+            uint64_t *d_comp = ctx->sc_big_comp.get<uint64_t>(comp_total), *d_sorted = ctx->sc_big_sorted.get<uint64_t>(comp_total);
+            if (!d_big || !d_seg_n || !d_seg_off || !d_bounds || !d_comp || !d_sorted) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort buffers of %llu candidate slots)", (unsigned long long)comp_total);
+            MG_CUDA(ctx, cudaMemcpyAsync(d_big, big.data(), n_big * 4ull, cudaMemcpyHostToDevice, st));
+            MG_CUDA(ctx, cudaMemcpyAsync(d_seg_off, seg_off.data(), n_big * 8ull, cudaMemcpyHostToDevice, st));
+            MG_CUDA(ctx, cudaMemsetAsync(d_seg_n, 0, n_big * 4ull, st));
+            const unsigned bx = (unsigned)std::min<uint64_t>((max_cap + 255) / 256, 256);
+            select_big_compact_kernel<<<dim3(bx, n_big), 256, 0, st>>>(d_big, n_big, d_seg_off, d_off.p, d_log2.p, d_keys.p, d_cnt.p, d_flags.p, mc, d_comp, d_seg_n);
+            select_big_bounds_kernel<<<(n_big + 255) / 256, 256, 0, st>>>(d_seg_off, d_seg_n, n_big, d_bounds, d_bounds + n_big);
+            size_t tmp_bytes = 0;
+            cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, d_comp, d_sorted, (int)comp_total, (int)n_big, d_bounds, d_bounds + n_big, 0, 64, st);
+            uint8_t *d_tmp = ctx->sc_big_tmp.get<uint8_t>(tmp_bytes);
+            if (!d_tmp) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (segmented sort scratch)");
+            MG_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortKeys(d_tmp, tmp_bytes, d_comp, d_sorted, (int)comp_total, (int)n_big, d_bounds, d_bounds + n_big, 0, 64, st));
+            select_big_emit_kernel<<<n_big, SEL_THREADS, 0, st>>>(d_big, n_big, d_seg_off, d_seg_n, d_sorted, d_t.p, d_off.p, d_log2.p, d_keys.p, d_cnt.p, d_maxhash.p, d_flags.p,
+                                                                s, S.t_cap ? S.t_cap_value : EMPTY_KEY, d_out_hashes, d_out_counts, d_out_n, mc);
+            ctx->kernel_launches += 4;
+            MG_CUDA(ctx, cudaGetLastError());
+        }
+    }
     if (want_counts) {
         quirk_kernel<<<n_units, SEL_THREADS, 0, st>>>(0, n_units, s, d_out_hashes, d_out_counts, d_out_n, d_off.p, d_log2.p, d_keys.p, d_cnt.p,
                                                       d_first, d_last, d_flags.p, d_qtarget, d_qtstar, mc);
@@ -856,7 +945,6 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         int64_t wave = -1;
         uint64_t *h_codes = nullptr, *d_codes = nullptr; uint32_t *d_inval = nullptr;
         std::vector<uint64_t> unit_start; std::vector<PackRun> runs; uint64_t len = 0;
-        std::future<int> job;
     };
     PackSlot pslot[2];
     const int n_pslots = (feed & FEED_PACK) ? (n_waves > 1 ? 2 : 1) : 0;
@@ -910,15 +998,17 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         apply_runs_kernel<<<std::max(1u, blocks), 256, 0, cs>>>(d_runs, nr, P.d_inval);
         if (cudaGetLastError() != cudaSuccess) return MASHGPU_ERR_CUDA;
         if (cudaEventRecord(ctx->pack_copied[b], cs) != cudaSuccess) return MASHGPU_ERR_CUDA;
-        if (cudaEventSynchronize(ctx->pack_copied[b]) != cudaSuccess) return MASHGPU_ERR_CUDA;      // P.runs / pinned codes are reused by the next job
-        return MASHGPU_OK;
+        return MASHGPU_OK;          // the upload is in flight: the slot is ready once the event has fired (its buffers are reused only after that)
     };
 
     // ---- scheduler: both producers claim the next unclaimed wave they may take; this thread runs the kernels of whichever
     // wave is ready first and hands its sketches back
     std::vector<uint8_t> claimed(n_waves, 0);
     size_t a_cursor = 0, p_cursor = 0, done = 0;
+    std::mutex mu;                      // guards `claimed` and the packed slots' states (this thread and the packer thread)
+    std::condition_variable cv;
     auto claim = [&](size_t &cursor, bool need_ascii) -> int64_t {
+        std::lock_guard<std::mutex> lock(mu);
         for (size_t wi = cursor; wi < n_waves; wi++) {
             if (claimed[wi]) { if (wi == cursor) cursor++; continue; }
             if (need_ascii && !ascii_ok[wi] && (feed & FEED_PACK)) continue;      // left to the packer
@@ -928,7 +1018,10 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         return -1;
     };
     int rc = MASHGPU_OK;
-    bool packer_busy = false;
+    enum { P_EMPTY, P_PACKING, P_UPLOADING };
+    int pstate[2] = {P_EMPTY, P_EMPTY};         // under `mu`
+    int pack_rc = MASHGPU_OK;                   // under `mu`: first failure of the packer thread
+    bool stop = false, packer_done = n_pslots == 0;
     auto run_wave = [&](size_t wi, const SketchStream &S) -> int {
         const Wave &w = waves[wi];
         const uint64_t nu = w.unit_end - w.unit_begin;
@@ -941,29 +1034,57 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return MASHGPU_OK;
     };
+    // the packer thread: claims a wave whenever one of its two slots is empty, packs it on `threads` host threads, enqueues the
+    // upload and moves on -- it never waits for this thread's kernels
+    std::thread packer;
+    if (n_pslots)
+        packer = std::thread([&]() {
+            cudaSetDevice(ctx->device);
+            for (;;) {
+                int b = -1;
+                {
+                    std::unique_lock<std::mutex> lock(mu);
+                    cv.wait(lock, [&] { return stop || pstate[0] == P_EMPTY || (n_pslots > 1 && pstate[1] == P_EMPTY); });
+                    if (stop) break;
+                    b = pstate[0] == P_EMPTY ? 0 : 1;
+                }
+                const int64_t wi = claim(p_cursor, false);
+                if (wi < 0) break;
+                { std::lock_guard<std::mutex> lock(mu); pslot[b].wave = wi; pstate[b] = P_PACKING; }
+                const int r = pack_job((size_t)wi, b);
+                std::lock_guard<std::mutex> lock(mu);
+                if (r != MASHGPU_OK) { pack_rc = r; break; }
+                pstate[b] = P_UPLOADING;
+            }
+            std::lock_guard<std::mutex> lock(mu);
+            packer_done = true;
+        });
     while (done < n_waves && rc == MASHGPU_OK) {
-        // 1. keep the producers busy
+        // 1. keep the ASCII producer busy
         for (int b = 0; b < n_aslots && rc == MASHGPU_OK; b++)
             if (aslot[b].wave < 0) {
                 const int64_t wi = claim(a_cursor, true);
                 if (wi >= 0) rc = issue_copy((size_t)wi, b);
             }
         if (rc != MASHGPU_OK) break;
-        if (!packer_busy)
-            for (int b = 0; b < n_pslots; b++)
-                if (pslot[b].wave < 0) {
-                    const int64_t wi = claim(p_cursor, false);
-                    if (wi >= 0) {
-                        pslot[b].wave = wi;
-                        pslot[b].job = std::async(std::launch::async, pack_job, (size_t)wi, b);
-                        packer_busy = true;
-                    }
-                    break;
+        // 2. a finished wave?  packed first, then ASCII copies in issue order
+        int ready_p = -1, ready_a = -1, uploading = -1;
+        bool packing = false, p_done = false;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (pack_rc != MASHGPU_OK) { rc = fail(ctx, pack_rc, "host packing / packed upload failed"); break; }
+            p_done = packer_done;
+            for (int b = 0; b < n_pslots; b++) {
+                if (pstate[b] == P_PACKING) packing = true;
+                if (pstate[b] == P_UPLOADING) {
+                    const cudaError_t q = cudaEventQuery(ctx->pack_copied[b]);
+                    if (q == cudaSuccess) { if (ready_p < 0 || pslot[b].wave < pslot[ready_p].wave) ready_p = b; }
+                    else if (q != cudaErrorNotReady) { rc = fail(ctx, MASHGPU_ERR_CUDA, "packed upload failed: %s", cudaGetErrorString(q)); break; }
+                    else { cudaGetLastError(); uploading = b; }
                 }
-        // 2. a finished wave?  packed first (its slot also frees the packer), then ASCII copies in issue order
-        int ready_p = -1, ready_a = -1;
-        for (int b = 0; b < n_pslots; b++)
-            if (pslot[b].wave >= 0 && pslot[b].job.valid() && pslot[b].job.wait_for(std::chrono::seconds(0)) == std::future_status::ready) { ready_p = b; break; }
+            }
+        }
+        if (rc != MASHGPU_OK) break;
         if (ready_p < 0) {
             int64_t best = -1;
             for (int b = 0; b < n_aslots; b++)
@@ -977,49 +1098,449 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
         if (rc != MASHGPU_OK) break;
         if (ready_p >= 0) {
             PackSlot &P = pslot[ready_p];
-            rc = P.job.get();
-            packer_busy = false;
-            if (rc != MASHGPU_OK) { rc = fail(ctx, rc, "packed upload of wave %lld failed", (long long)P.wave); break; }
-            ctx->kernel_launches++;             // apply_runs_kernel
+            ctx->kernel_launches++;             // apply_runs_kernel of the upload
             SketchStream S;
             S.d_codes = P.d_codes; S.d_inval = P.d_inval; S.unit_start = P.unit_start.data(); S.n_units = waves[P.wave].unit_end - waves[P.wave].unit_begin;
-            // the other pinned buffer is free: let the packer start on its next wave while the kernels of this one run
-            for (int b = 0; b < n_pslots; b++)
-                if (pslot[b].wave < 0) {
-                    const int64_t wi = claim(p_cursor, false);
-                    if (wi >= 0) { pslot[b].wave = wi; pslot[b].job = std::async(std::launch::async, pack_job, (size_t)wi, b); packer_busy = true; }
-                    break;
-                }
             rc = run_wave((size_t)P.wave, S);
-            P.wave = -1;
+            { std::lock_guard<std::mutex> lock(mu); P.wave = -1; pstate[ready_p] = P_EMPTY; }
+            cv.notify_all();
             done++;
         } else if (ready_a >= 0) {
             AsciiSlot &A = aslot[ready_a];
             SketchStream S;
             S.d_stream = A.d; S.unit_start = A.unit_start.data(); S.n_units = waves[A.wave].unit_end - waves[A.wave].unit_begin;
-            const size_t wi = (size_t)A.wave;
-            rc = run_wave(wi, S);
+            rc = run_wave((size_t)A.wave, S);
             A.wave = -1;
             done++;
         } else {
             // nothing ready: wait for whichever producer is in flight
-            bool waited = false;
-            for (int b = 0; b < n_pslots && !waited; b++)
-                if (pslot[b].wave >= 0 && pslot[b].job.valid()) { pslot[b].job.wait_for(std::chrono::microseconds(200)); waited = true; }
-            if (!waited) {
-                int64_t best = -1; int bb = -1;
-                for (int b = 0; b < n_aslots; b++)
-                    if (aslot[b].wave >= 0 && (best < 0 || aslot[b].wave < best)) { best = aslot[b].wave; bb = b; }
-                if (bb >= 0) MG_CUDA(ctx, cudaEventSynchronize(copied[bb]));
-                else { rc = fail(ctx, MASHGPU_ERR_INVALID, "feed scheduler stalled (%zu of %zu waves done)", done, n_waves); break; }
-            }
+            int64_t best = -1; int bb = -1;
+            for (int b = 0; b < n_aslots; b++)
+                if (aslot[b].wave >= 0 && (best < 0 || aslot[b].wave < best)) { best = aslot[b].wave; bb = b; }
+            if (uploading >= 0) cudaEventSynchronize(ctx->pack_copied[uploading]);
+            else if (packing || (!p_done && bb < 0)) std::this_thread::sleep_for(std::chrono::microseconds(50));
+            else if (bb >= 0) MG_CUDA(ctx, cudaEventSynchronize(copied[bb]));
+            else { rc = fail(ctx, MASHGPU_ERR_INVALID, "feed scheduler stalled (%zu of %zu waves done)", done, n_waves); break; }
         }
     }
-    for (int b = 0; b < n_pslots; b++)
-        if (pslot[b].job.valid()) pslot[b].job.wait();          // never leave a packing thread behind (it references this frame)
+    if (packer.joinable()) {
+        { std::lock_guard<std::mutex> lock(mu); stop = true; }
+        cv.notify_all();
+        packer.join();                           // never leave the packer thread behind (it references this frame)
+    }
     cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->pack_stream) cudaStreamSynchronize(ctx->pack_stream);
     return rc;
+}
+
+extern "C" int mashgpu_sketch_batch_packed(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                           const uint64_t *codes, uint64_t stream_len, const uint64_t *runs, uint64_t n_runs,
+                                           const uint64_t *unit_start, uint64_t n_units,
+                                           uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    if (n_units == 0) return MASHGPU_OK;
+    if (!is_dna_alphabet(params)) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "the packed source only carries the alphabet {A,C,G,T}");
+    if (!codes || !unit_start || !out_hashes || !out_n || (n_runs && !runs)) return fail(ctx, MASHGPU_ERR_INVALID, "NULL argument");
+    if (n_units > 0xFFFFFFF0ull) return fail(ctx, MASHGPU_ERR_INVALID, "too many units");
+    for (uint64_t u = 0; u < n_units; u++)
+        if (unit_start[u + 1] < unit_start[u]) return fail(ctx, MASHGPU_ERR_INVALID, "unit_start must be ascending");
+    if (unit_start[n_units] > stream_len) return fail(ctx, MASHGPU_ERR_INVALID, "unit_start exceeds stream_len");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t s = params->sketch_size;
+    // waves of whole units, each starting at the 32-position group that holds its first unit's first position
+    struct PWave { uint64_t u0, u1, g0, g1; };      // units [u0, u1), groups [g0, g1)
+    uint64_t wave_units_max = std::max<uint64_t>(64, (1ull << 28) / ((uint64_t)s * 8));
+    uint64_t wave_bytes = WAVE_BYTES;
+    if (const char *env = getenv("MASHGPU_WAVE_BYTES")) wave_bytes = std::max<uint64_t>(1024, strtoull(env, nullptr, 10));
+    if (const char *env = getenv("MASHGPU_WAVE_UNITS")) wave_units_max = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+    std::vector<PWave> waves;
+    for (uint64_t u = 0; u < n_units;) {
+        uint64_t v = u + 1;
+        while (v < n_units && v - u < wave_units_max && unit_start[v + 1] - unit_start[u] <= wave_bytes) v++;
+        waves.push_back(PWave{u, v, unit_start[u] / 32, (unit_start[v] + 31) / 32});
+        u = v;
+    }
+    uint64_t max_groups = 1, max_units = 1;
+    for (auto &w : waves) { max_groups = std::max(max_groups, w.g1 - w.g0); max_units = std::max(max_units, w.u1 - w.u0); }
+    const uint64_t max_tiles = (max_groups * 32 + SCAN_TILE - 1) / SCAN_TILE;
+    const uint64_t groups_alloc = max_tiles * (SCAN_TILE / 32) + 64;       // tile-padded + halo
+    const int nbuf = waves.size() > 1 ? 2 : 1;
+    uint64_t *d_codes[2] = {nullptr, nullptr}; uint32_t *d_inval[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; b++) {
+        d_codes[b] = ctx->sc_codes[b].get<uint64_t>(groups_alloc);
+        d_inval[b] = ctx->sc_inval[b].get<uint32_t>(groups_alloc);
+        if (!d_codes[b] || !d_inval[b]) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (packed stream of %llu groups)", (unsigned long long)groups_alloc);
+        if (!ctx->pack_copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pack_copied[b], cudaEventDisableTiming));
+    }
+    if (!ctx->pack_stream) MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pack_stream, cudaStreamNonBlocking));
+    uint64_t *d_hashes = ctx->sc_out_hashes.get<uint64_t>(max_units * s);
+    uint32_t *d_n = ctx->sc_out_n.get<uint32_t>(max_units);
+    uint32_t *d_counts = out_counts ? ctx->sc_out_counts.get<uint32_t>(max_units * s) : nullptr;
+    if (!d_hashes || !d_n || (out_counts && !d_counts)) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (outputs)");
+
+    std::vector<PackRun> wruns[2];
+    std::vector<uint64_t> wstart[2];
+    uint64_t run_cursor = 0;        // first run that may still reach into the current wave (runs ascending)
+    auto upload = [&](size_t wi) -> int {
+        const PWave &w = waves[wi];
+        const int b = (int)(wi % nbuf);
+        cudaStream_t cs = ctx->pack_stream;
+        const uint64_t p0 = w.g0 * 32, p1 = unit_start[w.u1];           // wave-local position = position - p0
+        MG_CUDA(ctx, cudaMemcpyAsync(d_codes[b], codes + w.g0, (w.g1 - w.g0) * 8, cudaMemcpyHostToDevice, cs));
+        MG_CUDA(ctx, cudaMemsetAsync(d_inval[b], 0, groups_alloc * 4, cs));
+        std::vector<PackRun> &R = wruns[b];
+        R.clear();
+        if (unit_start[w.u0] > p0) R.push_back(PackRun{0, unit_start[w.u0] - p0});       // the tail of the previous unit in the first group
+        while (run_cursor < n_runs && runs[2 * run_cursor] + runs[2 * run_cursor + 1] <= unit_start[w.u0]) run_cursor++;
+        for (uint64_t r = run_cursor; r < n_runs && runs[2 * r] < p1; r++) {
+            const uint64_t a = std::max(runs[2 * r], unit_start[w.u0]), e = std::min(runs[2 * r] + runs[2 * r + 1], p1);
+            if (e > a) R.push_back(PackRun{a - p0, e - a});
+        }
+        R.push_back(PackRun{p1 - p0, groups_alloc * 32 - (p1 - p0)});                   // everything past the wave's last unit
+        PackRun *d_runs = ctx->sc_runs[b].get<PackRun>(R.size());
+        if (!d_runs) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (invalid runs)");
+        MG_CUDA(ctx, cudaMemcpyAsync(d_runs, R.data(), R.size() * sizeof(PackRun), cudaMemcpyHostToDevice, cs));
+        const unsigned blocks = (unsigned)std::min<uint64_t>((R.size() * 32 + 255) / 256, 148 * 16);
+        apply_runs_kernel<<<std::max(1u, blocks), 256, 0, cs>>>(d_runs, R.size(), d_inval[b]);
+        ctx->kernel_launches++;
+        MG_CUDA(ctx, cudaGetLastError());
+        MG_CUDA(ctx, cudaEventRecord(ctx->pack_copied[b], cs));
+        wstart[b].resize(w.u1 - w.u0 + 1);
+        for (uint64_t u = w.u0; u <= w.u1; u++) wstart[b][u - w.u0] = unit_start[u] - p0;
+        return MASHGPU_OK;
+    };
+    MG_TRY(upload(0));
+    int rc = MASHGPU_OK;
+    for (size_t wi = 0; wi < waves.size() && rc == MASHGPU_OK; wi++) {
+        const PWave &w = waves[wi];
+        const int b = (int)(wi % nbuf);
+        if (wi + 1 < waves.size()) {
+            // buffer (wi+1)%2 was last read by the kernels of wave wi-1 (synchronised below); its run list by upload(wi-1)
+            if (wi >= 1) MG_CUDA(ctx, cudaEventSynchronize(ctx->pack_copied[(wi + 1) % nbuf]));
+            rc = upload(wi + 1);
+            if (rc != MASHGPU_OK) break;
+        }
+        MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pack_copied[b], 0));
+        const uint64_t nu = w.u1 - w.u0;
+        SketchStream S;
+        S.d_codes = d_codes[b]; S.d_inval = d_inval[b]; S.unit_start = wstart[b].data(); S.n_units = nu;
+        rc = sketch_stream_core(ctx, params, S, d_hashes, d_counts, d_n, ctx->stream, nullptr);
+        if (rc != MASHGPU_OK) break;
+        MG_CUDA(ctx, cudaMemcpyAsync(out_hashes + w.u0 * s, d_hashes, nu * s * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaMemcpyAsync(out_n + w.u0, d_n, nu * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_counts) MG_CUDA(ctx, cudaMemcpyAsync(out_counts + w.u0 * s, d_counts, nu * s * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaStreamSynchronize(ctx->pack_stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// `mash sketch -r -m -c`: the order-dependent stop at a target coverage, found exactly.
+//
+// MinHashHeap::tryInsert only looks at a k-mer when the heap is not full or its hash is below the heap's top (MinHashHeap.cpp:70-74),
+// and once the heap is full the top never rises.  So the exact top at a stream position P (the largest hash of the ordinary
+// bottom-s(-m) sketch of the prefix [0, P), computed by the normal kernels) bounds every k-mer after P that can still change the
+// heap.  Prefixes at record boundaries near total / 2^j give position bands with a threshold each (the first band, and any
+// band that starts before the heap is full, keeps everything); one more scan collects the k-mers at or below their band's
+// threshold as events {position, hash}; sorted by position they are replayed through the reference's heap logic by
+// reads_replay_kernel -- a faithful, sequential restatement of MinHashHeap::tryInsert (MinHashHeap.cpp:68-146) with the stop
+// test of Sketch.cpp:1258-1262 at every read boundary.  A few 10^5 events for a read set of any size.
+// ---------------------------------------------------------------------------------------------------------
+namespace mashgpu {
+
+struct ReplayMap { uint64_t *key; uint32_t *cnt; uint64_t mask; };     // open addressing, cnt == 0 marks a free slot
+
+__device__ __forceinline__ uint64_t rm_slot(const ReplayMap &m, uint64_t key) { return ((key * 0x9E3779B97F4A7C15ULL) >> 11) & m.mask; }
+__device__ uint32_t *rm_find(const ReplayMap &m, uint64_t key)
+{
+    uint64_t i = rm_slot(m, key);
+    while (m.cnt[i]) {
+        if (m.key[i] == key) return &m.cnt[i];
+        i = (i + 1) & m.mask;
+    }
+    return nullptr;
+}
+__device__ void rm_insert_new(const ReplayMap &m, uint64_t key, uint32_t cnt)
+{
+    uint64_t i = rm_slot(m, key);
+    while (m.cnt[i]) i = (i + 1) & m.mask;
+    m.key[i] = key; m.cnt[i] = cnt;
+}
+__device__ void rm_erase(const ReplayMap &m, uint64_t key)      // backward-shift deletion
+{
+    uint64_t i = rm_slot(m, key);
+    while (m.cnt[i] && m.key[i] != key) i = (i + 1) & m.mask;
+    if (!m.cnt[i]) return;
+    uint64_t j = i;
+    for (;;) {
+        j = (j + 1) & m.mask;
+        if (!m.cnt[j]) break;
+        const uint64_t k = rm_slot(m, m.key[j]);
+        const bool between = (i <= j) ? (i < k && k <= j) : (i < k || k <= j);
+        if (!between) { m.key[i] = m.key[j]; m.cnt[i] = m.cnt[j]; i = j; }
+    }
+    m.cnt[i] = 0;
+}
+__device__ void rh_push(uint64_t *heap, uint64_t &n, uint64_t v)     // binary max-heap
+{
+    uint64_t i = n++;
+    while (i > 0) {
+        const uint64_t p = (i - 1) / 2;
+        if (heap[p] >= v) break;
+        heap[i] = heap[p]; i = p;
+    }
+    heap[i] = v;
+}
+__device__ void rh_pop(uint64_t *heap, uint64_t &n)
+{
+    const uint64_t v = heap[--n];
+    uint64_t i = 0;
+    for (;;) {
+        uint64_t c = 2 * i + 1;
+        if (c >= n) break;
+        if (c + 1 < n && heap[c + 1] > heap[c]) c++;
+        if (heap[c] <= v) break;
+        heap[i] = heap[c]; i = c;
+    }
+    if (n) heap[i] = v;
+}
+
+// One thread replays the events.  acc = hashes + hashesQueue, pend = hashesPending + hashesQueuePending of MinHashHeap.
+__global__ void reads_replay_kernel(const uint64_t *ev_pos, const uint64_t *ev_hash, uint64_t n_ev, const uint64_t *rec_end, uint64_t n_rec,
+                                    uint32_t s, uint32_t m, double target_cov,
+                                    ReplayMap acc, uint64_t *acc_heap, ReplayMap pend, uint64_t *pend_heap,
+                                    uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_used)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    uint64_t size = 0, heap_n = 0, pend_n = 0, msum = 0;
+    uint64_t rec = 0, cur = ~0ull, used = n_rec;
+    bool stopped = false;
+    for (uint64_t e = 0; e <= n_ev && !stopped; e++) {
+        uint64_t r = ~0ull;
+        if (e < n_ev) {
+            const uint64_t pos = ev_pos[e];
+            while (rec < n_rec && rec_end[rec] <= pos) rec++;
+            r = rec;
+        }
+        if (cur != ~0ull && r != cur) {                     // record `cur` is complete: Sketch.cpp:1258-1262
+            if (size && (double)msum / (double)size >= target_cov) { used = cur + 1; stopped = true; break; }
+        }
+        if (e == n_ev) break;
+        cur = r;
+        const uint64_t hash = ev_hash[e];
+        if (!(size < s || hash < acc_heap[0])) continue;    // MinHashHeap.cpp:70-74
+        uint32_t *c = rm_find(acc, hash);
+        if (!c) {
+            uint32_t *pc = m > 1 ? rm_find(pend, hash) : nullptr;
+            const uint64_t pending = pc ? *pc : 0;
+            if (m == 1 || pending == m - 1) {               // :96-108
+                rm_insert_new(acc, hash, m);
+                rh_push(acc_heap, heap_n, hash);
+                size++; msum += m;
+                if (m > 1 && pc) rm_erase(pend, hash);
+            } else if (!pc) {                               // :110-118
+                rh_push(pend_heap, pend_n, hash);
+                rm_insert_new(pend, hash, 1);
+            } else (*pc)++;
+        } else { (*c)++; msum++; }                          // :120-124
+        if (size > s) {                                     // :126-144
+            const uint64_t top = acc_heap[0];
+            uint32_t *tc = rm_find(acc, top);
+            msum -= tc ? *tc : 0;
+            rm_erase(acc, top);
+            while (pend_n > 0 && top < pend_heap[0]) {
+                if (rm_find(pend, pend_heap[0])) rm_erase(pend, pend_heap[0]);
+                rh_pop(pend_heap, pend_n);
+            }
+            rh_pop(acc_heap, heap_n);
+            size--;
+        }
+    }
+    // toHashList: ascending hashes + counts (HashSet.cpp:78-118); popping the max-heap yields them in descending order
+    *out_n = (uint32_t)size;
+    *out_used = used;
+    for (uint64_t i = size; i-- > 0;) {
+        const uint64_t v = acc_heap[0];
+        out_hashes[i] = v;
+        if (out_counts) { const uint32_t *c = rm_find(acc, v); out_counts[i] = c ? *c : 0; }
+        rh_pop(acc_heap, heap_n);
+    }
+}
+
+}  // namespace mashgpu
+
+extern "C" int mashgpu_sketch_reads(mashgpu_ctx *ctx, const mashgpu_sketch_params *params,
+                                    uint64_t n_records, const char *const *seq, const uint64_t *len,
+                                    uint64_t *out_hashes, uint32_t *out_counts, uint32_t *out_n, uint64_t *out_records_used)
+{
+    if (!ctx) return MASHGPU_ERR_INVALID;
+    MG_TRY(validate_sketch_params(ctx, params));
+    if (!out_hashes || !out_n || !out_records_used) return fail(ctx, MASHGPU_ERR_INVALID, "NULL output");
+    if (n_records && (!seq || !len)) return fail(ctx, MASHGPU_ERR_INVALID, "seq/len is NULL");
+    if (!is_dna_alphabet(params)) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reads mode with a target coverage is only provided for the alphabet {A,C,G,T}");
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t s = params->sketch_size;
+    const uint64_t k = (uint64_t)params->kmer_size;
+    const uint32_t mc = std::max(1u, params->min_copies);
+    *out_n = 0; *out_records_used = 0;
+    // kept records -> one flat device stream (record, separator, record, ...) + the end offset of every kept record
+    std::vector<uint64_t> rec_end;
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < n_records; r++)
+        if (len[r] >= k) { total += len[r] + 1; rec_end.push_back(total - 1); }
+    const uint64_t n_rec = rec_end.size();
+    if (n_rec == 0) return MASHGPU_OK;
+    DevBuf<uint8_t> d_stream; DevBuf<uint64_t> d_hashes, d_rec_end; DevBuf<uint32_t> d_n, d_counts;
+    if (d_stream.alloc(((total + 15) / 16) * 16 + 64) != cudaSuccess || d_hashes.alloc(s) != cudaSuccess || d_n.alloc(1) != cudaSuccess ||
+        d_counts.alloc(s) != cudaSuccess || d_rec_end.alloc(n_rec) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (read set of %llu B)", (unsigned long long)total);
+    {
+        const size_t chunk = 64ull << 20;
+        PinnedBuf<uint8_t> stage[2];
+        if (stage[0].alloc(chunk) != cudaSuccess || stage[1].alloc(chunk) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory");
+        cudaEvent_t done[2];
+        MG_CUDA(ctx, cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+        MG_CUDA(ctx, cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+        uint64_t off = 0, fill = 0, base = 0;
+        int b = 0;
+        bool used_ev[2] = {false, false};
+        auto flush = [&]() -> cudaError_t {
+            if (!fill) return cudaSuccess;
+            cudaError_t e = cudaMemcpyAsync(d_stream.p + base, stage[b].p, fill, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(done[b], st);
+            used_ev[b] = true;
+            b ^= 1;
+            if (used_ev[b]) cudaEventSynchronize(done[b]);
+            base += fill; fill = 0;
+            return e;
+        };
+        cudaError_t e = cudaSuccess;
+        for (uint64_t r = 0; r < n_records && e == cudaSuccess; r++) {
+            if (len[r] < k) continue;
+            uint64_t done_r = 0;
+            while (done_r < len[r] + 1 && e == cudaSuccess) {            // the record's bytes, then its separator
+                const uint64_t room = chunk - fill, want = len[r] + 1 - done_r;
+                const uint64_t take = std::min(room, want);
+                const uint64_t from_seq = done_r < len[r] ? std::min(take, len[r] - done_r) : 0;
+                if (from_seq) memcpy(stage[b].p + fill, seq[r] + done_r, from_seq);
+                if (take > from_seq) stage[b].p[fill + from_seq] = 0;
+                fill += take; done_r += take; off += take;
+                if (fill == chunk) e = flush();
+            }
+        }
+        if (e == cudaSuccess) e = flush();
+        cudaStreamSynchronize(st);
+        cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+        if (e != cudaSuccess) return fail(ctx, MASHGPU_ERR_CUDA, "upload of the read set failed: %s", cudaGetErrorString(e));
+        (void)off;
+    }
+    MG_CUDA(ctx, cudaMemcpyAsync(d_rec_end.p, rec_end.data(), n_rec * 8, cudaMemcpyHostToDevice, st));
+    auto prefix_sketch = [&](uint64_t end, bool want_counts) -> int {        // ordinary sketch of the stream prefix [0, end)
+        uint64_t us[2] = {0, end};
+        SketchStream S;
+        S.d_stream = d_stream.p; S.unit_start = us; S.n_units = 1;
+        return sketch_stream_core(ctx, params, S, d_hashes.p, want_counts ? d_counts.p : nullptr, d_n.p, st, nullptr);
+    };
+    auto emit_result = [&](uint64_t used) -> int {
+        uint32_t n = 0;
+        MG_CUDA(ctx, cudaMemcpyAsync(&n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n) MG_CUDA(ctx, cudaMemcpyAsync(out_hashes, d_hashes.p, n * 8ull, cudaMemcpyDeviceToHost, st));
+        if (n && out_counts) MG_CUDA(ctx, cudaMemcpyAsync(out_counts, d_counts.p, n * 4ull, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(ctx, cudaStreamSynchronize(st));
+        *out_n = n; *out_records_used = used;
+        return MASHGPU_OK;
+    };
+    if (!(params->target_cov > 0)) {
+        MG_TRY(prefix_sketch(total, out_counts != nullptr));
+        return emit_result(n_rec);
+    }
+    // ---- position bands: record boundaries near total / 2^j, down to ~2^20 positions; threshold = exact top of the heap at the band's start
+    std::vector<uint64_t> band_start(1, 0), band_t(1, EMPTY_KEY);
+    {
+        std::vector<uint64_t> cuts;
+        for (uint64_t target = total / 2; target >= (1ull << 20); target /= 2) {
+            auto it = std::upper_bound(rec_end.begin(), rec_end.end(), target);     // first record that ends after the target
+            if (it == rec_end.begin()) break;
+            const uint64_t cut = *(it - 1) + 1;                                     // the position after that record's separator
+            if (cuts.empty() || cut < cuts.back()) cuts.push_back(cut);
+        }
+        std::reverse(cuts.begin(), cuts.end());
+        for (uint64_t cut : cuts) {
+            if (cut <= band_start.back()) continue;
+            MG_TRY(prefix_sketch(cut, false));
+            uint32_t n = 0; uint64_t top = EMPTY_KEY;
+            MG_CUDA(ctx, cudaMemcpyAsync(&n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+            MG_CUDA(ctx, cudaStreamSynchronize(st));
+            if (n == s) {
+                MG_CUDA(ctx, cudaMemcpyAsync(&top, d_hashes.p + (s - 1), 8, cudaMemcpyDeviceToHost, st));
+                MG_CUDA(ctx, cudaStreamSynchronize(st));
+            }
+            band_start.push_back(cut);
+            band_t.push_back(n == s ? top : EMPTY_KEY);                             // heap not full yet: its gate is open
+        }
+    }
+    // ---- events
+    const uint32_t n_bands = (uint32_t)band_start.size();
+    const uint64_t ev_cap = 1ull << 24;
+    DevBuf<uint64_t> d_bstart, d_bt, ev_pos, ev_hash, ev_pos2, ev_hash2, d_tmax; DevBuf<unsigned long long> ev_count; DevBuf<uint8_t> tmp;
+    const uint64_t ntiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+    if (d_bstart.alloc(n_bands + 1) != cudaSuccess || d_bt.alloc(n_bands) != cudaSuccess || ev_pos.alloc(ev_cap) != cudaSuccess || ev_hash.alloc(ev_cap) != cudaSuccess ||
+        ev_pos2.alloc(ev_cap) != cudaSuccess || ev_hash2.alloc(ev_cap) != cudaSuccess || ev_count.alloc(1) != cudaSuccess || d_tmax.alloc(ntiles) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (event buffers)");
+    band_start.push_back(total);
+    MG_CUDA(ctx, cudaMemcpyAsync(d_bstart.p, band_start.data(), (n_bands + 1) * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_bt.p, band_t.data(), n_bands * 8ull, cudaMemcpyHostToDevice, st));
+    MG_CUDA(ctx, cudaMemsetAsync(ev_count.p, 0, 8, st));
+    tile_tmax_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(d_bstart.p, n_bands, d_bt.p, total, params->kmer_size, 0, ntiles, d_tmax.p);
+    ScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.stream = d_stream.p; a.stream_len = total;
+    a.tile_begin = 0; a.tile_end = ntiles; a.tile_tmax = d_tmax.p;
+    a.seed = params->seed; a.use64 = params->use64; a.preserve_case = params->preserve_case;
+    fill_byte_lut(a, params);
+    a.mode = SCAN_EVENTS; a.only_unit = -1; a.min_copies = 1;
+    a.unit_start = d_bstart.p; a.n_units = n_bands; a.unit_t = d_bt.p;
+    a.ev_pos = ev_pos.p; a.ev_hash = ev_hash.p; a.ev_count = ev_count.p; a.ev_capacity = ev_cap;
+    MG_TRY(launch_scan(ctx, params, a, st));
+    unsigned long long n_ev = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&n_ev, ev_count.p, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->kernel_launches++;
+    if (n_ev > ev_cap)
+        return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "-c: %llu k-mers could pass the heap's gate (more than %llu): the heap fills too slowly on this read set "
+                                                  "(very low coverage or a high -m)", n_ev, (unsigned long long)ev_cap);
+    if (n_ev) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, ev_pos.p, ev_pos2.p, ev_hash.p, ev_hash2.p, (int)n_ev, 0, 64, st);
+        if (tmp.alloc(tb) != cudaSuccess) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (sort scratch)");
+        MG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, ev_pos.p, ev_pos2.p, ev_hash.p, ev_hash2.p, (int)n_ev, 0, 64, st));
+        ctx->kernel_launches += 8;
+    }
+    // ---- replay
+    uint64_t cap_a = 16, cap_p = 16;
+    while (cap_a < 4ull * (s + 2)) cap_a <<= 1;
+    while (cap_p < 2 * n_ev + 16) cap_p <<= 1;
+    DevBuf<uint64_t> a_key, a_heap, p_key, p_heap, d_used; DevBuf<uint32_t> a_cnt, p_cnt;
+    if (a_key.alloc(cap_a) != cudaSuccess || a_cnt.alloc(cap_a) != cudaSuccess || a_heap.alloc(s + 2) != cudaSuccess || p_key.alloc(cap_p) != cudaSuccess ||
+        p_cnt.alloc(cap_p) != cudaSuccess || p_heap.alloc(n_ev + 2) != cudaSuccess || d_used.alloc(1) != cudaSuccess)
+        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (replay tables)");
+    MG_CUDA(ctx, cudaMemsetAsync(a_cnt.p, 0, cap_a * 4, st));
+    MG_CUDA(ctx, cudaMemsetAsync(p_cnt.p, 0, cap_p * 4, st));
+    ReplayMap acc{a_key.p, a_cnt.p, cap_a - 1}, pend{p_key.p, p_cnt.p, cap_p - 1};
+    reads_replay_kernel<<<1, 32, 0, st>>>(ev_pos2.p, ev_hash2.p, n_ev, d_rec_end.p, n_rec, s, mc, params->target_cov, acc, a_heap.p, pend, p_heap.p,
+                                          d_hashes.p, d_counts.p, d_n.p, d_used.p);
+    ctx->kernel_launches++;
+    MG_CUDA(ctx, cudaGetLastError());
+    uint64_t used = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&used, d_used.p, 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(ctx, cudaStreamSynchronize(st));
+    return emit_result(used);
 }
 
 extern "C" int mashgpu_host_pack(const mashgpu_sketch_params *params, uint64_t n_records, const char *const *seq, const uint64_t *len,

@@ -12,7 +12,10 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <chrono>
+#include <condition_variable>
 #include <list>
+#include <mutex>
 #include <thread>
 
 #include "capnp_lite.hpp"
@@ -22,15 +25,20 @@ using namespace std;
 
 namespace mash {
 
+static double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool traceOn() { static const bool on = getenv("MASHGPU_TRACE") != 0; return on; }
+
 mashgpu_ctx *gpuContext()
 {
     static mashgpu_ctx *ctx = 0;
     if (!ctx) {
+        const double t0 = nowMs();
         const char *dev = getenv("MASH_GPU_DEVICE");
         if (mashgpu_create(dev ? atoi(dev) : 0, &ctx) != MASHGPU_OK) {
             cerr << "ERROR: " << mashgpu_last_error(0) << endl;
             exit(1);
         }
+        if (traceOn()) cerr << "[mash] GPU context: " << nowMs() - t0 << " ms" << endl;
     }
     return ctx;
 }
@@ -46,6 +54,7 @@ void fillGpuParams(mashgpu_sketch_params &p, const Sketch::Parameters &parameter
     p.preserve_case = parameters.preserveCase;
     for (int i = 0; i < 256; i++) p.alphabet[i] = parameters.alphabet[i];
     p.min_copies = parameters.reads ? parameters.minCov : 1;      // reference Sketch.cpp:1186: MinHashHeap(use64, s, reads ? minCov : 1, ...)
+    p.target_cov = parameters.reads ? parameters.targetCov : 0;   // reference Sketch.cpp:1258
 }
 
 bool hasSuffix(string const &whole, string const &suffix)   // reference Sketch.cpp:897-905
@@ -116,6 +125,15 @@ struct Sketch::Batch {
 
 static const uint64_t batchBytesMax = 1ull << 31;
 
+// A batch is handed to the GPU when it holds 2 GiB of sequence or so many units that their sketches (units x s hashes on the
+// host and on the device) reach 256 MiB -- `-i` on a multi-FASTA of millions of short records must not allocate by unit count
+template <typename B>
+static bool batchFull(const B &batch, const Sketch::Parameters &parameters)
+{
+    const uint64_t unitsMax = std::max<uint64_t>(1024, (1ull << 28) / (8 * std::max<uint64_t>(1, parameters.minHashesPerWindow)));
+    return batch.bytes > batchBytesMax || batch.refs.size() >= unitsMax;
+}
+
 void Sketch::flushBatch(Batch &batch)
 {
     const uint64_t units = batch.refs.size();
@@ -129,8 +147,19 @@ void Sketch::flushBatch(Batch &batch)
     vector<uint64_t> hashes(units * s), lengths(units);
     vector<uint32_t> n(units), counts(parameters.counts ? units * s : 0);
     mashgpu_ctx *ctx = gpuContext();
-    int rc = mashgpu_sketch_batch(ctx, &p, ptrs.size(), ptrs.data(), lens.data(), batch.unitOfRecord.data(), units,
+    const double tFlush = nowMs();
+    int rc;
+    uint64_t readsUsed = 0;
+    vector<uint32_t> readCounts;
+    if (batch.reads) {
+        // one sketch of all reads (sketchFile with parameters.reads, reference Sketch.cpp:1186-1282): -m and the -c stop inside
+        readCounts.resize(s);
+        rc = mashgpu_sketch_reads(ctx, &p, ptrs.size(), ptrs.data(), lens.data(), hashes.data(), readCounts.data(), n.data(), &readsUsed);
+        if (parameters.counts) std::copy(readCounts.begin(), readCounts.end(), counts.begin());
+    } else
+        rc = mashgpu_sketch_batch(ctx, &p, ptrs.size(), ptrs.data(), lens.data(), batch.unitOfRecord.data(), units,
                                   hashes.data(), parameters.counts ? counts.data() : 0, n.data(), lengths.data());
+    if (traceOn()) cerr << "[mash] sketch batch: " << units << " units, " << batch.bytes / 1e6 << " MB in " << nowMs() - tFlush << " ms" << endl;
     if (rc != MASHGPU_OK) {
         cerr << "ERROR: " << mashgpu_last_error(ctx) << endl;
         exit(1);
@@ -145,14 +174,15 @@ void Sketch::flushBatch(Batch &batch)
         if (batch.reads) {   // reference Sketch.cpp:1272-1282, 1319-1328; estimateSetSize = MinHashHeap.h:45
             double setSize = n[u] ? pow(2.0, parameters.use64 ? 64.0 : 32.0) * (double)n[u] / (double)hashes[u * s + n[u] - 1] : 0;
             reference.length = parameters.genomeSize != 0 ? parameters.genomeSize : (uint64_t)setSize;
-            double multiplicity = 0;
-            if (n[u] && parameters.counts) {
+            double multiplicity = 0;                         // estimateMultiplicity, MinHashHeap.h:44
+            if (n[u]) {
                 uint64_t sum = 0;
-                for (uint32_t i = 0; i < n[u]; i++) sum += counts[u * s + i];
+                for (uint32_t i = 0; i < n[u]; i++) sum += readCounts[i];
                 multiplicity = (double)sum / n[u];
             }
             cerr << "Estimated genome size: " << setSize << endl;
             cerr << "Estimated coverage:    " << multiplicity << endl;
+            if (parameters.targetCov > 0) cerr << "Reads used:            " << readsUsed << endl;      // reference Sketch.cpp:1324-1327
         } else {
             reference.length = lengths[u];
         }
@@ -163,9 +193,9 @@ void Sketch::flushBatch(Batch &batch)
 
 static void unsupportedReadsOptions(const Sketch::Parameters &parameters)
 {
-    if (parameters.memoryBound != 0 || parameters.targetCov > 0) {
-        cerr << "ERROR: the read filters -b and -c are not available in the GPU engine: both depend on the order in which reads arrive "
-                "(a Bloom filter with false positives, a stop at the first read boundary that reaches the target coverage); -m is (see DESIGN.md)." << endl;
+    if (parameters.memoryBound != 0) {
+        cerr << "ERROR: the Bloom filter -b is not available in the GPU engine: it is the reference's memory-saving approximation of -m "
+                "(unique k-mers may pass, copies are not counted beyond 2); use -m, which is exact here (see DESIGN.md)." << endl;
         exit(1);
     }
 }
@@ -189,6 +219,8 @@ static void parseUnit(const vector<string> &fileNames, const Sketch::Parameters 
         if (fp == 0) { cerr << "ERROR: could not open " << fileNames[f] << endl; exit(1); }
         fps.push_back(fp);
         readers.push_back(new mashhost::FastxReader(fp));
+        struct stat info;
+        if (fileNames[f] != "-" && stat(fileNames[f].c_str(), &info) == 0) readers.back()->setSizeHint((size_t)info.st_size);
     }
     auto it = readers.begin();
     while (readers.begin() != readers.end()) {
@@ -301,34 +333,57 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
             }
             if (parameters.concatenated && parameters.parallelism > 1 && files[i] != "-") {
                 // -p N: the reference parses N files at a time, one ThreadPool job each (Sketch.cpp:202-212), and takes the
-                // outputs in submission order.  Same here for the host-side parse of a run of sequence files: N threads
-                // parse one file each into private buffers, appended to the batch in input order.
+                // outputs in submission order.  Here N parser threads work through the whole run of sequence files that starts
+                // at files[i], a bounded number of files ahead of this thread, which appends the parsed files to the batch in
+                // input order and hands full batches to the GPU -- the parse of the next files overlaps the sketching.
                 size_t run = 1;
-                while (i + run < files.size() && run < (size_t)parameters.parallelism && !hasSuffix(files[i + run], suffixSketch) && files[i + run] != "-") run++;
-                struct Parsed { Reference ref; vector<string> seqs; vector<uint32_t> unitOfRecord; uint64_t bytes = 0; };
-                vector<Parsed> parsed(run);
-                vector<std::thread> workers;
-                for (size_t t = 0; t < run; t++) {
-                    if (t > 0) {
-                        if (verbosity > 0) cerr << "Sketching " << files[i + t] << "..." << endl;
-                        FILE *test = fopen(files[i + t].c_str(), "r");
-                        if (test == NULL) { cerr << "ERROR: could not open " << files[i + t] << " for reading." << endl; exit(1); }
-                        fclose(test);
-                    }
-                    workers.emplace_back([&, t]() {
-                        vector<string> file(1, files[i + t]);
-                        parseUnit(file, parameters, parsed[t].ref, parsed[t].seqs, parsed[t].unitOfRecord, 0, parsed[t].bytes);
-                    });
+                while (i + run < files.size() && !hasSuffix(files[i + run], suffixSketch) && files[i + run] != "-") run++;
+                for (size_t t = 1; t < run; t++) {
+                    FILE *test = fopen(files[i + t].c_str(), "r");
+                    if (test == NULL) { cerr << "ERROR: could not open " << files[i + t] << " for reading." << endl; exit(1); }
+                    fclose(test);
                 }
-                for (auto &w : workers) w.join();
+                struct Parsed { Reference ref; vector<string> seqs; vector<uint32_t> unitOfRecord; uint64_t bytes = 0; bool ready = false; };
+                vector<Parsed> parsed(run);
+                std::mutex mu;
+                std::condition_variable cvReady, cvRoom;
+                size_t nextFile = 0, consumed = 0;
+                const size_t window = 4 * (size_t)parameters.parallelism;      // files parsed ahead of the consumer
+                const size_t nWorkers = std::min<size_t>((size_t)parameters.parallelism, run);
+                vector<std::thread> workers;
+                for (size_t w = 0; w < nWorkers; w++)
+                    workers.emplace_back([&]() {
+                        for (;;) {
+                            size_t t;
+                            {
+                                std::unique_lock<std::mutex> lock(mu);
+                                if (nextFile >= run) return;
+                                t = nextFile++;
+                                cvRoom.wait(lock, [&] { return t < consumed + window; });
+                            }
+                            vector<string> file(1, files[i + t]);
+                            parseUnit(file, parameters, parsed[t].ref, parsed[t].seqs, parsed[t].unitOfRecord, 0, parsed[t].bytes);
+                            { std::lock_guard<std::mutex> lock(mu); parsed[t].ready = true; }
+                            cvReady.notify_all();
+                        }
+                    });
                 for (size_t t = 0; t < run; t++) {
+                    if (t > 0 && verbosity > 0) cerr << "Sketching " << files[i + t] << "..." << endl;
+                    {
+                        std::unique_lock<std::mutex> lock(mu);
+                        cvReady.wait(lock, [&] { return parsed[t].ready; });
+                    }
                     const uint32_t unit = (uint32_t)batch.refs.size();
                     batch.refs.push_back(std::move(parsed[t].ref));
                     for (auto &q : parsed[t].seqs) batch.seqs.push_back(std::move(q));
                     batch.unitOfRecord.insert(batch.unitOfRecord.end(), parsed[t].seqs.size(), unit);
                     batch.bytes += parsed[t].bytes;
-                    if (batch.bytes > batchBytesMax) flushBatch(batch);
+                    vector<string>().swap(parsed[t].seqs);
+                    { std::lock_guard<std::mutex> lock(mu); consumed = t + 1; }
+                    cvRoom.notify_all();
+                    if (batchFull(batch, parameters)) flushBatch(batch);
                 }
+                for (auto &w : workers) w.join();
                 i += run - 1;
             } else if (parameters.concatenated) {
                 vector<string> file(1, files[i]);
@@ -347,12 +402,12 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
                     batch.bytes += reader.seq.size();
                     batch.seqs.push_back(std::move(reader.seq));
                     batch.unitOfRecord.push_back((uint32_t)batch.refs.size() - 1);
-                    if (batch.bytes > batchBytesMax) flushBatch(batch);
+                    if (batchFull(batch, parameters)) flushBatch(batch);
                 }
                 gzclose(fp);
                 if (l != -1) { cerr << "\nERROR: reading " << files[i] << "." << endl; exit(1); }
             }
-            if (batch.bytes > batchBytesMax) flushBatch(batch);
+            if (batchFull(batch, parameters)) flushBatch(batch);
         }
     }
     flushBatch(batch);
@@ -455,6 +510,7 @@ void Sketch::loadCapnp(const char *file)   // reference Sketch.cpp:907-1067
             }
             if (!msg.pointerIsNull(r, 6)) {
                 auto counts = msg.getList(r, 6);
+                if (!counts.valid || counts.count < hashCount) throw std::runtime_error("counts list shorter than the hash list");
                 reference.counts.resize(hashCount);
                 for (uint64_t j = 0; j < hashCount; j++) reference.counts[j] = msg.elementU32(counts, (uint32_t)j);
             }

@@ -211,8 +211,18 @@ public:
         s.dataWords = l.dataWords; s.ptrCount = l.ptrCount; s.valid = true;
         return s;
     }
-    uint64_t elementU64(const ListRef &l, uint32_t i) const { uint64_t v; memcpy(&v, reinterpret_cast<const uint8_t *>(segs_[l.seg].w + l.off) + 8ull * i, 8); return v; }
-    uint32_t elementU32(const ListRef &l, uint32_t i) const { uint32_t v; memcpy(&v, reinterpret_cast<const uint8_t *>(segs_[l.seg].w + l.off) + 4ull * i, 4); return v; }
+    // primitive list elements; the element size code of the list must be the one asked for (5 = 64 bit, 4 = 32 bit) and the
+    // index inside the list (followList checked that `count` elements lie inside the segment) -- as libcapnp bounds-checks
+    uint64_t elementU64(const ListRef &l, uint32_t i) const
+    {
+        if (!l.valid || l.elemSize != 5 || i >= l.count) throw std::runtime_error("bad 64-bit list access");
+        uint64_t v; memcpy(&v, reinterpret_cast<const uint8_t *>(segs_[l.seg].w + l.off) + 8ull * i, 8); return v;
+    }
+    uint32_t elementU32(const ListRef &l, uint32_t i) const
+    {
+        if (!l.valid || l.elemSize != 4 || i >= l.count) throw std::runtime_error("bad 32-bit list access");
+        uint32_t v; memcpy(&v, reinterpret_cast<const uint8_t *>(segs_[l.seg].w + l.off) + 4ull * i, 4); return v;
+    }
 
 private:
     struct Seg { const word *w; uint32_t n; };
@@ -275,6 +285,8 @@ private:
             l.count = (uint32_t)(tag & 0xFFFFFFFFu) >> 2;
             l.dataWords = (uint16_t)(tag >> 32); l.ptrCount = (uint16_t)(tag >> 48);
             if ((uint64_t)l.off + 1 + count > segs_[tseg].n) throw std::runtime_error("list out of bounds");
+            // `count` of a composite list is its size in words: the tag's element count times the element size must fit in it
+            if ((uint64_t)l.count * ((uint64_t)l.dataWords + l.ptrCount) > count) throw std::runtime_error("composite list larger than its word count");
             l.off += 1;
         } else {
             static const int bits[8] = {0, 1, 8, 16, 32, 64, 64, 0};

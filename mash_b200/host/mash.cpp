@@ -4,6 +4,7 @@
 // defaults (Command.cpp:165-200), same stdout formats (iostream default precision), same ordering contracts.
 // It exists so that the reference's `make test` flow can be replayed against the GPU engine; help text, `paste`,
 // `bounds`, `taxscreen`, `within`, `find`, winner-take-all and translated screening are out of scope.
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -243,8 +244,12 @@ int runSketch(int argc, const char **argv)
     if (c.opt("id").active || c.opt("comment").active)
         if (files.size() > 1 && !parameters.reads) cerr << "WARNING: -I and -C will only apply to first sketch" << endl;
     Sketch sketch;
+    const bool trace = getenv("MASHGPU_TRACE") != 0;
+    const auto tStart = std::chrono::steady_clock::now();
+    auto elapsed = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count(); };
     if (parameters.reads) sketch.initFromReads(files, parameters);
-    else sketch.initFromFiles(files, parameters, 1);
+    else sketch.initFromFiles(files, parameters, trace ? 0 : 1);
+    if (trace) cerr << "[mash] parse + sketch of " << files.size() << " files: " << elapsed() << " ms" << endl;
     if (c.opt("id").active) sketch.setReferenceName(0, c.opt("id").argument);
     if (c.opt("comment").active) sketch.setReferenceComment(0, c.opt("comment").argument);
     KmerWarning w;
@@ -253,6 +258,7 @@ int runSketch(int argc, const char **argv)
     if (!hasSuffix(prefix, suffixSketch)) prefix += suffixSketch;
     cerr << "Writing to " << prefix << "..." << endl;
     sketch.writeToCapnp(prefix.c_str());
+    if (trace) cerr << "[mash] .msh written at " << elapsed() << " ms" << endl;
     if (w.warningCount > 0 && !parameters.reads) warnKmerSize(parameters, w.lengthMax, w.lengthMaxName, w.randomChance, w.kMin, w.warningCount);
     return 0;
 }

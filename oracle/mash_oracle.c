@@ -498,6 +498,35 @@ MO_API uint64_t mo_sketch_unit_m(const mo_params *p, uint64_t sketch_size, uint6
     return n;
 }
 
+/* sketchFile's record loop with `-m min_copies -c target_cov` (Sketch.cpp:1186-1282): after every kept record the loop stops when
+ * estimateMultiplicity() >= targetCov (:1258-1262, reads mode only).  *out_records_used = records fed to the heap (the "Reads
+ * used" line, :1324-1327). */
+MO_API uint64_t mo_sketch_unit_mc(const mo_params *p, uint64_t sketch_size, uint64_t min_copies, double target_cov,
+                                  uint64_t n_records, const char *const *seqs, const uint64_t *lens,
+                                  int reads, uint64_t genome_size,
+                                  uint64_t *out_hashes, uint32_t *out_counts, uint64_t *out_length, uint64_t *out_records_used)
+{
+    mo_heap_m *hm = mo_heap_m_new(p->use64, sketch_size, min_copies);
+    uint64_t length = 0, used = 0;
+    uint64_t *buf = NULL, cap = 0;
+    for (uint64_t r = 0; r < n_records; r++) {
+        if (lens[r] < (uint64_t)p->kmer_size) continue;
+        if (!reads) length += lens[r];
+        if (lens[r] > cap) { cap = lens[r]; buf = (uint64_t *)realloc(buf, sizeof(uint64_t) * cap); }
+        const uint64_t n = mo_all_hashes(seqs[r], lens[r], p, buf);
+        for (uint64_t i = 0; i < n; i++) mo_heap_m_try_insert(hm, buf[i]);
+        used++;
+        if (reads && target_cov > 0 && mo_heap_estimate_multiplicity(hm->acc) >= target_cov) break;     /* :1258-1262 */
+    }
+    free(buf);
+    if (reads) length = genome_size ? genome_size : (uint64_t)mo_heap_estimate_set_size(hm->acc);
+    const uint64_t n = mo_heap_to_list(hm->acc, out_hashes, out_counts);
+    if (out_length) *out_length = length;
+    if (out_records_used) *out_records_used = used;
+    mo_heap_m_free(hm);
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Binomial upper tail P[Bin(n, r) >= x]  ==  gsl_cdf_binomial_Q(x-1, r, n)
  * (call sites CommandDistance.cpp:444-446, CommandScreen.cpp:611-613).  GSL/Boost are not in

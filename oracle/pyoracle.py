@@ -159,6 +159,19 @@ class Oracle:
                                int(reads), genome_size, _ptr(out, u64p), _ptr(cnt, u32p), C.byref(length))
         return out[:n].copy(), (cnt[:n].copy() if counts else None), length.value
 
+    def sketch_unit_mc(self, records, p, s=1000, min_copies=1, target_cov=0.0, genome_size=0, counts=False):
+        """`mash sketch -r -m min_copies -c target_cov`: returns (hashes, counts|None, length, records_used)."""
+        L = self.lib
+        L.mo_sketch_unit_mc.restype = C.c_uint64
+        L.mo_sketch_unit_mc.argtypes = [C.POINTER(Params), C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_void_p, u64p,
+                                        C.c_int, C.c_uint64, u64p, u32p, u64p, u64p]
+        bufs, ptrs, lens = _seq_arrays(records)
+        out = np.empty(s, dtype=np.uint64); cnt = np.empty(s, dtype=np.uint32)
+        length = C.c_uint64(0); used = C.c_uint64(0)
+        n = L.mo_sketch_unit_mc(C.byref(p), s, min_copies, target_cov, len(bufs), C.cast(ptrs, C.c_void_p), _ptr(lens, u64p),
+                                1, genome_size, _ptr(out, u64p), _ptr(cnt, u32p), C.byref(length), C.byref(used))
+        return out[:n].copy(), (cnt[:n].copy() if counts else None), length.value, used.value
+
     # ---- dist --------------------------------------------------------------------------------
     def binomial_upper_tail(self, x, r, n):
         return self.lib.mo_binomial_upper_tail(x, r, n)
@@ -271,6 +284,18 @@ class RefLib:
         n = L.ref_sketch_unit_m(C.byref(p), s, min_copies, bloom_bytes, len(bufs), C.cast(ptrs, C.c_void_p), _ptr(lens, u64p),
                                 int(reads), genome_size, _ptr(out, u64p), _ptr(cnt, u32p), C.byref(length))
         return out[:n].copy(), (cnt[:n].copy() if counts else None), length.value
+
+    def sketch_unit_mc(self, records, p, s=1000, min_copies=1, target_cov=0.0, genome_size=0, counts=False):
+        L = self.lib
+        L.ref_sketch_unit_mc.restype = C.c_uint64
+        L.ref_sketch_unit_mc.argtypes = [C.POINTER(Params), C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_void_p, u64p,
+                                         C.c_int, C.c_uint64, u64p, u32p, u64p, u64p]
+        bufs, ptrs, lens = _seq_arrays(records)
+        out = np.empty(s, dtype=np.uint64); cnt = np.empty(s, dtype=np.uint32)
+        length = C.c_uint64(0); used = C.c_uint64(0)
+        n = L.ref_sketch_unit_mc(C.byref(p), s, min_copies, target_cov, len(bufs), C.cast(ptrs, C.c_void_p), _ptr(lens, u64p),
+                                 1, genome_size, _ptr(out, u64p), _ptr(cnt, u32p), C.byref(length), C.byref(used))
+        return out[:n].copy(), (cnt[:n].copy() if counts else None), length.value, used.value
 
     def sketch_many(self, seqs, p, s=1000, threads=1):
         bufs, ptrs, lens = _seq_arrays(seqs)

@@ -309,3 +309,25 @@ REF_API uint64_t ref_sketch_unit_m(const ref_params *p, uint64_t sketch_size, ui
     if (out_length) *out_length = length;
     return emit(heap, p->use64 != 0, out_hashes, out_counts);
 }
+
+// ... and with `-c target_cov`: the loop stops after the first kept record that brings estimateMultiplicity() to the target
+// (Sketch.cpp:1258-1262).  *out_records_used = kept records fed to the heap.
+REF_API uint64_t ref_sketch_unit_mc(const ref_params *p, uint64_t sketch_size, uint64_t min_copies, double target_cov,
+                                    uint64_t n_records, const char *const *seqs, const uint64_t *lens,
+                                    int reads, uint64_t genome_size,
+                                    uint64_t *out_hashes, uint32_t *out_counts, uint64_t *out_length, uint64_t *out_records_used)
+{
+    MinHashHeap heap(p->use64 != 0, sketch_size, min_copies, 0);
+    uint64_t length = 0, used = 0;
+    for (uint64_t r = 0; r < n_records; r++) {
+        if (lens[r] < (uint64_t)p->kmer_size) continue;
+        if (!reads) length += lens[r];
+        add_min_hashes(heap, seqs[r], lens[r], *p);
+        used++;
+        if (reads && target_cov > 0 && heap.estimateMultiplicity() >= target_cov) break;
+    }
+    if (reads) length = genome_size ? genome_size : (uint64_t)heap.estimateSetSize();
+    if (out_length) *out_length = length;
+    if (out_records_used) *out_records_used = used;
+    return emit(heap, p->use64 != 0, out_hashes, out_counts);
+}

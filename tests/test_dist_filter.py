@@ -26,3 +26,8 @@ def test_filter_has_no_false_negatives(cf_binary, mode, seed):
     # sequential inserts never duplicate a fingerprint; two ranks with the same (bucket, fingerprint) share a slot
     assert info["distinct"] - 8 <= info["slots_used"] <= info["distinct"]
     assert info["false_positive_rate"] < 2e-4
+    # reference-id side table (which of the tile's 32 references owns a fingerprint): never misses an owner; unrelated rows
+    # almost never share a slot, related rows mostly do (those hits are confirmed exactly by the probe kernel)
+    assert info["owner_missing"] == 0
+    if mode == 0:
+        assert info["owner_multi_fraction"] < 0.01

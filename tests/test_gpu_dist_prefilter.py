@@ -62,7 +62,8 @@ def test_prefilter_equals_merge_and_oracle(gpu, oracle, s, k):
     check_against_oracle(res, want)
     assert st["active"] and st["combos_probed"] == 77 * 5          # ceil(150 / 32) reference tiles
     if s >= 200:
-        assert 0 < st["combos_flagged"] < st["combos_probed"]      # both the closed form and the merge were exercised
+        assert st["combos_flagged"] < st["combos_probed"]          # the closed form was exercised ...
+        assert st["combos_flagged"] + st["pairs_from_lists"] > 0   # ... and so was a merge (whole combinations and / or listed pairs)
 
 
 def test_prefilter_self_ranges_and_thresholds(gpu, oracle):
@@ -153,3 +154,55 @@ def test_triangle_needs_self_comparison(gpu):
             job.set_triangle(True)
     finally:
         job.close()
+
+
+@pytest.mark.parametrize("pair_max", ["4", "0", "31"])
+def test_scattered_relatives_take_the_pair_list(gpu, oracle, monkeypatch, pair_max):
+    # Related sketches scattered over the collection (one or two per reference tile): the probe kernel names the candidate
+    # references of each (query, tile) combination and only those pairs are merged, one warp per pair (dist_pair_kernel).
+    # MASHGPU_DIST_PAIR_MAX=0 switches the path off (whole combinations merged), 31 sends everything through it.
+    monkeypatch.setenv("MASHGPU_DIST_PAIR_MAX", pair_max)
+    s, k = 1000, 21
+    n = 700
+    rng = np.random.Generator(np.random.PCG64(2024))
+    H, N, L = mixed_sketches(n, s, seed=91, n_related=0)
+    Hf, Nf, _ = synth_sketches(44, s, 92, n_families=4, ragged=True)       # 4 families of 11, two ragged members, placed far apart
+    pos = rng.choice(n, 44, replace=False)
+    H[pos], N[pos] = Hf, Nf
+    res, st = run_modes(gpu, H, N, L, s=s, k=k)
+    want = oracle.compare_all(H, N, L, H, N, L, s, k, 4.0 ** k)
+    check_against_oracle(res, want)
+    if pair_max == "0":
+        assert st["pairs_from_lists"] == 0 and st["combos_flagged"] > 0
+    else:
+        assert st["pairs_from_lists"] >= 44 * 10               # every related pair went through the list (plus a few false candidates)
+    # filtered list output and the triangle enumeration through the same path
+    job = gpu.dist_open(H, N, L, sketch_size=s, k=k, kmer_space=4.0 ** k, max_distance=0.3, max_pvalue=1.0)
+    try:
+        job.set_prefilter(1)
+        job.set_triangle(True)
+        n_pass, lst = job.run_list(0, n, n * n)
+    finally:
+        job.close()
+    wf = oracle.compare_all(H, N, L, H, N, L, s, k, 4.0 ** k, max_distance=0.3, max_pvalue=1.0)
+    lower = np.arange(n)[None, :] < np.arange(n)[:, None]
+    flat = np.flatnonzero((wf["pass"].astype(bool) & lower).ravel())
+    assert n_pass == flat.size and np.array_equal(lst["index"], flat.astype(np.uint64))
+    assert np.array_equal(lst["numer"], wf["numer"].ravel()[flat])
+
+
+@pytest.mark.parametrize("s", [1036, 2500, 10000])
+def test_large_sketch_sizes_use_the_warp_per_pair_merge(gpu, oracle, s):
+    # `mash sketch -s 10000` is a documented setting: sketches whose 32-reference tile does not fit shared memory are compared one
+    # warp per pair (zooming union count) -- same results as the reference's sequential merge, ragged and empty rows included
+    H, N, L = synth_sketches(48, s, seed=5 + s, n_families=3, ragged=True)
+    Hq, Nq, Lq = synth_sketches(21, s, seed=77 + s, n_families=3, ragged=True)
+    Hq[:6] = H[:6]; Nq[:6] = N[:6]
+    N[7] = 0; Nq[3] = 1
+    ks = 4.0 ** 21
+    res = gpu.dist(H, N, L, Hq, Nq, Lq, sketch_size=s, k=21, kmer_space=ks)
+    want = oracle.compare_all(H, N, L, Hq, Nq, Lq, s, 21, ks)
+    check_against_oracle(res, want)
+    # a smaller sketch_size than the lists hold: only the first s' elements of a row can matter
+    res2 = gpu.dist(H, N, L, Hq, Nq, Lq, sketch_size=s - 500, k=21, kmer_space=ks)
+    check_against_oracle(res2, oracle.compare_all(H, N, L, Hq, Nq, Lq, s - 500, 21, ks))

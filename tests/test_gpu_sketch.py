@@ -325,3 +325,51 @@ def test_min_copies_filter_matches_reference_heap(gpu, oracle, m, s, k, cov):
         assert_sketch_equal(out, u, oh)
         assert np.array_equal(out[3][u, :out[1][u]], oc)
     assert any(not np.array_equal(out[0][u, :out[1][u]], plain[0][u, :plain[1][u]]) for u in range(3))     # the filter really bites
+
+
+@pytest.mark.parametrize("wave_bytes", [None, "300000"])
+def test_caller_packed_stream_equals_ascii_batch(gpu, oracle, monkeypatch, wave_bytes):
+    # mashgpu_sketch_batch_packed: the caller keeps its collection 2-bit packed (+ invalid runs, the format of mashgpu_host_pack)
+    # and sketches units of that stream; many waves (the 32-position alignment of a wave's first unit is the delicate part)
+    if wave_bytes:
+        monkeypatch.setenv("MASHGPU_WAVE_BYTES", wave_bytes)
+        monkeypatch.setenv("MASHGPU_WAVE_UNITS", "2")
+    p = gpu.params(k=21, s=300)
+    po = oracle.params(k=21)
+    recs, uor = [], []
+    for u in range(9):
+        for r in range(1 + u % 3):
+            recs.append(bytes(synth_genome(2000 + 10 * u + r, 60_000 + 7919 * u + 13 * r, n_runs=u % 2, lower_frac=0.02)))
+            uor.append(u)
+    recs.append(b"ACGTNACGT"); uor.append(9)                       # a unit without any k-mer
+    codes, runs, starts = gpu.host_pack(recs, p, threads=3)
+    unit_first = [uor.index(u) for u in range(10)]
+    unit_start = np.array([starts[i] for i in unit_first] + [starts[-1]], np.uint64)
+    h, n, c = gpu.sketch_packed(codes, int(starts[-1]), runs, unit_start, p, counts=True)
+    ref = gpu.sketch(recs, p, unit_of_record=uor, n_units=10, counts=True)
+    assert np.array_equal(n, ref[1]) and np.array_equal(h, ref[0]) and np.array_equal(c, ref[3])
+    for u in (0, 4, 8):
+        oh, _, _ = oracle.sketch_unit([r for r, x in zip(recs, uor) if x == u], po, s=300)
+        assert np.array_equal(h[u, :n[u]], oh)
+    assert n[9] == 0
+
+
+@pytest.mark.parametrize("m,c,s,n_reads,glen", [(1, 3.0, 300, 60_000, 300_000), (2, 4.0, 200, 50_000, 200_000), (1, 1e9, 300, 30_000, 400_000),
+                                               (3, 2.5, 100, 45_000, 150_000), (1, 1.5, 1000, 50_000, 1_000_000), (1, 0.0, 300, 5_000, 100_000)])
+def test_reads_mode_target_coverage_stop_is_exact(gpu, oracle, m, c, s, n_reads, glen):
+    # `mash sketch -r -m m -c c`: the sketch is the heap as it stood after the first read that brought the average multiplicity
+    # to c (Sketch.cpp:1258-1262) -- order dependent.  The engine finds that read exactly (position bands bounded by exact
+    # prefix sketches, events replayed through the heap logic on the device); oracle pinned to the reference's heap object code
+    # in tests/test_oracle_vs_ref.py.  Several bands (streams above 2^21 positions), early and late stops, no stop at all.
+    p = gpu.params(k=21, s=s, min_copies=m, target_cov=c)
+    po = oracle.params(k=21)
+    reads = _reads(4000 + m + s, glen, n_reads, err=0.004)
+    reads[7] = b"ACGT"                                       # shorter than k: skipped, not counted as used
+    h, cnt, used = gpu.sketch_reads(reads, p, counts=True)
+    oh, oc, _, ou = oracle.sketch_unit_mc(reads, po, s=s, min_copies=m, target_cov=c, counts=True)
+    assert used == ou
+    assert np.array_equal(h, oh) and np.array_equal(cnt, oc)
+    if 0 < c < 100:
+        assert 0 < used < n_reads - 1                        # the stop really happened inside the stream
+    else:
+        assert used == n_reads - 1

@@ -100,3 +100,35 @@ def test_sketch_without_gpu_fails_loudly(mash, tmp_path):
     fa.write_text(">s1 comment\nACGTACGTACGTACGTACGTACGTACGT\n")
     p = subprocess.run([mash, "sketch", str(fa)], capture_output=True, text=True)
     assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
+def test_malformed_msh_is_rejected_not_read_out_of_bounds(mash, tmp_path):
+    # users download .msh files: list shapes are validated the way libcapnp bounds-checks (element size code of hash / count
+    # lists, list length vs the hashes read, composite list word count) -- a damaged file ends in an error message, not in
+    # reads past the mapping
+    import struct
+    good = tmp_path / "g.msh"
+    run(mash, "import-json", os.path.join(GOLDEN, "ref_genomes.json"), str(good))
+    data = bytearray(good.read_bytes())
+    nseg = struct.unpack_from("<I", data, 0)[0] + 1
+    table = (4 + 4 * nseg + 7) & ~7
+    seg_sizes = [struct.unpack_from("<I", data, 4 + 4 * i)[0] for i in range(nseg)]
+    # the hash lists of genomes.msh live in segments 1 and 2 behind far pointers: the first word of segment 1 is the landing pad,
+    # a list pointer to 1000 64-bit elements
+    off = table + 8 * seg_sizes[0]
+    w = struct.unpack_from("<Q", data, off)[0]
+    assert (w & 3) == 1 and ((w >> 32) & 7) == 5 and (w >> 35) == 1000
+    variants = {"declared_32_bit": (w & ~(7 << 32)) | (4 << 32),                       # hashes64 declared as a 32-bit list
+                "count_beyond_segment": (w & ((1 << 35) - 1)) | ((2 ** 28) << 35),      # more elements than the segment holds
+                "short_list": (w & ((1 << 35) - 1)) | (10 << 35)}                        # fewer hashes than sketchSize: legal, just a short sketch
+    for name, word in variants.items():
+        d = bytearray(data)
+        struct.pack_into("<Q", d, off, word)
+        f = tmp_path / f"{name}.msh"
+        f.write_bytes(bytes(d))
+        p = subprocess.run([mash, "info", "-d", str(f)], capture_output=True)
+        err = p.stderr.decode(errors="replace")
+        if name == "short_list":
+            assert p.returncode == 0, err
+        else:
+            assert p.returncode == 1 and "not a valid sketch file" in err, (name, p.returncode, err)

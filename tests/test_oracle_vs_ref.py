@@ -141,3 +141,18 @@ def test_min_copies_heap_oracle_equals_reference_object_code(oracle, reflib, m, 
     assert np.array_equal(oh, want)
     assert np.all(oc[:-1] == c[np.searchsorted(u, oh[:-1])]) if oh.size else True
     assert oh.size == 0 or m <= oc[-1] <= c[np.searchsorted(u, oh[-1])]
+
+
+@pytest.mark.parametrize("m,c,s,cov", [(1, 3.0, 200, 10), (2, 4.0, 100, 12), (1, 50.0, 200, 4), (3, 3.5, 300, 20), (2, 2.0, 50, 6)])
+def test_target_coverage_stop_oracle_equals_reference_object_code(oracle, reflib, m, c, s, cov):
+    """`-c`: the record loop stops after the first read that brings the heap's average multiplicity to the target (Sketch.cpp:1258-1262)."""
+    p = oracle.params(k=21)
+    reads = _read_set(500 + m + s, 20_000, 200 * cov, err=0.005)
+    oh, oc, ol, ou = oracle.sketch_unit_mc(reads, p, s=s, min_copies=m, target_cov=c, counts=True)
+    rh, rc, rl, ru = reflib.sketch_unit_mc(reads, p, s=s, min_copies=m, target_cov=c, counts=True)
+    assert ou == ru and np.array_equal(oh, rh) and np.array_equal(oc, rc) and ol == rl
+    if c < 20:
+        assert 0 < ou < len(reads)                     # stopped early
+        assert oc.sum() / oc.size >= c
+    else:
+        assert ou == len(reads)

@@ -41,6 +41,17 @@ int main(int argc, char **argv)
         form_mismatch += o1 != 4u * cf_bucket(h) || o2 != 4u * cf_alt(cf_bucket(h), fp) || f2 != fp * 0x00010001u ||
                          (fp & 0x4000u) != 0 || (fp & 1u) == 0 || fp > 0xFFFFu;
     }
+    // reference-id side table: after marking, every (rank, reference) must be named by its slot or flagged as shared
+    std::vector<uint8_t> ids(2 * CF_BUCKETS, (uint8_t)CF_ID_NONE);
+    const size_t per_ref = (stream.size() + 31) / 32;
+    for (size_t i = 0; i < stream.size(); i++) cf_mark_ids(tab.data(), ids.data(), stream[i], (uint32_t)(i / per_ref));      // one reference after the other
+    int owner_missing = 0; uint64_t owner_multi = 0;
+    for (size_t i = 0; i < stream.size(); i++) {
+        bool multi = false;
+        const uint32_t bits = cf_owner_bits(tab.data(), ids.data(), stream[i], &multi);
+        if (!multi && !((bits >> (i / per_ref)) & 1u)) owner_missing++;
+        owner_multi += multi;
+    }
     uint64_t used = 0;
     for (uint32_t w : tab) used += ((w & 0xFFFF) != 0) + ((w >> 16) != 0);
     uint64_t fp = 0, probes = 0;
@@ -50,7 +61,9 @@ int main(int argc, char **argv)
         probes++;
         fp += cf_lookup(tab.data(), c);
     }
-    printf("{\"distinct\": %zu, \"slots_used\": %llu, \"insert_failures\": %d, \"missing\": %d, \"form_mismatch\": %d, \"false_positive_rate\": %.3g}\n",
-           members.size(), (unsigned long long)used, failed, missing, form_mismatch, probes ? (double)fp / probes : 0.0);
-    return (missing == 0 && failed == 0 && form_mismatch == 0) ? 0 : 1;
+    printf("{\"distinct\": %zu, \"slots_used\": %llu, \"insert_failures\": %d, \"missing\": %d, \"form_mismatch\": %d, \"false_positive_rate\": %.3g, "
+           "\"owner_missing\": %d, \"owner_multi_fraction\": %.4g}\n",
+           members.size(), (unsigned long long)used, failed, missing, form_mismatch, probes ? (double)fp / probes : 0.0,
+           owner_missing, (double)owner_multi / stream.size());
+    return (missing == 0 && failed == 0 && form_mismatch == 0 && owner_missing == 0) ? 0 : 1;
 }
