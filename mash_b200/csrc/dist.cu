@@ -334,9 +334,14 @@ constexpr size_t PROBE_SMEM = CF_BUCKETS * sizeof(uint32_t) + 2 * CF_BUCKETS;   
 // Returns the updated candidate mask; stops confirming once more than pair_max references are in it (the combination is merged
 // as a whole then).
 template <bool FULL>
-__device__ __noinline__ uint32_t probe_resolve(const uint32_t *s_tab, const uint8_t *s_ids, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t base,
-                                               uint32_t nB, int lane, const uint32_t *rowA, uint32_t nA_lim, uint32_t mask, int pair_max, int &confirms)
+__device__ __noinline__ uint2 probe_resolve(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t base, uint32_t nB, const uint32_t *rowA,
+                                            uint32_t nA_lim, uint32_t mask, int pair_max, int confirms)
 {
+    // (the filter's address, the lane and the running state travel in as few registers as possible: what is live across this call
+    // is live across the caller's hot loop, and at 1024 threads per CTA the loop has 64 registers)
+    extern __shared__ uint32_t s_tab[];
+    const uint8_t *s_ids = reinterpret_cast<const uint8_t *>(s_tab + CF_BUCKETS);
+    const int lane = threadIdx.x & 31;
     const uint32_t b[PROBE_DEPTH] = {b0, b1, b2, b3};      // by value: an array reference would pin the caller's ranks in local memory
 #pragma unroll
     for (int c = 0; c < PROBE_DEPTH; c++) {
@@ -351,7 +356,7 @@ __device__ __noinline__ uint32_t probe_resolve(const uint32_t *s_tab, const uint
         while (m && __popc(mask) <= pair_max) {
             // A confirmation costs ~10 dependent global loads.  A query that keeps hitting shared slots is related to several
             // references of the tile (same family): after a few confirmations merge the whole combination instead.
-            if (pair_max > 0 && ++confirms > PROBE_MAX_CONFIRMS) return 0xFFFFFFFFu;
+            if (pair_max > 0 && ++confirms > PROBE_MAX_CONFIRMS) return make_uint2(0xFFFFFFFFu, (uint32_t)confirms);
             const int src = __ffs(m) - 1;
             m &= m - 1;
             const uint32_t bb = __shfl_sync(0xFFFFFFFFu, b[c], src);
@@ -363,7 +368,7 @@ __device__ __noinline__ uint32_t probe_resolve(const uint32_t *s_tab, const uint
             mask |= __ballot_sync(0xFFFFFFFFu, lo < nA_lim && rowA[lo] == bb);
         }
     }
-    return mask;
+    return make_uint2(mask, (uint32_t)confirms);
 }
 
 // One group of PROBE_DEPTH x 32 ranks of a query against the filter.  FULL: the whole group lies inside the query's list.
@@ -458,8 +463,9 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
 #pragma unroll
             for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = __ldg(pB + 32 * c);
             if (probe_group<true, LAZY>(tab_s, cur, base, nB, lane)) {
-                mask = probe_resolve<true>(s_tab, s_ids, cur[0], cur[1], cur[2], cur[3], base, nB, lane, rowA, nA_lim, mask, pair_max, confirms);
-                dense = __popc(mask) > pair_max;
+                const uint2 st = probe_resolve<true>(cur[0], cur[1], cur[2], cur[3], base, nB, rowA, nA_lim, mask, a.pair_max, confirms);
+                mask = st.x; confirms = (int)st.y;
+                if (__popc(mask) > a.pair_max) { dense = true; break; }
             }
             base += GROUP; pB += GROUP;
         }
@@ -467,7 +473,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
 #pragma unroll
             for (int c = 0; c < PROBE_DEPTH; c++) cur[c] = (base + 32 * c + lane < nB) ? __ldg(pB + 32 * c) : RANK_PAD;
             if (probe_group<false, LAZY>(tab_s, cur, base, nB, lane)) {
-                mask = probe_resolve<false>(s_tab, s_ids, cur[0], cur[1], cur[2], cur[3], base, nB, lane, rowA, nA_lim, mask, pair_max, confirms);
+                const uint2 st = probe_resolve<false>(cur[0], cur[1], cur[2], cur[3], base, nB, rowA, nA_lim, mask, pair_max, confirms);
+                mask = st.x;
                 dense = __popc(mask) > pair_max;
             }
         }

@@ -144,3 +144,22 @@ def test_screen_winner_take_all_cli(work, oracle, golden):
     for line, i in zip(got, rows):
         assert line[:4] == [fmt_g(want["identity"][i]), f"{want['shared'][i]}/1000", str(want["median"][i]), fmt_g(want["pvalue"][i])]
         assert line[4] == golden.golden_sketch(i)[2]
+
+
+@pytest.mark.parametrize("m,c", [(2, 0.0), (1, 1.1), (2, 2.03), (1, 1.08)])
+def test_reads_mode_filters_through_the_cli(work, oracle, golden, m, c):
+    # `mash sketch -r -m m [-c c] reads1.fastq reads2.fastq`: the shim reads the files round robin (Sketch.cpp:1202-1270) and hands the
+    # records to mashgpu_sketch_reads; hashes, counts and the "Reads used" line against the oracle (pinned to the reference's heap)
+    import json
+    args = [MASH, "sketch", "-r", "-m", str(m)] + (["-c", str(c)] if c > 0 else []) + ["-o", f"filt_{m}_{c}.msh", "reads1.fastq", "reads2.fastq"]
+    pr = subprocess.run(args, cwd=work, check=True, capture_output=True, text=True)
+    reads = golden.reads_round_robin()
+    po = oracle.params(k=21)
+    # Command::Option keeps numbers as float (reference Command.h:51): -c 1.1 is float(1.1) widened to double
+    oh, oc, ol, ou = oracle.sketch_unit_mc(reads, po, s=1000, min_copies=m, target_cov=float(np.float32(c)), counts=True)
+    dump = json.loads(out(work, "info", "-d", f"filt_{m}_{c}.msh"))
+    sk = dump["sketches"][0]
+    assert sk["hashes"] == [int(x) for x in oh] and sk["counts"] == [int(x) for x in oc] and sk["length"] == ol
+    if c > 0:
+        assert f"Reads used:            {ou}" in pr.stderr
+        assert 0 < ou < len([r for r in reads if len(r) >= 21])

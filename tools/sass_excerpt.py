@@ -3,9 +3,8 @@
 
     python tools/sass_excerpt.py mash_b200/libmashgpu.so profiles/r02_sass
 
-writes, per kernel, `<name>.sass` (the full function as cuobjdump prints it, addresses and encodings stripped) and appends to
-`summary.md` its opcode histogram, the share of the pipes the kernel is bound by, and the innermost loop (the longest backward
-branch-free run that ends in a backward BRA is printed as the hot loop candidate)."""
+writes, per kernel, `<name>.sass` (its innermost loops as cuobjdump prints them, encodings stripped, plus every TMA / mbarrier
+instruction) and `summary.md` with the opcode histogram, the static share of the pipes and the opcode mix of each innermost loop."""
 import collections
 import os
 import re
@@ -18,7 +17,7 @@ KERNELS = {
     "dist_kernel": "_ZN7mashgpu11dist_kernelILb0EEEvNS_8DistArgsE",
     "dist_kernel_bulk_copy_variant": "_ZN7mashgpu11dist_kernelILb1EEEvNS_8DistArgsE",
     "dist_probe_kernel": "_ZN7mashgpu17dist_probe_kernelILb0EEEvNS_8DistArgsE",
-    "dist_pair_kernel": "_ZN7mashgpu16dist_pair_kernelENS_8DistArgsEj",
+    "dist_pair_kernel": "_ZN7mashgpu16dist_pair_kernelENS_8DistArgs",
 }
 PIPES = {
     "ALU (SHF/LOP3/IADD3/PRMT/ISETP/SEL/...)": ("SHF", "LOP3", "IADD3", "IADD", "PRMT", "ISETP", "SEL", "LEA", "MOV", "PLOP3", "HSETP2", "VOTE", "POPC", "FLO", "BREV", "IABS", "IMNMX", "VIMNMX", "LOP"),
@@ -39,7 +38,7 @@ def main():
     idx = sorted(starts)
     summary = ["# SASS of the hot kernels (sm_100a), from `cuobjdump -sass mash_b200/libmashgpu.so` via tools/sass_excerpt.py", ""]
     for name, mangled in KERNELS.items():
-        at = [i for i in idx if starts[i] == mangled]
+        at = [i for i in idx if starts[i].startswith(mangled)]
         if not at:
             summary.append(f"## {name}: not found in {so}\n")
             continue
@@ -50,10 +49,7 @@ def main():
             m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
             if m:
                 ins.append((int(m.group(1), 16), m.group(2).strip()))
-        with open(os.path.join(out, name + ".sass"), "w") as f:
-            f.write(f"// {mangled}\n")
-            for addr, t in ins:
-                f.write(f"/*{addr:05x}*/  {t}\n")
+        excerpt = [f"// {mangled}: {len(ins)} instructions; the innermost loops, longest first (full listing: cuobjdump -sass)"]
         ops = collections.Counter()
         for _, t in ins:
             t2 = re.sub(r"^@!?U?P\d+\s+", "", t)
@@ -91,6 +87,16 @@ def main():
             lo = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for _, t in body)
             summary.append("")
             summary.append(f"innermost loop, {len(body)} instructions at {body[0][0]:#x}..{body[-1][0]:#x}: " + ", ".join(f"{o} {c}" for o, c in lo.most_common(12)))
+        for body in loops[:4]:
+            excerpt.append(f"\n// ---- loop {body[0][0]:#x}..{body[-1][0]:#x} ({len(body)} instructions)")
+            excerpt += [f"/*{addr:05x}*/  {t}" for addr, t in body[:400]]
+            if len(body) > 400:
+                excerpt.append(f"// ... {len(body) - 400} more")
+        tma = [f"/*{addr:05x}*/  {t}" for addr, t in ins if re.search(r"UBLKCP|UTMALDG|SYNCS|UTMASTG", t)]
+        if tma:
+            excerpt.append("\n// ---- TMA / mbarrier instructions in this kernel")
+            excerpt += tma[:40]
+        open(os.path.join(out, name + ".sass"), "w").write("\n".join(excerpt) + "\n")
         summary.append("")
     open(os.path.join(out, "summary.md"), "w").write("\n".join(summary) + "\n")
     print("\n".join(summary))
