@@ -69,6 +69,10 @@ struct mashgpu_ctx {
     void *flags_pinned = nullptr;                   // per-unit status flags of the sketch pass in flight (sketch.cu)
     size_t flags_pinned_n = 0;
     cudaStream_t pack_stream = nullptr;             // packed uploads (next to the ASCII copies on copy_stream)
+    // screen: chunk staging buffers and the finish() outputs outlive a job (cudaMalloc of a few hundred MB inside a timed pass cost
+    // 1-50 ms depending on the box); scr_stage_owner = the job using the staging pair, others allocate their own
+    mashgpu::Scratch scr_stage[2], scr_out;
+    const void *scr_stage_owner = nullptr;
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
     cudaEvent_t wave_copied[2] = {nullptr, nullptr};

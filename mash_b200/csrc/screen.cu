@@ -399,14 +399,23 @@ int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)
     const int b = job->next_buf;
     job->next_buf ^= 1;
     const uint64_t padded = ((len + 15) / 16) * 16;
-    if (job->stage[b].n < padded && job->stage[b].alloc(padded + (padded >> 2)) != cudaSuccess)
-        return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+    uint8_t *stage;
+    if (!ctx->scr_stage_owner || ctx->scr_stage_owner == job) {     // the context's staging pair (kept across jobs)
+        ctx->scr_stage_owner = job;
+        // (buffer b was last read by the chunk before the one in flight, which has been collected: it may move)
+        stage = ctx->scr_stage[b].get<uint8_t>(ctx->scr_stage[b].bytes < padded ? padded + (padded >> 2) : padded);
+        if (!stage) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+    } else {
+        if (job->stage[b].n < padded && job->stage[b].alloc(padded + (padded >> 2)) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+        stage = job->stage[b].p;
+    }
     if (!job->copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&job->copied[b], cudaEventDisableTiming));
-    MG_CUDA(ctx, cudaMemcpyAsync(job->stage[b].p, chunk, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MG_CUDA(ctx, cudaMemcpyAsync(stage, chunk, len, cudaMemcpyHostToDevice, ctx->copy_stream));
     MG_CUDA(ctx, cudaEventRecord(job->copied[b], ctx->copy_stream));
     MG_TRY(screen_collect(job));                                    // the chunk before this one: its kernels overlapped the copy above
     MG_CUDA(ctx, cudaEventSynchronize(job->copied[b]));
-    return screen_enqueue(job, job->stage[b].p, len);
+    return screen_enqueue(job, stage, len);
 }
 
 int screen_flush_acc(mashgpu_screen_job *job)
@@ -477,9 +486,11 @@ extern "C" int mashgpu_screen_finish(mashgpu_screen_job *job, uint64_t *shared, 
         MG_CUDA(ctx, cudaMemcpyAsync(mixture_hashes, job->mix.p, job->h_mix_n * 8ull, cudaMemcpyDeviceToHost, st));
     const uint64_t n = job->n_ref;
     if (n) {
-        DevBuf<uint64_t> d_shared, d_median; DevBuf<double> d_ident, d_p;
-        if (d_shared.alloc(n) != cudaSuccess || d_median.alloc(n) != cudaSuccess || d_ident.alloc(n) != cudaSuccess || d_p.alloc(n) != cudaSuccess)
-            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen outputs)");
+        struct { uint64_t *p; } d_shared, d_median; struct { double *p; } d_ident, d_p;        // four n-element arrays in the context's scratch
+        uint64_t *outs = ctx->scr_out.get<uint64_t>(4 * n);
+        if (!outs) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (screen outputs)");
+        d_shared.p = outs; d_median.p = outs + n;
+        d_ident.p = reinterpret_cast<double *>(outs + 2 * n); d_p.p = reinterpret_cast<double *>(outs + 3 * n);
         uint32_t N = 2;
         while (N < job->stride) N <<= 1;
         if ((size_t)N * 4 > 200 * 1024) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "reference sketches larger than 51200 hashes");
@@ -632,6 +643,7 @@ extern "C" int mashgpu_screen_close(mashgpu_screen_job *job)
     screen_collect(job);                 // never leave a chunk in flight behind
     cudaStreamSynchronize(job->ctx->stream);
     cudaStreamSynchronize(job->ctx->copy_stream);
+    if (job->ctx->scr_stage_owner == job) job->ctx->scr_stage_owner = nullptr;     // the staging pair stays with the context for the next job
     delete job;
     return MASHGPU_OK;
 }

@@ -28,19 +28,39 @@ namespace mash {
 static double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool traceOn() { static const bool on = getenv("MASHGPU_TRACE") != 0; return on; }
 
+// One engine context per process.  Creating it (CUDA context, streams, pinned staging) takes ~0.4 s, as long as parsing 2 GB of
+// FASTA: gpuContextBegin() starts that work on a helper thread so that the parser threads fill the first batch meanwhile;
+// gpuContext() waits for it (or does the work itself when nobody began).
+static mashgpu_ctx *gpuCtx = 0;
+static std::once_flag gpuCtxOnce;
+static std::mutex gpuCtxMutex;
+static std::condition_variable gpuCtxReady;
+static bool gpuCtxDone = false;
+
+static void gpuContextCreate()
+{
+    const double t0 = nowMs();
+    const char *dev = getenv("MASH_GPU_DEVICE");
+    if (mashgpu_create(dev ? atoi(dev) : 0, &gpuCtx) != MASHGPU_OK) {
+        cerr << "ERROR: " << mashgpu_last_error(0) << endl;
+        exit(1);
+    }
+    if (traceOn()) cerr << "[mash] GPU context: " << nowMs() - t0 << " ms" << endl;
+    { std::lock_guard<std::mutex> lock(gpuCtxMutex); gpuCtxDone = true; }
+    gpuCtxReady.notify_all();
+}
+
+void gpuContextBegin()
+{
+    std::call_once(gpuCtxOnce, [] { std::thread(gpuContextCreate).detach(); });     // detached: an exit(1) elsewhere must not find a joinable thread
+}
+
 mashgpu_ctx *gpuContext()
 {
-    static mashgpu_ctx *ctx = 0;
-    if (!ctx) {
-        const double t0 = nowMs();
-        const char *dev = getenv("MASH_GPU_DEVICE");
-        if (mashgpu_create(dev ? atoi(dev) : 0, &ctx) != MASHGPU_OK) {
-            cerr << "ERROR: " << mashgpu_last_error(0) << endl;
-            exit(1);
-        }
-        if (traceOn()) cerr << "[mash] GPU context: " << nowMs() - t0 << " ms" << endl;
-    }
-    return ctx;
+    std::call_once(gpuCtxOnce, gpuContextCreate);
+    std::unique_lock<std::mutex> lock(gpuCtxMutex);
+    gpuCtxReady.wait(lock, [] { return gpuCtxDone; });
+    return gpuCtx;
 }
 
 void fillGpuParams(mashgpu_sketch_params &p, const Sketch::Parameters &parameters)
@@ -116,16 +136,17 @@ void Sketch::createIndex()   // reference Sketch.cpp:492-510 (non-windowed part)
 // batched GPU sketching
 // --------------------------------------------------------------------------------------------------------------
 struct Sketch::Batch {
-    vector<string> seqs;             // records
+    vector<mashhost::SeqBuffer> seqs;   // records (pool storage: returned for reuse when the batch is dropped)
     vector<uint32_t> unitOfRecord;
     vector<Reference> refs;          // one per unit, name/comment filled at parse time
     uint64_t bytes = 0;
     bool reads = false;              // -r: length = genome size or estimateSetSize()
 };
 
-static const uint64_t batchBytesMax = 1ull << 31;
+static const uint64_t batchBytesMax = 1ull << 28;
 
-// A batch is handed to the GPU when it holds 2 GiB of sequence or so many units that their sketches (units x s hashes on the
+// A batch is handed to the GPU when it holds 256 MiB of sequence (one call then takes ~10 ms, and batch + parser look-ahead stay
+// a few hundred MB of recycled buffers, seqbuf.hpp) or so many units that their sketches (units x s hashes on the
 // host and on the device) reach 256 MiB -- `-i` on a multi-FASTA of millions of short records must not allocate by unit count
 template <typename B>
 static bool batchFull(const B &batch, const Sketch::Parameters &parameters)
@@ -202,7 +223,7 @@ static void unsupportedReadsOptions(const Sketch::Parameters &parameters)
 
 // One unit over all records of the listed files, round robin (sketchFile, reference Sketch.cpp:1147-1336).
 static void parseUnit(const vector<string> &fileNames, const Sketch::Parameters &parameters, Sketch::Reference &reference,
-                      vector<string> &seqs, vector<uint32_t> &unitOfRecord, uint32_t unit, uint64_t &bytes)
+                      vector<mashhost::SeqBuffer> &seqs, vector<uint32_t> &unitOfRecord, uint32_t unit, uint64_t &bytes)
 {
     int count = 0;
     bool skipped = false;
@@ -274,6 +295,7 @@ void Sketch::initFromReads(const vector<string> &files, const Parameters &parame
 {
     parameters = parametersNew;
     unsupportedReadsOptions(parameters);
+    gpuContextBegin();
     Batch batch;
     batch.reads = true;
     batch.refs.resize(1);
@@ -286,6 +308,8 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
 {
     parameters = parametersNew;
     Batch batch;
+    for (const string &f : files)
+        if (!hasSuffix(f, suffixSketch)) { gpuContextBegin(); break; }      // sequence input: the context comes up while the first files are parsed
 
     for (size_t i = 0; i < files.size(); i++) {
         bool isSketch = hasSuffix(files[i], suffixSketch);
@@ -343,12 +367,12 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
                     if (test == NULL) { cerr << "ERROR: could not open " << files[i + t] << " for reading." << endl; exit(1); }
                     fclose(test);
                 }
-                struct Parsed { Reference ref; vector<string> seqs; vector<uint32_t> unitOfRecord; uint64_t bytes = 0; bool ready = false; };
+                struct Parsed { Reference ref; vector<mashhost::SeqBuffer> seqs; vector<uint32_t> unitOfRecord; uint64_t bytes = 0; bool ready = false; };
                 vector<Parsed> parsed(run);
                 std::mutex mu;
                 std::condition_variable cvReady, cvRoom;
                 size_t nextFile = 0, consumed = 0;
-                const size_t window = 4 * (size_t)parameters.parallelism;      // files parsed ahead of the consumer
+                const size_t window = 2 * (size_t)parameters.parallelism;      // files parsed ahead of the consumer
                 const size_t nWorkers = std::min<size_t>((size_t)parameters.parallelism, run);
                 vector<std::thread> workers;
                 for (size_t w = 0; w < nWorkers; w++)
@@ -378,7 +402,7 @@ int Sketch::initFromFiles(const vector<string> &files, const Parameters &paramet
                     for (auto &q : parsed[t].seqs) batch.seqs.push_back(std::move(q));
                     batch.unitOfRecord.insert(batch.unitOfRecord.end(), parsed[t].seqs.size(), unit);
                     batch.bytes += parsed[t].bytes;
-                    vector<string>().swap(parsed[t].seqs);
+                    vector<mashhost::SeqBuffer>().swap(parsed[t].seqs);
                     { std::lock_guard<std::mutex> lock(mu); consumed = t + 1; }
                     cvRoom.notify_all();
                     if (batchFull(batch, parameters)) flushBatch(batch);

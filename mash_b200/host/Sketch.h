@@ -136,6 +136,7 @@ private:
 void setAlphabetFromString(Sketch::Parameters &parameters, const char *characters);
 bool hasSuffix(std::string const &whole, std::string const &suffix);
 mashgpu_ctx *gpuContext();     // one engine context per process (device from MASH_GPU_DEVICE, default 0)
+void gpuContextBegin();        // start creating it on a helper thread (gpuContext() then waits for that)
 void fillGpuParams(mashgpu_sketch_params &p, const Sketch::Parameters &parameters);
 
 }  // namespace mash

@@ -17,13 +17,16 @@
 #include <string>
 #include <vector>
 
+#include "seqbuf.hpp"
+
 namespace mashhost {
 
 class FastxReader {
 public:
-    std::string name, comment, seq;
+    std::string name, comment;
+    SeqBuffer seq;          // sequence of the current record (pool storage, seqbuf.hpp); move it out to keep it
 
-    explicit FastxReader(gzFile f) : f_(f), buf_(1 << 20)
+    explicit FastxReader(gzFile f) : f_(f), buf_(1 << 18)
     {
         for (int c = 0; c < 256; c++) cls_[c] = (c == '>' || c == '+' || c == '@') ? 2 : (isgraph(c) ? 0 : 1);
     }

@@ -535,7 +535,7 @@ int runScreen(int argc, const char **argv)
         count++;
         if (len >= kmerSize) {
             input.append(1, '*');
-            input.append(readers[it]->seq);
+            input.append(readers[it]->seq.data(), readers[it]->seq.size());
         }
         it++;
         if (it >= readers.size()) it = 0;
