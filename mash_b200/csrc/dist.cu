@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     extern __shared__ uint32_t s_tab[];                      // CF_BUCKETS words, then 2 * CF_BUCKETS id bytes
     uint8_t *s_ids = reinterpret_cast<uint8_t *>(s_tab + CF_BUCKETS);
     __shared__ int s_fail;
+    __shared__ uint32_t s_mx[32];                            // s_mx[l] = max over the tile's references of their rank at index 32 l (probe cut-off, below)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r0 = blockIdx.x * DIST_TILE_R;
     const uint32_t q_lo = a.q_begin + blockIdx.y * a.q_per_cta;
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     if (a.pair_max > 0)       // the owner bytes exist only when the pair path is on (the launch then asks for 64 KB more shared memory)
         for (uint32_t i = threadIdx.x; i < CF_BUCKETS / 2; i += PROBE_THREADS) reinterpret_cast<uint32_t *>(s_ids)[i] = 0xFFFFFFFFu;     // CF_ID_NONE
     if (threadIdx.x == 0) s_fail = 0;
+    if (threadIdx.x < 32) s_mx[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t rr = warp; rr < DIST_TILE_R; rr += PROBE_WARPS) {
         const uint32_t rb = r0 + rr;
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
         const uint32_t *row = a.ranks + (a.ref_row0 + rb) * (uint64_t)a.P;
         for (uint32_t i = lane; i < n; i += 32)
             if (!cf_insert(s_tab, row[i], threadIdx.x * 2654435761u + i)) s_fail = 1;
+        atomicMax(&s_mx[lane], 32u * lane < n ? row[32 * lane] : RANK_PAD);       // a list that ends before index 32 l bounds nothing there
     }
     __syncthreads();
     // id side table: one reference per phase, so that only ranks of the same reference ever write a slot concurrently
@@ -439,6 +442,14 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
     const double p_const = far ? 0.0 : 1.0;
     const uint8_t pass_const = (far || (a.max_pvalue >= 0 && 1.0 > a.max_pvalue)) ? 0 : 1;
     const int pair_max = a.pair_max;
+    // Cut-off.  In the merge of a reference A with the query B (both sorted, ties kept apart) only the first s' elements matter: if none
+    // of them is shared they are the first s' elements of the union, common = 0 and denom = s' whatever lies behind.  A query element
+    // B[j] is among them iff j + |{a in A: a < B[j]}| < s', so once j + (a lower bound of that count for every reference of the tile)
+    // reaches s' the rest of the query need not be looked up: unrelated sketches of similar size are done after about half their
+    // ranks.  Lower bound: lane l holds mx = max over the tile of A[32 l]; mx < x means every reference has more than 32 l ranks
+    // below x, and mx grows with l, so with L lanes below x the count is at least 32 L - 31.
+    const uint32_t mx = s_mx[lane];
+    const uint32_t cut_at = a.S + 31;
 
     for (uint32_t q = q_lo + warp; q < q_hi; q += PROBE_WARPS) {
         if (a.triangle && q <= a.tri_r0 + r0) continue;            // the whole tile lies on or above the diagonal
@@ -468,6 +479,9 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) dist_probe_kernel(const Dist
                 if (__popc(mask) > a.pair_max) { dense = true; break; }
             }
             base += GROUP; pB += GROUP;
+            // cut-off test for the next group with the last rank of this one (already in a register; B[base] > B[base - 1], so the
+            // bound is merely a little weaker than with B[base], which would have to be waited for)
+            if (base + 32 * __popc(__ballot_sync(0xFFFFFFFFu, mx < __shfl_sync(0xFFFFFFFFu, cur[PROBE_DEPTH - 1], 31))) >= cut_at) { base = nB; break; }
         }
         if (base < nB && !dense) {      // ragged last group
 #pragma unroll
