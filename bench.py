@@ -514,9 +514,15 @@ def main():
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
-    # host packer threads of the hybrid feed path: the ranks of one node share its CPUs
+    # host side of a rank: the CPUs (and with them the memory) of the NUMA node next to its GPU -- before any pinned allocation
+    from mash_b200.shard import bind_to_gpu_numa_node
+    cpus_before_binding = usable_cpus()
+    affinity_before_binding = os.sched_getaffinity(0)
+    numa = None if os.environ.get("MASHGPU_BENCH_NUMA", "1") == "0" else bind_to_gpu_numa_node(local)
+    # host packer threads of the hybrid feed path: the ranks of one node share its CPUs (an equal share of what the process may
+    # use, counted before the binding narrowed the affinity mask to one socket)
     local_world_n = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("MASHGPU_PACK_THREADS", str(max(1, usable_cpus() // max(1, local_world_n) - 1)))
+    os.environ.setdefault("MASHGPU_PACK_THREADS", str(max(1, cpus_before_binding // max(1, local_world_n) - 1)))
     eng = mash_b200.Engine(local)
     eng_sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     p = eng.params(k=K, s=S, seed=SEED)
@@ -967,24 +973,41 @@ def main():
             host_chunks.copy_(chunks[:, :chunk_bytes])
             torch.cuda.synchronize()
             hnp = host_chunks.numpy()
-            wjob = mash_b200._capi.ScreenJob(eng, sset, None, p)         # warm-up pass of the host path (staging buffers, first-use costs), like the resident one
-            for c in range(3):
-                wjob.feed(hnp[c])
-            wjob.finish()
-            wjob.close()
-            ejob = mash_b200._capi.ScreenJob(eng, sset, None, p)
-            dt_e, res_e, feed_e, fin_e = screen_pass(ejob, lambda j, c: j.feed(hnp[c]), n_chunks)
-            ejob.close()
-            same_e2e = bool(np.array_equal(res_e["shared"], res["shared"]) and res_e["set_size"] == res["set_size"])
+            def host_pass(mode):
+                """mode None: the library's choice (host 2-bit packer when the process has >= 10 threads, else ASCII copies); "0" / "1" force one"""
+                if mode is None:
+                    os.environ.pop("MASHGPU_SCREEN_HOST_PACK", None)
+                else:
+                    os.environ["MASHGPU_SCREEN_HOST_PACK"] = mode
+                wjob = mash_b200._capi.ScreenJob(eng, sset, None, p)     # warm-up pass of the host path (staging buffers, first-use costs), like the resident one
+                for c in range(3):
+                    wjob.feed(hnp[c])
+                wjob.finish()
+                wjob.close()
+                ejob = mash_b200._capi.ScreenJob(eng, sset, None, p)
+                out = screen_pass(ejob, lambda j, c: j.feed(hnp[c]), n_chunks)
+                ejob.close()
+                os.environ.pop("MASHGPU_SCREEN_HOST_PACK", None)
+                return out
+
+            dt_e, res_e, feed_e, fin_e = host_pass(None)
+            dt_a, res_a, _, _ = host_pass("0")
+            dt_p, res_p, _, _ = host_pass("1")
+            same_e2e = bool(all(np.array_equal(r["shared"], res["shared"]) and r["set_size"] == res["set_size"] for r in (res_e, res_a, res_p)))
             screen_obj = {"metric": "Gbp_per_s_screened", "value": world * bases / dt / 1e9, "unit": "Gbp/s",
                           "workload": f"configs[3]: {QH.shape[0]}-sketch reference table ({int(QN.sum().item())} hashes) vs {n_chunks * chunk_reads} synthetic 150 bp reads "
                                       f"per rank in {n_chunks} distinct '*'-joined chunks of {chunk_reads} reads resident in HBM; "
                                       f"{'counters all-reduced over NCCL + mixtures merged on the device, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"],
                           "host_ms": {"feed_first": feed_ms[0], "feed_median": float(np.median(feed_ms)), "feed_max": max(feed_ms), "allreduce_and_finish": fin_ms}, "gpu_launches": int(sstats["kernel_launches"]),
-                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * chunk_bytes), "ms_total": dt_e * 1e3,
+                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * (((chunk_bytes + 31) // 32 + 2) * 12 if int(os.environ.get("MASHGPU_PACK_THREADS", "0")) >= 10 else chunk_bytes)),
+                                  "host_chunk_bytes": int(n_chunks * chunk_bytes), "ms_total": dt_e * 1e3,
                                   "feed_median_ms": float(np.median(feed_e)), "feed_max_ms": float(max(feed_e)), "allreduce_and_finish_ms": fin_e, "matches_device_path": same_e2e,
-                                  "api": "mashgpu_screen_feed with pinned host chunks: the copy of chunk i+1 overlaps the kernels of chunk i; finish() and its D2H inside"},
+                                  "ascii_copies_only": world * bases / dt_a / 1e9, "host_packer_only": world * bases / dt_p / 1e9,
+                                  "pack_threads": int(os.environ.get("MASHGPU_PACK_THREADS", "0")),
+                                  "api": "mashgpu_screen_feed with pinned host chunks (library's choice of feed: host 2-bit packer + invalid mask, 0.375 B/base over PCIe, "
+                                         "when the process has >= 10 threads, else ASCII copies): packing of chunk i+1 overlaps the upload of chunk i and the kernels "
+                                         "of chunk i-1; finish() and its D2H inside"},
                           "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()), "exact_reruns": int(sstats["exact_reruns"]),
                           "source_genomes": n_src, "median_multiplicity_of_hit_references": float(np.median(res["median"][res["shared"] > 0])) if (res["shared"] > 0).any() else 0.0,
                           "mean_identity_of_source_genomes": float(np.mean(res["identity"][:n_src]))}
@@ -1025,6 +1048,7 @@ def main():
 
     # ---------------- CPU baseline on rank 0 --------------------------------------------------------------------------
     cpu = None
+    os.sched_setaffinity(0, affinity_before_binding)       # the CPU arms (and the CLI run) get every CPU the process was given
     if rank == 0 and world == 1 and not args.skip_cpu:
         n_cpu = max(128, 2 * (os.cpu_count() or 1))
         rate, kind, dt, cores, tried = best_cpu_sketch_rate(n_cpu, glen)
@@ -1048,7 +1072,8 @@ def main():
                 "config": {"workload": WORKLOAD_SKETCH.format(units=n_units, glen=glen),
                            "k": K, "s": S, "units_per_gpu": n_units, "genome_len": glen,
                            "l2": "inputs larger than L2 (one step streams %.1f GB)" % (bases_per_step / 1e9),
-                           "parallelism": f"records sharded over {world} rank(s), no data-path collective"},
+                           "parallelism": f"records sharded over {world} rank(s), no data-path collective",
+                           "host_binding": (f"rank 0 bound to NUMA node {numa[0]} of its GPU ({numa[1]} CPUs allowed)" if numa else "no NUMA topology visible / single node: not bound")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]),
                 "roofline": roofline, "cpu_baseline": cpu, "dist": dist_obj, "dist5": dist5_obj, "screen": screen_obj, "sanity": sanity,
                 "exact_reruns": int(stats["exact_reruns"])}

@@ -59,6 +59,7 @@ extern "C" void mashgpu_destroy(mashgpu_ctx *ctx)
         if (ctx->wave_copied[b]) cudaEventDestroy(ctx->wave_copied[b]);
         if (ctx->pinned_codes[b]) cudaFreeHost(ctx->pinned_codes[b]);
         if (ctx->pack_copied[b]) cudaEventDestroy(ctx->pack_copied[b]);
+        if (ctx->scr_pinned[b]) cudaFreeHost(ctx->scr_pinned[b]);
     }
     if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
     if (ctx->flags_pinned) cudaFreeHost(ctx->flags_pinned);

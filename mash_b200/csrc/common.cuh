@@ -73,6 +73,8 @@ struct mashgpu_ctx {
     // 1-50 ms depending on the box); scr_stage_owner = the job using the staging pair, others allocate their own
     mashgpu::Scratch scr_stage[2], scr_out;
     const void *scr_stage_owner = nullptr;
+    void *scr_pinned[2] = {nullptr, nullptr};       // packed host feed of screen: pinned codes + mask per slot (with scr_stage)
+    size_t scr_pinned_bytes[2] = {0, 0};
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
     cudaEvent_t wave_copied[2] = {nullptr, nullptr};

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "scan.cuh"
+#include "pack.h"
 #include "sketch_core.cuh"
 #include "binom.cuh"
 
@@ -223,6 +224,9 @@ struct mashgpu_screen_job {
     DevBuf<uint32_t> bitmap; uint32_t bitmap_shift = 0;      // value-indexed presence bitmap (built when the table is large)
     // host-chunk pipeline: two device staging buffers; the kernels of chunk i run while chunk i+1 crosses PCIe
     DevBuf<uint8_t> stage[2];
+    PinnedBuf<uint64_t> h_pack[2];       // packed host feed: codes, then the invalid mask, of the chunk being uploaded from this slot
+    int host_pack = -1;                  // -1 not decided yet, 0 ASCII copies, 1 host 2-bit packer (screen_feed_host)
+    int pack_threads = 1;
     cudaEvent_t copied[2] = {nullptr, nullptr};
     int next_buf = 0;
     SketchTicket ticket;
@@ -342,14 +346,14 @@ constexpr uint64_t SCREEN_SMALL_CHUNK = 4ull << 20;     // host chunks below thi
 constexpr uint64_t SCREEN_FLUSH_BYTES = 32ull << 20;    // ... until this much has accumulated (the reference feeds 1 MiB HashInputs)
 
 // kernels of one chunk: scan (+ table probe) -> chunk bottom-s -> merge into the running mixture -> {n, top} read-back.  No sync.
-int screen_enqueue(mashgpu_screen_job *job, const void *d_chunk, uint64_t len)
+int screen_enqueue(mashgpu_screen_job *job, const void *d_chunk, uint64_t len, const uint64_t *d_codes = nullptr, const uint32_t *d_inval = nullptr)
 {
     mashgpu_ctx *ctx = job->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t s = job->params.sketch_size;
     uint64_t unit_start[2] = {0, len};
     SketchStream S;
-    S.d_stream = d_chunk; S.unit_start = unit_start; S.n_units = 1;
+    S.d_stream = d_chunk; S.d_codes = d_codes; S.d_inval = d_inval; S.unit_start = unit_start; S.n_units = 1;
     if (job->h_mix_n == s) { S.t_cap = true; S.t_cap_value = job->h_mix_top; }   // nothing above the running s-th smallest can matter
     ScreenProbe probe{job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, job->hmax, job->bitmap.p, job->bitmap_shift};
     MG_CUDA(ctx, cudaMemsetAsync(job->chunk_n.p, 0, 4, st));      // an overflowing chunk leaves an empty list until its exact re-run
@@ -393,9 +397,67 @@ int screen_collect(mashgpu_screen_job *job)
 }
 
 // host chunk -> staging buffer (async) while the previous chunk's kernels finish; returns once the caller's buffer is free
+// Host chunk, packed on the way: this thread's pool turns the chunk into 2-bit codes + an invalid bit mask in pinned memory
+// (pack.cpp; 0.375 B per base cross PCIe instead of 1), the upload and the kernels are enqueued behind it and the call returns --
+// the caller's buffer is free as soon as it has been read by the packer.  Packing chunk i+1 overlaps the upload of chunk i and
+// the kernels of chunk i-1.
+int screen_feed_host_packed(mashgpu_screen_job *job, const void *chunk, uint64_t len)
+{
+    mashgpu_ctx *ctx = job->ctx;
+    const int b = job->next_buf;
+    job->next_buf ^= 1;
+    const uint64_t groups = (len + 31) / 32 + 2;                    // + padding words (the kernel reads whole tiles)
+    const uint64_t bytes = groups * 12;
+    if (!job->copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&job->copied[b], cudaEventDisableTiming));
+    else MG_CUDA(ctx, cudaEventSynchronize(job->copied[b]));        // the upload that last used this slot's pinned buffer (two chunks ago)
+    uint8_t *stage;
+    uint64_t *h_codes;
+    if (!ctx->scr_stage_owner || ctx->scr_stage_owner == job) {     // the context's buffers (kept across jobs)
+        ctx->scr_stage_owner = job;
+        stage = ctx->scr_stage[b].get<uint8_t>(ctx->scr_stage[b].bytes < bytes ? bytes + (bytes >> 2) : bytes);
+        if (!stage) return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+        if (ctx->scr_pinned_bytes[b] < bytes) {
+            if (ctx->scr_pinned[b]) cudaFreeHost(ctx->scr_pinned[b]);
+            ctx->scr_pinned[b] = nullptr; ctx->scr_pinned_bytes[b] = 0;
+            if (cudaMallocHost(&ctx->scr_pinned[b], bytes + (bytes >> 2)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (packed chunk of %llu B)", (unsigned long long)len);
+            }
+            ctx->scr_pinned_bytes[b] = bytes + (bytes >> 2);
+        }
+        h_codes = static_cast<uint64_t *>(ctx->scr_pinned[b]);
+    } else {
+        if (job->stage[b].n < bytes && job->stage[b].alloc(bytes + (bytes >> 2)) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (chunk of %llu B)", (unsigned long long)len);
+        stage = job->stage[b].p;
+        if (job->h_pack[b].n * 8 < bytes && job->h_pack[b].alloc((bytes + (bytes >> 2)) / 8 + 1) != cudaSuccess)
+            return fail(ctx, MASHGPU_ERR_NOMEM, "out of pinned host memory (packed chunk of %llu B)", (unsigned long long)len);
+        h_codes = job->h_pack[b].p;
+    }
+    uint32_t *h_inval = reinterpret_cast<uint32_t *>(h_codes + groups);
+    const uint64_t real = (len + 31) / 32;
+    pack_chunk_mask(static_cast<const uint8_t *>(chunk), len, job->params.preserve_case, job->pack_threads, h_codes, h_inval);
+    for (uint64_t g = real; g < groups; g++) { h_codes[g] = 0; h_inval[g] = 0xFFFFFFFFu; }
+    uint64_t *d_codes = reinterpret_cast<uint64_t *>(stage);
+    uint32_t *d_inval = reinterpret_cast<uint32_t *>(d_codes + groups);
+    MG_CUDA(ctx, cudaMemcpyAsync(d_codes, h_codes, groups * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MG_CUDA(ctx, cudaEventRecord(job->copied[b], ctx->copy_stream));
+    MG_TRY(screen_collect(job));                                    // the chunk before this one: its kernels overlapped the packing
+    MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, job->copied[b], 0));   // the kernels wait for the upload, this thread does not
+    return screen_enqueue(job, nullptr, len, d_codes, d_inval);
+}
+
 int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)
 {
     mashgpu_ctx *ctx = job->ctx;
+    if (job->host_pack < 0) {
+        // the packer pays off when the process may run enough threads to out-pack the PCIe-ASCII rate (~52 GB/s; 6-8 GB/s per
+        // thread); MASHGPU_SCREEN_HOST_PACK = 0 / 1 forces a path
+        job->pack_threads = host_pack_threads();
+        const char *e = getenv("MASHGPU_SCREEN_HOST_PACK");
+        job->host_pack = e ? (atoi(e) != 0) : (job->pack_threads >= 10);
+    }
+    if (job->host_pack) return screen_feed_host_packed(job, chunk, len);
     const int b = job->next_buf;
     job->next_buf ^= 1;
     const uint64_t padded = ((len + 15) / 16) * 16;

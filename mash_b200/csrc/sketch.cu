@@ -845,18 +845,10 @@ extern "C" int mashgpu_sketch_batch(mashgpu_ctx *ctx, const mashgpu_sketch_param
             ascii_ok[wi] = ok;
         }
     }
-    // packer threads: as many as the process may actually run -- a container's CPU quota (cgroup v2 cpu.max) can be far below
-    // the visible core count, and threads beyond it are throttled together (measured on this pool's B200 box, 128 vCPUs visible,
-    // quota 16: 61 GB/s with 16 threads, 13 GB/s with 128; tools/pack_bench.py) -- minus one for this thread
-    int threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 96u);
-    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
-        long long quota = 0, period = 0;
-        if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
-            threads = std::min(threads, (int)std::max(1ll, (quota + period - 1) / period));
-        fclose(f);
-    }
-    if (feed & FEED_ASCII) threads = std::max(1, threads - 1);
-    if (const char *t = getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, atoi(t));
+    // packer threads: as many as the process may actually run (pack.cpp: hardware threads, the container's CPU quota,
+    // MASHGPU_PACK_THREADS) -- minus one for this thread when it also drives the ASCII copies
+    int threads = host_pack_threads();
+    if ((feed & FEED_ASCII) && !getenv("MASHGPU_PACK_THREADS")) threads = std::max(1, threads - 1);
 
     uint64_t *d_hashes = ctx->sc_out_hashes.get<uint64_t>(max_units * s);
     uint32_t *d_n = ctx->sc_out_n.get<uint32_t>(max_units);

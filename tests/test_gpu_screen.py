@@ -137,8 +137,11 @@ def test_table_spanning_the_whole_hash_range(gpu, oracle, monkeypatch, bitmap):
     assert want["shared"][3] > 0 and want["shared"][5] == 0
 
 
-def test_many_small_host_chunks_are_joined(gpu, oracle):
+@pytest.mark.parametrize("host_pack", ["0", "1"])
+def test_many_small_host_chunks_are_joined(gpu, oracle, monkeypatch, host_pack):
     # the reference feeds 1 MiB HashInputs; smaller host chunks are joined inside the library before a kernel pass
+    # (host_pack: the joined chunk goes up as ASCII, or 2-bit packed by the host threads with an invalid-position mask)
+    monkeypatch.setenv("MASHGPU_SCREEN_HOST_PACK", host_pack)
     s = 200
     p = gpu.params(k=21, s=s)
     po = oracle.params(k=21)
@@ -148,14 +151,20 @@ def test_many_small_host_chunks_are_joined(gpu, oracle):
     check(run_screen(gpu, ref, ref_n, p, chunks), want)
 
 
-def test_large_host_chunks_are_pipelined(gpu, oracle):
-    # chunks above the joining threshold go through the two-buffer pipeline (copy of chunk i+1 overlaps the kernels of chunk i)
+@pytest.mark.parametrize("host_pack,threads", [("0", "1"), ("1", "1"), ("1", "5")])
+def test_large_host_chunks_are_pipelined(gpu, oracle, monkeypatch, host_pack, threads):
+    # chunks above the joining threshold go through the two-buffer pipeline (copy of chunk i+1 overlaps the kernels of chunk i);
+    # with the host packer the chunk crosses PCIe as 2-bit codes + an invalid mask (lower case, N, '*' separators, a ragged tail)
+    monkeypatch.setenv("MASHGPU_SCREEN_HOST_PACK", host_pack)
+    monkeypatch.setenv("MASHGPU_PACK_THREADS", threads)
     s = 300
     p = gpu.params(k=21, s=s)
     po = oracle.params(k=21)
     ref, ref_n, reads = _refs_and_reads(oracle, po, s, 90_000, seed=13)
     per = 30_000                                                   # 30 000 x 151 B = 4.5 MB per chunk
+    reads = [r.lower() if i % 17 == 0 else r for i, r in enumerate(reads)]        # case folding happens in the packer on that path
     chunks = [b"".join(b"*" + r for r in reads[i:i + per]) for i in range(0, len(reads), per)]
+    chunks[1] = chunks[1] + b"*ACGTACGTACGTACGTACGTACGTAC"                           # a length that is not a multiple of 32 or 64
     assert min(len(c) for c in chunks) >= 4 << 20
     want = oracle.screen(ref, ref_n, chunks, po, s=s)
     job = gpu.screen_open(ref, ref_n, p)

@@ -13,7 +13,7 @@ MASHGPU_TRACE=1 timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/$
 echo "bench rc=$?"; tail -3 gpurun_out/${tag}_bench_n1.err
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/${tag}_ab_*.json')):
+for f in sorted(glob.glob('gpurun_out/r02e_ab_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, json.dumps(d.get('dist')))
     except Exception as e: print(f, e)
