@@ -1000,7 +1000,7 @@ def main():
                                       f"{'counters all-reduced over NCCL + mixtures merged on the device, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"],
                           "host_ms": {"feed_first": feed_ms[0], "feed_median": float(np.median(feed_ms)), "feed_max": max(feed_ms), "allreduce_and_finish": fin_ms}, "gpu_launches": int(sstats["kernel_launches"]),
-                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * (((chunk_bytes + 31) // 32 + 2) * 12 if int(os.environ.get("MASHGPU_PACK_THREADS", "0")) >= 10 else chunk_bytes)),
+                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * ((-(-chunk_bytes // 8192) * 256 + 64) * 12 if int(os.environ.get("MASHGPU_PACK_THREADS", "0")) >= 10 else chunk_bytes)),
                                   "host_chunk_bytes": int(n_chunks * chunk_bytes), "ms_total": dt_e * 1e3,
                                   "feed_median_ms": float(np.median(feed_e)), "feed_max_ms": float(max(feed_e)), "allreduce_and_finish_ms": fin_e, "matches_device_path": same_e2e,
                                   "ascii_copies_only": world * bases / dt_a / 1e9, "host_packer_only": world * bases / dt_p / 1e9,

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <chrono>
 #include <memory>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1020,6 +1021,9 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
     const uint64_t total = rows * P;
     if (total >= 0x7FFFFFFFull) return fail(ctx, MASHGPU_ERR_UNSUPPORTED, "more than 2^31 dictionary slots (%llu rows x %u)", (unsigned long long)rows, P);
 
+    const bool trace = getenv("MASHGPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_open = now();
     SetOnDevice dr, dq;
     MG_TRY(stage_set(ctx, ref, dr, st));
     if (!self) MG_TRY(stage_set(ctx, qry, dq, st));
@@ -1033,6 +1037,7 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
         if (keys.alloc(total) != cudaSuccess || slots.alloc(total) != cudaSuccess)
             return fail(ctx, MASHGPU_ERR_NOMEM, "out of device memory (dictionary scratch for %llu hashes)", (unsigned long long)total);
         uint64_t n_r = 0, n_q = 0, n_distinct = 0;
+        if (trace) fprintf(stderr, "[mashgpu] dist_open: staging + 5 allocations (%.0f MB) %.2f ms\n", total * 16e-6, now() - t_open);
         MG_TRY(dict_gather(ctx, dr, job->n_ref, ref->stride, P, 0, job->n_eff.p, 0, keys.p, slots.p, &n_r, st));
         if (!self) MG_TRY(dict_gather(ctx, dq, job->n_qry, qry->stride, P, job->n_ref, job->n_eff.p, n_r, keys.p, slots.p, &n_q, st));
         MG_CUDA(ctx, cudaMemsetAsync(job->ranks.p, 0xFF, total * 4, st));                  // padding code everywhere, then the real ranks
@@ -1041,8 +1046,11 @@ extern "C" int mashgpu_dist_open(mashgpu_ctx *ctx, const mashgpu_sketch_set *ref
         MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p, dr.length, job->n_ref * 8, cudaMemcpyDeviceToDevice, st));
         if (!self && job->n_qry)
             MG_CUDA(ctx, cudaMemcpyAsync(job->lens.p + job->n_ref, dq.length, job->n_qry * 8, cudaMemcpyDeviceToDevice, st));
+        if (trace) fprintf(stderr, "[mashgpu] dist_open: dictionary built at %.2f ms\n", now() - t_open);
     }
+    if (trace) fprintf(stderr, "[mashgpu] dist_open: scratch freed at %.2f ms\n", now() - t_open);
     MG_TRY(dist_job_tables(ctx, job.get(), st));
+    if (trace) fprintf(stderr, "[mashgpu] dist_open: tables at %.2f ms\n", now() - t_open);
     *job_out = job.release();
     return MASHGPU_OK;
 }

@@ -346,14 +346,15 @@ constexpr uint64_t SCREEN_SMALL_CHUNK = 4ull << 20;     // host chunks below thi
 constexpr uint64_t SCREEN_FLUSH_BYTES = 32ull << 20;    // ... until this much has accumulated (the reference feeds 1 MiB HashInputs)
 
 // kernels of one chunk: scan (+ table probe) -> chunk bottom-s -> merge into the running mixture -> {n, top} read-back.  No sync.
-int screen_enqueue(mashgpu_screen_job *job, const void *d_chunk, uint64_t len, const uint64_t *d_codes = nullptr, const uint32_t *d_inval = nullptr)
+int screen_enqueue(mashgpu_screen_job *job, const void *d_chunk, uint64_t len, const uint64_t *d_codes = nullptr, const uint32_t *d_inval = nullptr,
+                   cudaEvent_t data_ready = nullptr)
 {
     mashgpu_ctx *ctx = job->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t s = job->params.sketch_size;
     uint64_t unit_start[2] = {0, len};
     SketchStream S;
-    S.d_stream = d_chunk; S.d_codes = d_codes; S.d_inval = d_inval; S.unit_start = unit_start; S.n_units = 1;
+    S.d_stream = d_chunk; S.d_codes = d_codes; S.d_inval = d_inval; S.unit_start = unit_start; S.n_units = 1; S.data_ready = data_ready;
     if (job->h_mix_n == s) { S.t_cap = true; S.t_cap_value = job->h_mix_top; }   // nothing above the running s-th smallest can matter
     ScreenProbe probe{job->keys.p, job->slot_idx.p, job->cnt.p, job->log2cap, job->hmax, job->bitmap.p, job->bitmap_shift};
     MG_CUDA(ctx, cudaMemsetAsync(job->chunk_n.p, 0, 4, st));      // an overflowing chunk leaves an empty list until its exact re-run
@@ -406,7 +407,9 @@ int screen_feed_host_packed(mashgpu_screen_job *job, const void *chunk, uint64_t
     mashgpu_ctx *ctx = job->ctx;
     const int b = job->next_buf;
     job->next_buf ^= 1;
-    const uint64_t groups = (len + 31) / 32 + 2;                    // + padding words (the kernel reads whole tiles)
+    // the scan kernel reads whole tiles of the packed stream plus a halo without looking at the stream length: everything from the
+    // end of the chunk to the end of the tile-padded allocation must read as invalid (sketch.cu pads its packed waves the same way)
+    const uint64_t groups = ((len + SCAN_TILE - 1) / SCAN_TILE) * (SCAN_TILE / 32) + 64;
     const uint64_t bytes = groups * 12;
     if (!job->copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&job->copied[b], cudaEventDisableTiming));
     else MG_CUDA(ctx, cudaEventSynchronize(job->copied[b]));        // the upload that last used this slot's pinned buffer (two chunks ago)
@@ -443,8 +446,7 @@ int screen_feed_host_packed(mashgpu_screen_job *job, const void *chunk, uint64_t
     MG_CUDA(ctx, cudaMemcpyAsync(d_codes, h_codes, groups * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
     MG_CUDA(ctx, cudaEventRecord(job->copied[b], ctx->copy_stream));
     MG_TRY(screen_collect(job));                                    // the chunk before this one: its kernels overlapped the packing
-    MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, job->copied[b], 0));   // the kernels wait for the upload, this thread does not
-    return screen_enqueue(job, nullptr, len, d_codes, d_inval);
+    return screen_enqueue(job, nullptr, len, d_codes, d_inval, job->copied[b]);      // the scan kernel waits for the upload, this thread does not
 }
 
 int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)

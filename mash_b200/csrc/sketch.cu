@@ -603,6 +603,7 @@ int sketch_stream_enqueue(mashgpu_ctx *ctx, const mashgpu_sketch_params *p, cons
         a.coarse_t = std::max(tm, probe->hmax);
         a.screen_mix_t = tm;
     }
+    if (S.data_ready) MG_CUDA(ctx, cudaStreamWaitEvent(st, S.data_ready, 0));
     MG_TRY(launch_scan(ctx, p, a, st));
 
     const size_t sel_smem = (size_t)8 << SEL_MAX_LOG2;

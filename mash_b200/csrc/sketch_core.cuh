@@ -12,6 +12,9 @@ struct SketchStream {
     const uint64_t *unit_start = nullptr;   // host, n_units + 1
     uint64_t n_units = 0;
     bool force_keep_all = false;
+    cudaEvent_t data_ready = nullptr;       // when set: the scan kernel waits for this event (an upload on another stream); the parameter
+                                            // copies of the pass are enqueued before the wait -- they come from pageable memory and would
+                                            // otherwise hold the calling thread until the upload has finished
     bool t_cap = false;                     // clamp every unit threshold to t_cap_value (screen: running s-th smallest)
     uint64_t t_cap_value = 0;
 };
