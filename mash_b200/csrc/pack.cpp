@@ -12,9 +12,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #if defined(__x86_64__)
@@ -24,6 +27,59 @@
 namespace mashgpu {
 
 namespace {
+
+// Worker threads that outlive a call.  A pack call used to start and join its threads itself: ~14 thread creations per call cost
+// as much as packing 300 MB does (measured through the screen feed on the 16-CPU box: 8.2 ms per 302 MB chunk against 2.6 ms of
+// packing at the rate the 1 GiB sketch waves reach), so small jobs -- screen chunks -- could not pay for themselves.
+class PackPool {
+public:
+    static PackPool &instance() { static PackPool *p = new PackPool; return *p; }       // never destroyed: workers may be parked at exit
+    // `work` is run on `threads` threads in total, the caller included; it pulls its items from its own atomic counter
+    void run(int threads, const std::function<void()> &work)
+    {
+        std::lock_guard<std::mutex> one_job(run_mu_);
+        const int helpers = std::max(0, threads - 1);
+        {
+            std::unique_lock<std::mutex> lock(mu_);
+            while ((int)workers_.size() < helpers) {
+                const int id = (int)workers_.size();
+                workers_.emplace_back([this, id] { loop(id); });
+                workers_.back().detach();
+            }
+            job_ = &work; want_ = helpers; active_ = helpers; gen_++;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_done_.wait(lock, [&] { return active_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void()> *job;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_work_.wait(lock, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (id >= want_) continue;
+                job = job_;
+            }
+            (*job)();
+            std::lock_guard<std::mutex> lock(mu_);
+            if (--active_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    const std::function<void()> *job_ = nullptr;
+    int want_ = 0, active_ = 0;
+    uint64_t gen_ = 0;
+};
 
 struct Lut {
     uint8_t v[2][256];   // [preserve_case][byte] -> code (0..3) or 4 = invalid
@@ -230,10 +286,7 @@ void pack_stream(const PackSegment *segments, size_t n_segments, uint64_t stream
             pack_range(segs, n_segments, g0 * 32, std::min(stream_len, g1 * 32), preserve_case, codes + g0, chunk_runs[ci]);
         }
     };
-    std::vector<std::thread> pool;
-    for (uint64_t t = 1; t < nt; t++) pool.emplace_back(work);
-    work();
-    for (auto &t : pool) t.join();
+    PackPool::instance().run((int)nt, work);
     for (auto &cr : chunk_runs)
         for (auto &r : cr) {
             if (!runs.empty() && runs.back().start + runs.back().len == r.start) runs.back().len += r.len;
@@ -277,10 +330,7 @@ void pack_chunk_mask(const uint8_t *src, uint64_t len, int preserve_case, int th
             range(ci * chunk_groups, std::min(groups, (ci + 1) * chunk_groups));
         }
     };
-    std::vector<std::thread> pool;
-    for (uint64_t t = 1; t < nt; t++) pool.emplace_back(work);
-    work();
-    for (auto &t : pool) t.join();
+    PackPool::instance().run((int)nt, work);
 }
 
 int host_pack_threads()

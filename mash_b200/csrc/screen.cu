@@ -411,8 +411,12 @@ int screen_feed_host_packed(mashgpu_screen_job *job, const void *chunk, uint64_t
     // end of the chunk to the end of the tile-padded allocation must read as invalid (sketch.cu pads its packed waves the same way)
     const uint64_t groups = ((len + SCAN_TILE - 1) / SCAN_TILE) * (SCAN_TILE / 32) + 64;
     const uint64_t bytes = groups * 12;
+    static const bool trace = getenv("MASHGPU_TRACE_FEED") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (!job->copied[b]) MG_CUDA(ctx, cudaEventCreateWithFlags(&job->copied[b], cudaEventDisableTiming));
     else MG_CUDA(ctx, cudaEventSynchronize(job->copied[b]));        // the upload that last used this slot's pinned buffer (two chunks ago)
+    const double t1 = now();
     uint8_t *stage;
     uint64_t *h_codes;
     if (!ctx->scr_stage_owner || ctx->scr_stage_owner == job) {     // the context's buffers (kept across jobs)
@@ -443,10 +447,15 @@ int screen_feed_host_packed(mashgpu_screen_job *job, const void *chunk, uint64_t
     for (uint64_t g = real; g < groups; g++) { h_codes[g] = 0; h_inval[g] = 0xFFFFFFFFu; }
     uint64_t *d_codes = reinterpret_cast<uint64_t *>(stage);
     uint32_t *d_inval = reinterpret_cast<uint32_t *>(d_codes + groups);
+    const double t2 = now();
     MG_CUDA(ctx, cudaMemcpyAsync(d_codes, h_codes, groups * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
     MG_CUDA(ctx, cudaEventRecord(job->copied[b], ctx->copy_stream));
     MG_TRY(screen_collect(job));                                    // the chunk before this one: its kernels overlapped the packing
-    return screen_enqueue(job, nullptr, len, d_codes, d_inval, job->copied[b]);      // the scan kernel waits for the upload, this thread does not
+    const double t3 = now();
+    const int rc = screen_enqueue(job, nullptr, len, d_codes, d_inval, job->copied[b]);      // the scan kernel waits for the upload, this thread does not
+    if (trace) fprintf(stderr, "[mashgpu] screen packed feed %llu B: wait %.2f, alloc + pack %.2f (%d threads), collect previous %.2f, enqueue %.2f ms\n",
+                       (unsigned long long)len, t1 - t0, t2 - t1, job->pack_threads, t3 - t2, now() - t3);
+    return rc;
 }
 
 int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)
