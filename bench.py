@@ -523,6 +523,14 @@ def main():
     # use, counted before the binding narrowed the affinity mask to one socket)
     local_world_n = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     os.environ.setdefault("MASHGPU_PACK_THREADS", str(max(1, cpus_before_binding // max(1, local_world_n) - 1)))
+    # feed of the drop-in sketch call: with 8 ranks on a 2-socket host the host memory system is the bound, and the packer's own
+    # reads and writes (1.25 B per base it packs) cost more than the PCIe bytes they save -- measured at N = 8 with the ranks bound
+    # to their sockets: ASCII copies only 397 Gbp/s, both producers 294 (profiles/r02_e2e_n8_ab.json); with 1-2 ranks per host the
+    # two producers win (81 against 52 Gbp/s at N = 1).  The library's default stays "both"; the launcher decides per deployment.
+    feed_note = None
+    if local_world_n >= 8 and "MASHGPU_HOST_PACK" not in os.environ:
+        os.environ["MASHGPU_HOST_PACK"] = "0"
+        feed_note = f"ASCII DMA only: chosen by bench.py for {local_world_n} ranks per host (host memory bound; the library default is the hybrid feed)"
     eng = mash_b200.Engine(local)
     eng_sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     p = eng.params(k=K, s=S, seed=SEED)
@@ -627,7 +635,8 @@ def main():
         e2e = {"value": world * e2e_units * glen * Ksteps / dt / 1e9, "unit": "Gbp/s",
                "h2d_bytes_per_step": int(e2e_units * span), "d2h_bytes_per_step": int(e2e_units * (S * 8 + 4)),
                "units_per_step": e2e_units, "ms_per_step": dt / Ksteps * 1e3, "matches_device_path": same,
-               "feed": os.environ.get("MASHGPU_HOST_PACK", "hybrid: ASCII DMA and host 2-bit packer side by side (default)"),
+               "feed": feed_note or {"0": "ASCII DMA only (MASHGPU_HOST_PACK=0)", "1": "host 2-bit packer only (MASHGPU_HOST_PACK=1)"}.get(
+                   os.environ.get("MASHGPU_HOST_PACK", ""), "hybrid: ASCII DMA and host 2-bit packer side by side (default)"),
                "api": "mashgpu_sketch_batch (host pinned buffers; H2D + kernels + D2H inside the timed region)"}
         # ---- the same batch from a collection the caller keeps 2-bit packed (mashgpu_sketch_batch_packed): packing is done once,
         # outside the timed region (that is the premise: a cached packed collection); per step 0.25 B/base cross PCIe
@@ -974,7 +983,7 @@ def main():
             torch.cuda.synchronize()
             hnp = host_chunks.numpy()
             def host_pass(mode):
-                """mode None: the library's choice (host 2-bit packer when the process has >= 10 threads, else ASCII copies); "0" / "1" force one"""
+                """mode None: the library's default (ASCII copies); "0" / "1" force ASCII copies / the host 2-bit packer"""
                 if mode is None:
                     os.environ.pop("MASHGPU_SCREEN_HOST_PACK", None)
                 else:
@@ -1000,14 +1009,13 @@ def main():
                                       f"{'counters all-reduced over NCCL + mixtures merged on the device, ' if dist_on else ''}finish() included",
                           "ms_total": dt * 1e3, "scan_kernel_ms": sstats["scan_kernel_ms"],
                           "host_ms": {"feed_first": feed_ms[0], "feed_median": float(np.median(feed_ms)), "feed_max": max(feed_ms), "allreduce_and_finish": fin_ms}, "gpu_launches": int(sstats["kernel_launches"]),
-                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * ((-(-chunk_bytes // 8192) * 256 + 64) * 12 if int(os.environ.get("MASHGPU_PACK_THREADS", "0")) >= 10 else chunk_bytes)),
+                          "e2e": {"value": world * bases / dt_e / 1e9, "unit": "Gbp/s", "h2d_bytes": int(n_chunks * chunk_bytes),
                                   "host_chunk_bytes": int(n_chunks * chunk_bytes), "ms_total": dt_e * 1e3,
                                   "feed_median_ms": float(np.median(feed_e)), "feed_max_ms": float(max(feed_e)), "allreduce_and_finish_ms": fin_e, "matches_device_path": same_e2e,
                                   "ascii_copies_only": world * bases / dt_a / 1e9, "host_packer_only": world * bases / dt_p / 1e9,
                                   "pack_threads": int(os.environ.get("MASHGPU_PACK_THREADS", "0")),
-                                  "api": "mashgpu_screen_feed with pinned host chunks (library's choice of feed: host 2-bit packer + invalid mask, 0.375 B/base over PCIe, "
-                                         "when the process has >= 10 threads, else ASCII copies): packing of chunk i+1 overlaps the upload of chunk i and the kernels "
-                                         "of chunk i-1; finish() and its D2H inside"},
+                                  "api": "mashgpu_screen_feed with pinned host chunks (default feed: ASCII copies, the copy of chunk i+1 overlaps the kernels of chunk i; "
+                                         "host_packer_only = MASHGPU_SCREEN_HOST_PACK=1: host 2-bit packer + invalid mask, 0.375 B/base over PCIe); finish() and its D2H inside"},
                           "set_size": int(res["set_size"]), "references_hit": int((res["shared"] > 0).sum()), "exact_reruns": int(sstats["exact_reruns"]),
                           "source_genomes": n_src, "median_multiplicity_of_hit_references": float(np.median(res["median"][res["shared"] > 0])) if (res["shared"] > 0).any() else 0.0,
                           "mean_identity_of_source_genomes": float(np.mean(res["identity"][:n_src]))}

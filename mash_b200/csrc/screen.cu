@@ -462,11 +462,12 @@ int screen_feed_host(mashgpu_screen_job *job, const void *chunk, uint64_t len)
 {
     mashgpu_ctx *ctx = job->ctx;
     if (job->host_pack < 0) {
-        // the packer pays off when the process may run enough threads to out-pack the PCIe-ASCII rate (~52 GB/s; 6-8 GB/s per
-        // thread); MASHGPU_SCREEN_HOST_PACK = 0 / 1 forces a path
+        // MASHGPU_SCREEN_HOST_PACK = 1 selects the packer.  It pays off when the process may run enough threads to out-pack the
+        // PCIe-ASCII rate (~52 GB/s; 6-8 GB/s per thread); measured so far (r02g, 15 threads, a thread start per call) it did
+        // not: 33 against 52 Gbp/s, so ASCII copies stay the default
         job->pack_threads = host_pack_threads();
         const char *e = getenv("MASHGPU_SCREEN_HOST_PACK");
-        job->host_pack = e ? (atoi(e) != 0) : (job->pack_threads >= 10);
+        job->host_pack = e ? (atoi(e) != 0) : 0;
     }
     if (job->host_pack) return screen_feed_host_packed(job, chunk, len);
     const int b = job->next_buf;
