@@ -85,3 +85,17 @@ def test_pack_matches_numpy(preserve_case, threads):
 def test_pack_empty():
     codes, runs, total = host_pack([])
     assert total == 0 and runs == []
+
+
+def test_chunk_mask_packer_matches_byte_by_byte_restatement(tmp_path):
+    # pack_chunk_mask (host packer of the screen feed: codes + invalid-position mask, no runs; AVX-512 / AVX2 / scalar paths, 1 and 5
+    # threads through the persistent worker pool, lengths 0..49 and random ones up to 40 MB) has no C-ABI entry point of its own: a small
+    # C++ harness links pack.cpp and compares every position with the definition
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pack_mask_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "mash_b200", "csrc"), os.path.join(root, "tools", "pack_mask_test.cpp"),
+                           os.path.join(root, "mash_b200", "csrc", "pack.cpp"), "-o", exe, "-pthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "bad 0" in out.stdout, out.stdout[-2000:]

@@ -132,3 +132,12 @@ def test_malformed_msh_is_rejected_not_read_out_of_bounds(mash, tmp_path):
             assert p.returncode == 0, err
         else:
             assert p.returncode == 1 and "not a valid sketch file" in err, (name, p.returncode, err)
+
+
+def test_sequence_buffer_pool(tmp_path):
+    # host/seqbuf.hpp: records parsed by `mash sketch` live in recycled pool buffers (fresh-memory page faults bounded the parse stage);
+    # contents through growth and moves, heap for short records, slab reuse, six threads at once
+    exe = str(tmp_path / "seqbuf_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "mash_b200", "host"), os.path.join(ROOT, "tools", "seqbuf_test.cpp"), "-o", exe, "-pthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "bad 0" in out.stdout, out.stdout[-2000:]

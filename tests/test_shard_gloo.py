@@ -102,3 +102,12 @@ def test_sharded_dictionary_protocol(tmp_path, world, n):
         assert np.array_equal(got["n_eff"].astype(np.uint32), want_neff) and np.array_equal(got["lens"].astype(np.uint64), L)
         total_ranked += int(got["ranked"])
     assert total_ranked == int(want_neff.sum())          # every hash was ranked exactly once, on the rank that owns its range
+
+
+def test_numa_binding_helper_without_a_gpu_is_a_no_op():
+    # bench.py binds a rank to the CPUs of its GPU's NUMA node; without CUDA (or without visible topology) it must leave the affinity alone
+    import os
+    from mash_b200.shard import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
