@@ -37,15 +37,16 @@ static std::mutex gpuCtxMutex;
 static std::condition_variable gpuCtxReady;
 static bool gpuCtxDone = false;
 
+static std::string gpuCtxError;
+
 static void gpuContextCreate()
 {
     const double t0 = nowMs();
     const char *dev = getenv("MASH_GPU_DEVICE");
     if (mashgpu_create(dev ? atoi(dev) : 0, &gpuCtx) != MASHGPU_OK) {
-        cerr << "ERROR: " << mashgpu_last_error(0) << endl;
-        exit(1);
-    }
-    if (traceOn()) cerr << "[mash] GPU context: " << nowMs() - t0 << " ms" << endl;
+        gpuCtx = 0;
+        gpuCtxError = mashgpu_last_error(0);        // reported by gpuContext() on the main thread: no exit() from the helper thread
+    } else if (traceOn()) cerr << "[mash] GPU context: " << nowMs() - t0 << " ms" << endl;
     { std::lock_guard<std::mutex> lock(gpuCtxMutex); gpuCtxDone = true; }
     gpuCtxReady.notify_all();
 }
@@ -60,6 +61,10 @@ mashgpu_ctx *gpuContext()
     std::call_once(gpuCtxOnce, gpuContextCreate);
     std::unique_lock<std::mutex> lock(gpuCtxMutex);
     gpuCtxReady.wait(lock, [] { return gpuCtxDone; });
+    if (!gpuCtx) {      // no CPU path: without the engine there is nothing to fall back to
+        cerr << "ERROR: " << gpuCtxError << endl;
+        exit(1);
+    }
     return gpuCtx;
 }
 
