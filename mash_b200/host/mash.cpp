@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "Sketch.h"
+#include "fastout.hpp"
 #include "fastx.hpp"
 
 using namespace std;
@@ -352,36 +353,36 @@ int runDist(int argc, const char **argv)
                 uint64_t nPass = 0;
                 if (mashgpu_dist_run_list(job, q, r, listCapacity, lIdx.data(), lNumer.data(), lDenom.data(), lDist.data(), lP.data(), &nPass) != MASHGPU_OK) gpuFail();
                 if (nPass <= listCapacity) {
-                    for (uint64_t e = 0; e < nPass; e++) {
+                    mashhost::writeRows(nPass, parameters.parallelism, 1, [&](uint64_t e, mashhost::OutBuf &o) {
                         uint64_t i = lIdx[e] / nRef, j = lIdx[e] % nRef;
-                        cout << sketchRef.getReference(j).name;
-                        if (comment) cout << ':' << sketchRef.getReference(j).comment;
-                        cout << '\t' << sketchQuery.getReference(q + i).name;
-                        if (comment) cout << ':' << sketchQuery.getReference(q + i).comment;
-                        cout << '\t' << lDist[e] << '\t' << lP[e] << '\t' << lNumer[e] << '/' << lDenom[e] << endl;
-                    }
+                        o.str(sketchRef.getReference(j).name);
+                        if (comment) { o.ch(':'); o.str(sketchRef.getReference(j).comment); }
+                        o.ch('\t'); o.str(sketchQuery.getReference(q + i).name);
+                        if (comment) { o.ch(':'); o.str(sketchQuery.getReference(q + i).comment); }
+                        o.ch('\t'); o.dbl(lDist[e]); o.ch('\t'); o.dbl(lP[e]); o.ch('\t'); o.u64(lNumer[e]); o.ch('/'); o.u64(lDenom[e]); o.ch('\n');
+                    });
                     continue;
                 }
                 // more passing pairs than the list holds: dense path for this block
             }
             if (mashgpu_dist_run(job, q, r, out.numer.data(), out.denom.data(), out.distance.data(), out.pValue.data(), out.pass.data()) != MASHGPU_OK) gpuFail();
-            for (uint64_t i = 0; i < r; i++) {                 // == writeOutput, reference CommandDistance.cpp:247-304
+            mashhost::writeRows(r, parameters.parallelism, nRef, [&](uint64_t i, mashhost::OutBuf &o) {   // == writeOutput, reference CommandDistance.cpp:247-304
                 for (uint64_t j = 0; j < nRef; j++) {
                     size_t k = i * nRef + j;
-                    if (table && j == 0) cout << sketchQuery.getReference(q + i).name;
+                    if (table && j == 0) o.str(sketchQuery.getReference(q + i).name);
                     if (table) {
-                        cout << '\t';
-                        if (out.pass[k]) cout << out.distance[k];
+                        o.ch('\t');
+                        if (out.pass[k]) o.dbl(out.distance[k]);
                     } else if (out.pass[k]) {
-                        cout << sketchRef.getReference(j).name;
-                        if (comment) cout << ':' << sketchRef.getReference(j).comment;
-                        cout << '\t' << sketchQuery.getReference(q + i).name;
-                        if (comment) cout << ':' << sketchQuery.getReference(q + i).comment;
-                        cout << '\t' << out.distance[k] << '\t' << out.pValue[k] << '\t' << out.numer[k] << '/' << out.denom[k] << endl;
+                        o.str(sketchRef.getReference(j).name);
+                        if (comment) { o.ch(':'); o.str(sketchRef.getReference(j).comment); }
+                        o.ch('\t'); o.str(sketchQuery.getReference(q + i).name);
+                        if (comment) { o.ch(':'); o.str(sketchQuery.getReference(q + i).comment); }
+                        o.ch('\t'); o.dbl(out.distance[k]); o.ch('\t'); o.dbl(out.pValue[k]); o.ch('\t'); o.u64(out.numer[k]); o.ch('/'); o.u64(out.denom[k]); o.ch('\n');
                     }
                 }
-                if (table) cout << endl;
-            }
+                if (table) o.ch('\n');
+            });
         }
         mashgpu_dist_close(job);
     }
@@ -436,23 +437,26 @@ int runTriangle(int argc, const char **argv)
         for (uint64_t q = 1; q < n; q += rows) {
             uint64_t r = std::min(rows, n - q);
             if (mashgpu_dist_run(job, q, r, out.numer.data(), out.denom.data(), out.distance.data(), out.pValue.data(), out.pass.data()) != MASHGPU_OK) gpuFail();
-            for (uint64_t i = 0; i < r; i++) {                 // == writeOutput, reference CommandTriangle.cpp:159-198
+            mashhost::writeRows(r, parameters.parallelism, n, [&](uint64_t i, mashhost::OutBuf &o) {   // == writeOutput, reference CommandTriangle.cpp:159-198
                 const Sketch::Reference &ref = sketch.getReference(q + i);
-                if (!edge) cout << (comment ? ref.comment : ref.name);
+                if (!edge) o.str(comment ? ref.comment : ref.name);
                 for (uint64_t j = 0; j < q + i; j++) {
                     size_t k = i * n + j;
                     if (edge) {
                         if (out.pass[k]) {
                             const Sketch::Reference &qry = sketch.getReference(j);
-                            cout << (comment ? ref.comment : ref.name) << '\t' << (comment ? qry.comment : qry.name) << '\t' << out.distance[k] << '\t' << out.pValue[k] << '\t' << out.numer[k] << '/' << out.denom[k] << endl;
+                            o.str(comment ? ref.comment : ref.name); o.ch('\t'); o.str(comment ? qry.comment : qry.name); o.ch('\t');
+                            o.dbl(out.distance[k]); o.ch('\t'); o.dbl(out.pValue[k]); o.ch('\t'); o.u64(out.numer[k]); o.ch('/'); o.u64(out.denom[k]); o.ch('\n');
                         }
                     } else {
-                        cout << '\t' << out.distance[k];
+                        o.ch('\t'); o.dbl(out.distance[k]);
                     }
-                    if (out.pValue[k] > pValuePeak) pValuePeak = out.pValue[k];
                 }
-                if (!edge) cout << endl;
-            }
+                if (!edge) o.ch('\n');
+            });
+            for (uint64_t i = 0; i < r; i++)
+                for (uint64_t j = 0; j < q + i; j++)
+                    if (out.pValue[i * n + j] > pValuePeak) pValuePeak = out.pValue[i * n + j];
         }
         mashgpu_dist_close(job);
     }

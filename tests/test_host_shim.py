@@ -141,3 +141,16 @@ def test_sequence_buffer_pool(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "mash_b200", "host"), os.path.join(ROOT, "tools", "seqbuf_test.cpp"), "-o", exe, "-pthread"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "bad 0" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("threads,rows,cols", [(1, 0, 5), (1, 1, 1), (3, 7, 3), (1, 1500, 400), (5, 1500, 400), (4, 3, 150000), (8, 200000, 2)])
+def test_pair_grid_writer_prints_what_the_stream_operators_print(tmp_path_factory, threads, rows, cols):
+    # `mash dist` / `mash triangle` format their rows into memory on the -p threads (host/fastout.hpp) instead of one
+    # `cout << ... << endl` per pair; the bytes must be the reference's -- doubles as `ostream << double` prints them (6 significant
+    # digits, %g), incl. denormals, rounding boundaries, 0, 1, 1e22 -- and keep their place between other cout output
+    exe = str(tmp_path_factory.getbasetemp() / "fastout_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "mash_b200", "host"), os.path.join(ROOT, "tools", "fastout_test.cpp"), "-o", exe, "-pthread"])
+    want = subprocess.run([exe, "stream", str(threads), str(rows), str(cols)], capture_output=True, check=True).stdout
+    got = subprocess.run([exe, "fast", str(threads), str(rows), str(cols)], capture_output=True, check=True).stdout
+    assert got == want and len(want) > 10
