@@ -267,7 +267,10 @@ typedef struct mashgpu_screen_job mashgpu_screen_job;
 int mashgpu_screen_open(mashgpu_ctx *ctx, const mashgpu_sketch_params *params, const mashgpu_sketch_set *refs,
                         mashgpu_screen_job **job);
 /* One HashInput (CommandScreen.h:104-133): a '*'-joined chunk of reads (CommandScreen.cpp:224-262; any byte
- * outside the alphabet separates reads).  Host buffer; chunks may be of any size. */
+ * outside the alphabet separates reads).  Host buffer; chunks may be of any size: chunks below 4 MiB are joined before a kernel
+ * pass, larger ones are pipelined (the copy of chunk i+1 overlaps the kernels of chunk i).  The call returns as soon as the
+ * caller's buffer may be reused; results are complete at mashgpu_screen_finish.  (MASHGPU_SCREEN_HOST_PACK=1: the chunk is 2-bit
+ * packed on the host threads and uploaded with an invalid-position mask instead of as ASCII.) */
 int mashgpu_screen_feed(mashgpu_screen_job *job, const char *chunk, uint64_t len);
 /* Same for a chunk already in device memory (readable up to len rounded up to 16). */
 int mashgpu_screen_feed_dev(mashgpu_screen_job *job, const void *d_chunk, uint64_t len);
