@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cli", action="store_true")
     ap.add_argument("--cli-files", type=int, default=1000, help="FASTA files in the file -> .msh side measurement of the host shim")
+    ap.add_argument("--cli-dist-sketches", type=int, default=6000, help="sketches in the `mash dist` wall-clock side measurement of the host shim")
     return ap.parse_args()
 
 
@@ -430,6 +431,49 @@ def cli_sketch_rate(n_files, genome_len, threads, seed=4321):
             "command": f"mash sketch -p {threads} -o out -l list.txt  ({n_files} uncompressed 70-column FASTA files of {genome_len} bp on tmpfs)",
             "note": "wall clock of the whole process: start-up and CUDA context creation, FASTA parse on the host threads, sketching on the GPU, "
                     ".msh (Cap'n Proto) write"}
+
+
+def cli_dist_rate(n_sketches, contig_len, threads, seed=8765):
+    """Wall clock of `mash dist -p threads x.msh x.msh > /dev/null` through the host shim (process start, CUDA context, .msh load,
+    dictionary, kernels, D2H, and the text of every pair -- one line per pair as the reference prints them).  The sketches come from
+    `mash sketch -l list` over n_sketches small FASTA files.  Never raises: returns a dict with an "error" key instead."""
+    try:
+        mash = os.path.join(ROOT, "mash_b200", "host", "mash")
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        if not os.path.exists(mash) or base is None:
+            return None
+        with tempfile.TemporaryDirectory(dir=base) as d:
+            paths = []
+            for c0 in range(0, n_sketches, 1000):
+                seqs = host_genomes(min(1000, n_sketches - c0), contig_len, seed + c0)
+                sub = os.path.join(d, f"b{c0}")
+                os.mkdir(sub)
+                paths += write_fasta_files(seqs, sub)
+            lst = os.path.join(d, "list.txt")
+            with open(lst, "w") as f:
+                f.write("\n".join(paths) + "\n")
+            out = os.path.join(d, "x")
+            pr = subprocess.run([mash, "sketch", "-p", str(threads), "-o", out, "-l", lst], capture_output=True, text=True, timeout=300)
+            if pr.returncode != 0 or not os.path.exists(out + ".msh"):
+                return {"error": "sketch: " + (pr.stderr or "")[-300:]}
+            res = {}
+            for label, th in (("threads_1", 1), (f"threads_{threads}", threads)):
+                with open(os.devnull, "wb") as null:
+                    t0 = time.perf_counter()
+                    pr = subprocess.run([mash, "dist", "-p", str(th), out + ".msh", out + ".msh"], stdout=null, stderr=subprocess.PIPE, text=True, timeout=600)
+                    dt = time.perf_counter() - t0
+                if pr.returncode != 0:
+                    return {"error": "dist: " + (pr.stderr or "")[-300:]}
+                res[label] = {"seconds": dt, "pairs_per_s": n_sketches * n_sketches / dt}
+                if th == threads:
+                    break
+        res.update({"pairs": n_sketches * n_sketches, "unit": "pairs/s, wall clock of the whole process",
+                    "command": f"mash dist -p T x.msh x.msh > /dev/null  ({n_sketches} sketches, s=1000: one output line per pair, {n_sketches * n_sketches} lines)",
+                    "note": "process start, CUDA context, .msh load, dictionary, kernels, D2H and the formatting of every line (host/fastout.hpp) inside; "
+                            "the reference prints ~1e6 lines/s from one thread (cout << ... << endl per pair)"})
+        return res
+    except Exception as e:          # a side measurement must not take the bench line down
+        return {"error": repr(e)[:300]}
 
 
 def run_reference_arm(args):
@@ -1072,6 +1116,7 @@ def main():
         cpu.update(cpu_arms(cores))
         if not args.skip_cli:
             cpu["gpu_cli_file_to_msh"] = cli_sketch_rate(args.cli_files, glen, usable_cpus())
+            cpu["gpu_cli_dist"] = cli_dist_rate(args.cli_dist_sketches, 20000, usable_cpus())
 
     if rank == 0:
         line = {"metric": "Gbp_per_s_sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
