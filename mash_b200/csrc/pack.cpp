@@ -18,6 +18,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 
 #if defined(__x86_64__)
@@ -33,7 +34,17 @@ namespace {
 // packing at the rate the 1 GiB sketch waves reach), so small jobs -- screen chunks -- could not pay for themselves.
 class PackPool {
 public:
-    static PackPool &instance() { static PackPool *p = new PackPool; return *p; }       // never destroyed: workers may be parked at exit
+    // never destroyed: workers may be parked at exit.  A forked child has none of the parent's threads: it starts over with a new
+    // pool (the old object is leaked; its mutexes may have been held at the time of the fork).
+    static PackPool &instance()
+    {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            current() = new PackPool;
+            pthread_atfork(nullptr, nullptr, [] { current() = new PackPool; });
+        });
+        return *current();
+    }
     // `work` is run on `threads` threads in total, the caller included; it pulls its items from its own atomic counter
     void run(int threads, const std::function<void()> &work)
     {
@@ -56,6 +67,7 @@ public:
     }
 
 private:
+    static PackPool *&current() { static PackPool *p = nullptr; return p; }
     void loop(int id)
     {
         uint64_t seen = 0;

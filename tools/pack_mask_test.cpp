@@ -6,6 +6,8 @@
 #include <cstring>
 #include <random>
 #include <vector>
+#include <sys/wait.h>
+#include <unistd.h>
 using namespace mashgpu;
 int main()
 {
@@ -34,6 +36,19 @@ int main()
             }
             if (codes[groups] != 0x1234 || inval[groups] != 0x5678) { printf("overrun trial %d\n", trial); bad++; }
         }
+    }
+    {   // a forked child must be able to pack too (the pool's worker threads do not exist there)
+        fflush(stdout);
+        const pid_t pid = fork();
+        if (pid == 0) {
+            std::vector<uint8_t> src(3000000, 'C');
+            std::vector<uint64_t> codes(src.size() / 32 + 1); std::vector<uint32_t> inval(src.size() / 32 + 1);
+            pack_chunk_mask(src.data(), src.size(), 0, 5, codes.data(), inval.data());
+            _exit(codes[100] == 0x5555555555555555ull && inval[100] == 0 ? 0 : 3);
+        }
+        int status = 0;
+        waitpid(pid, &status, 0);
+        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) { printf("forked child failed (status %d)\n", status); bad++; }
     }
     printf("bad %d\n", bad);
     return bad != 0;
