@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "Sketch.h"
+#include <unistd.h>
+
 #include "fastout.hpp"
 #include "fastx.hpp"
 
@@ -730,12 +732,8 @@ int runImportJson(int argc, const char **argv)
 
 }  // namespace
 
-int main(int argc, const char **argv)
+static int runCommand(int argc, const char **argv)
 {
-    if (argc < 2) {
-        cerr << "usage: mash <sketch|dist|triangle|screen|info> ...   (B200 engine; see INTEGRATION.md)" << endl;
-        return 0;
-    }
     string cmd = argv[1];
     if (cmd == "sketch") return runSketch(argc - 2, argv + 2);
     if (cmd == "dist") return runDist(argc - 2, argv + 2);
@@ -746,4 +744,18 @@ int main(int argc, const char **argv)
     if (cmd == "import-json") return runImportJson(argc - 2, argv + 2);
     cerr << "ERROR: Unrecognized command: " << cmd << endl;
     return 1;
+}
+
+int main(int argc, const char **argv)
+{
+    if (argc < 2) {
+        cerr << "usage: mash <sketch|dist|triangle|screen|info> ...   (B200 engine; see INTEGRATION.md)" << endl;
+        return 0;
+    }
+    const int rc = runCommand(argc, argv);
+    // Everything the command wrote is closed or flushed here; leave without the static destructors and the CUDA runtime's
+    // teardown (unmapping gigabytes of device and pinned memory one allocation at a time): the driver reclaims it all at once.
+    cout.flush(); cerr.flush();
+    fflush(stdout); fflush(stderr);
+    _exit(rc);
 }
