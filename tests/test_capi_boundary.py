@@ -62,3 +62,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("# oracle-free", ""), os.path.join(dirpath, f)
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    # INTEGRATION.md section 5 lists the switches; a getenv() added to the sources without a line there fails here
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    used = set()
+    for sub in ("mash_b200/csrc", "mash_b200/host"):
+        d = os.path.join(root, sub)
+        for name in os.listdir(d):
+            if name.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                used.update(re.findall(r'getenv\("(MASH[A-Z_0-9]*)"\)', open(os.path.join(d, name), errors="replace").read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(v for v in used if v not in doc)
+    assert used and not missing, missing
